@@ -1,0 +1,268 @@
+"""Synthetic descriptor batches for the benchmark configs of SURVEY.md §8(d) and batches rebuilt from the
+reference's debug dumps (golden fixtures). Pure numpy input generation — no decode arithmetic lives here.
+
+Config 2: 44.1 kHz stereo, mixed 256/2048, one coupling step, P packets per stream.
+Config 3: 48 kHz 5.1, long blocks only, 2 submaps, 3 coupling steps [(0,2),(3,4),(0,1)].
+Config 4: 16 kHz mono speech clips, 100 packets per clip.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+
+# floor1 X lists of the two bundled fixtures (dump entries "floor1_unpack xs"; SURVEY.md §8 header):
+FIXTURE_XS_SHORT = [0, 128, 14, 4, 58, 2, 8, 28, 90]                       # multiplier 4, blocksize 256
+FIXTURE_XS_LONG = [0, 1024, 93, 23, 372, 6, 46, 186, 750, 14, 33, 65, 130, 260, 556, 3, 10, 18, 28, 39, 55,
+                   79, 111, 158, 220, 312, 464, 650, 850]                   # multiplier 2, blocksize 2048
+FLOOR_RANGE = {1: 256, 2: 128, 3: 86, 4: 64}
+
+
+def scaled_xs(xs: Sequence[int], half_from: int, half_to: int) -> List[int]:
+    """Rescale an X list made for n/2 = half_from to n/2 = half_to, keeping the values distinct."""
+    out = [0, half_to]
+    seen = {0, half_to}
+    for x in xs[2:]:
+        v = max(1, min(half_to - 1, (x * half_to) // half_from))
+        while v in seen:
+            v += 1
+        assert v < half_to
+        seen.add(v)
+        out.append(v)
+    return out
+
+
+def make_setup(channels: int, blocksizes=(256, 2048), sample_rate=44100,
+               couplings: Sequence[Tuple[int, int]] = (), mux: Optional[Sequence[int]] = None,
+               n_submaps: int = 1, multipliers=(4, 2)) -> abi.Setup:
+    """A setup with one floor per blocksize class (the fixtures' post lists, rescaled if needed), one mapping
+    per class (same channel routing) and two modes: mode 0 = short, mode 1 = long."""
+    bs0, bs1 = blocksizes
+    xs0 = FIXTURE_XS_SHORT if bs0 == 256 else scaled_xs(FIXTURE_XS_SHORT, 128, bs0 // 2)
+    xs1 = FIXTURE_XS_LONG if bs1 == 2048 else scaled_xs(FIXTURE_XS_LONG, 1024, bs1 // 2)
+    floors = [abi.Floor1(xs0, multipliers[0]), abi.Floor1(xs1, multipliers[1])]
+    mux = list(mux) if mux is not None else [0] * channels
+    mappings = [
+        abi.Mapping(mux=mux, submap_floor=[0] * n_submaps, submap_residue=[0] * n_submaps, couplings=list(couplings)),
+        abi.Mapping(mux=mux, submap_floor=[1] * n_submaps, submap_residue=[0] * n_submaps, couplings=list(couplings)),
+    ]
+    modes = [abi.Mode(0, 0), abi.Mode(1, 1)]
+    return abi.Setup(channels=channels, sample_rate=sample_rate, blocksize=(bs0, bs1), floors=floors,
+                     mappings=mappings, modes=modes)
+
+
+def block_sequence(P: int, rng: np.random.Generator, p_short: float = 0.05, long_only: bool = False) -> np.ndarray:
+    """Block flags (1 = long) of P packets: Markov chain, P(long->short) = p_short, short runs of 2..8."""
+    if long_only:
+        return np.ones(P, np.uint8)
+    flags = np.ones(P, np.uint8)
+    i = 0
+    while i < P:
+        if rng.random() < p_short:
+            run = int(rng.integers(2, 9))
+            flags[i:i + run] = 0
+            i += run
+        else:
+            i += 1
+    return flags
+
+
+@dataclass
+class StreamPlan:
+    """Per-packet geometry of one stream (all arrays length P)."""
+    blockflag: np.ndarray
+    n: np.ndarray            # blocksize per packet
+    window_flags: np.ndarray
+    emit: np.ndarray
+    pcm_off: np.ndarray
+    frames: int
+
+
+def plan_stream(blockflag: np.ndarray, blocksizes, trim_last: int = 0) -> StreamPlan:
+    bs = np.asarray(blocksizes, np.int64)
+    n = bs[blockflag.astype(np.int64)]
+    P = len(n)
+    prev_long = np.concatenate([[1], blockflag[:-1]]).astype(np.uint8)
+    next_long = np.concatenate([blockflag[1:], [1]]).astype(np.uint8)
+    wf = np.where(blockflag == 1, prev_long | (next_long << 1), 0).astype(np.uint8)
+    emit = np.zeros(P, np.int64)
+    emit[1:] = n[:-1] // 4 + n[1:] // 4
+    if trim_last and P > 1:
+        emit[-1] = max(0, emit[-1] - trim_last)
+    off = np.concatenate([[0], np.cumsum(emit)[:-1]])
+    return StreamPlan(blockflag.astype(np.uint8), n, wf, emit, off, int(emit.sum()))
+
+
+def gen_ys(rng: np.random.Generator, count: int, posts: int, rng_max: int) -> np.ndarray:
+    """Coded floor1 Y lists: ys[0:2] ~ U[0,range); ys[i>=2]: 35 % zero else geometric(0.15), clipped < range
+    (any coded value < range unwraps to a final Y inside [0,range), see hpp:536-557)."""
+    ys = np.minimum(rng.geometric(0.15, size=(count, posts)), rng_max - 1).astype(np.uint16)
+    ys[rng.random((count, posts)) < 0.35] = 0
+    ys[:, :2] = rng.integers(0, rng_max, size=(count, 2))
+    return ys
+
+
+def gen_spectra(rng: np.random.Generator, rows: int, half: int) -> np.ndarray:
+    """after_residue-like vectors: round(Laplace(0,1.5)) below 0.78*half, zero above."""
+    cut = int(0.78 * half)
+    out = np.zeros((rows, half), np.float32)
+    out[:, :cut] = np.round(rng.laplace(0.0, 1.5, size=(rows, cut))).astype(np.float32)
+    return out
+
+
+def build_dense_batch(setup: abi.Setup, plans: Sequence[StreamPlan], rng: np.random.Generator,
+                      p_unused: float = 0.01, setup_id: int = 0,
+                      pcm_layout: int = abi.POV_PCM_PLANAR) -> abi.Batch:
+    """Random dense-spectra batch for the given stream plans (all streams use `setup`)."""
+    C = setup.channels
+    S = len(plans)
+    P = sum(len(p.n) for p in plans)
+    packets = np.zeros(P, abi.PACKET_DTYPE)
+    streams = np.zeros(S, abi.STREAM_DTYPE)
+    posts = [len(setup.floors[setup.mappings[m.mapping].submap_floor[0]].xs) for m in setup.modes]
+    ranges = [FLOOR_RANGE[setup.floors[setup.mappings[m.mapping].submap_floor[0]].multiplier] for m in setup.modes]
+    first = 0
+    pcm_base = 0
+    bf_all = np.concatenate([p.blockflag for p in plans])
+    n_all = np.concatenate([p.n for p in plans])
+    for s, p in enumerate(plans):
+        k = len(p.n)
+        sl = slice(first, first + k)
+        packets["stream"][sl] = s
+        packets["mode"][sl] = p.blockflag       # mode 0 = short, mode 1 = long
+        packets["window_flags"][sl] = p.window_flags
+        packets["emit_frames"][sl] = p.emit
+        packets["pcm_off"][sl] = p.pcm_off
+        streams[s] = (setup_id, first, k, 0, p.frames, pcm_base)
+        pcm_base += p.frames * C
+        first += k
+    used = rng.random((P, C)) >= p_unused
+    packets["floor_used"] = (used.astype(np.uint16) << np.arange(C, dtype=np.uint16)).sum(1).astype(np.uint16)
+    # Y arena: only used channels carry a list
+    per_packet_posts = np.where(bf_all == 1, posts[1], posts[0]).astype(np.int64)
+    ys_count = used.sum(1) * per_packet_posts
+    packets["ys_off"] = np.concatenate([[0], np.cumsum(ys_count)[:-1]])
+    ys = np.zeros(int(ys_count.sum()), np.uint16)
+    for cls in (0, 1):
+        rows = np.nonzero(bf_all == cls)[0]
+        if len(rows) == 0:
+            continue
+        nrows = int(used[rows].sum())
+        vals = gen_ys(rng, nrows, posts[cls], ranges[cls])
+        # destination index of every (packet, used channel) list
+        starts = (packets["ys_off"][rows][:, None] + (np.cumsum(used[rows], 1) - used[rows]) * posts[cls])[used[rows]]
+        idx = (starts[:, None] + np.arange(posts[cls])[None, :]).ravel()
+        ys[idx] = vals.ravel()
+    # dense spectra arena
+    half_all = n_all // 2
+    spec_count = half_all * C
+    packets["spec_off"] = np.concatenate([[0], np.cumsum(spec_count)[:-1]])
+    spec = np.zeros(int(spec_count.sum()), np.float32)
+    for cls in (0, 1):
+        rows = np.nonzero(bf_all == cls)[0]
+        if len(rows) == 0:
+            continue
+        half = int(setup.blocksize[cls] // 2)
+        data = gen_spectra(rng, len(rows) * C, half)
+        idx = (packets["spec_off"][rows][:, None] + np.arange(C * half)[None, :]).ravel()
+        spec[idx] = data.ravel()
+    return abi.Batch(streams=streams, packets=packets, ys=ys, payload=spec, pcm_floats=pcm_base,
+                     input_kind=abi.POV_INPUT_DENSE, pcm_layout=pcm_layout)
+
+
+def replicate_batch(b: abi.Batch, times: int) -> abi.Batch:
+    """`times` copies of a batch as independent streams with their own arena regions (distinct HBM addresses)."""
+    S, P = len(b.streams), len(b.packets)
+    streams = np.tile(b.streams, times)
+    packets = np.tile(b.packets, times)
+    rep_s = np.repeat(np.arange(times, dtype=np.uint64), S)
+    rep_p = np.repeat(np.arange(times, dtype=np.uint64), P)
+    streams["first_packet"] += (rep_s * P).astype(np.uint32)
+    streams["pcm_base"] += rep_s * np.uint64(b.pcm_floats)
+    packets["stream"] += (rep_p * S).astype(np.uint32)
+    packets["ys_off"] += rep_p * np.uint64(len(b.ys))
+    packets["spec_off"] += rep_p * np.uint64(b.payload.size if b.input_kind == abi.POV_INPUT_DENSE else b.payload.nbytes)
+    return abi.Batch(streams=streams, packets=packets, ys=np.tile(b.ys, times), payload=np.tile(b.payload, times),
+                     pcm_floats=b.pcm_floats * times, input_kind=b.input_kind, pcm_layout=b.pcm_layout)
+
+
+# ---- the named configs ---------------------------------------------------------------------------------------
+def config2(P: int = 4096, streams: int = 1, seed: int = 0, distinct: int = 1):
+    """Synthetic 44.1 kHz stereo, mixed 256/2048 (BASELINE.json configs[1]). `distinct` independently generated
+    streams are replicated up to `streams` streams."""
+    rng = np.random.default_rng(seed)
+    setup = make_setup(2, (256, 2048), 44100, couplings=[(0, 1)])
+    plans = [plan_stream(block_sequence(P, rng), setup.blocksize) for _ in range(distinct)]
+    b = build_dense_batch(setup, plans, rng)
+    if streams > distinct:
+        b = replicate_batch(b, streams // distinct)
+    return setup, b
+
+
+def config3(P: int = 4096, streams: int = 1, seed: int = 1, distinct: int = 1):
+    """Synthetic 48 kHz 5.1, long blocks only, 2 submaps (LFE alone), 3 coupling steps; channel 0 is in two steps
+    to pin the reverse-order rule (hpp:1214)."""
+    rng = np.random.default_rng(seed)
+    setup = make_setup(6, (256, 2048), 48000, couplings=[(0, 2), (3, 4), (0, 1)], mux=[0, 0, 0, 0, 0, 1],
+                       n_submaps=2)
+    plans = [plan_stream(block_sequence(P, rng, long_only=True), setup.blocksize) for _ in range(distinct)]
+    b = build_dense_batch(setup, plans, rng)
+    if streams > distinct:
+        b = replicate_batch(b, streams // distinct)
+    return setup, b
+
+
+def config4(clips: int = 100, packets_per_clip: int = 100, seed: int = 2, blocksizes=(256, 2048), replicate: int = 1):
+    """16 kHz mono speech clips (returnn_import use case): `clips` independent streams of 100 packets."""
+    rng = np.random.default_rng(seed)
+    setup = make_setup(1, blocksizes, 16000)
+    plans = [plan_stream(block_sequence(packets_per_clip, rng), setup.blocksize) for _ in range(clips)]
+    b = build_dense_batch(setup, plans, rng)
+    if replicate > 1:
+        b = replicate_batch(b, replicate)
+    return setup, b
+
+
+# ---- batches rebuilt from the reference's own dump (golden fixtures) -------------------------------------------
+def golden_setup_and_batch(g: Dict[str, np.ndarray]) -> Tuple[abi.Setup, abi.Batch]:
+    """Dense batch equivalent to one bundled fixture: Y lists = dump "floor1 ys", spectra = dump "after_residue",
+    emit counts = lengths of the dump's "pcm" entries. Coupling: stereo fixture has one step (0,1)."""
+    C = int(g["channels"])
+    bs = sorted(set(int(x) for x in g["blocksize"]))
+    bs0, bs1 = bs[0], bs[-1]
+    floors = [abi.Floor1(list(g["floor_xs"][i, :g["floor_nposts"][i]]), int(g["floor_multipliers"][i]))
+              for i in range(len(g["floor_nposts"]))]
+    coupl = [(0, 1)] if C == 2 else []
+    mappings = [abi.Mapping([0] * C, [0], [0], coupl), abi.Mapping([0] * C, [1], [0], coupl)]
+    setup = abi.Setup(C, int(g["sample_rate"]), (bs0, bs1), floors, mappings, [abi.Mode(0, 0), abi.Mode(1, 1)])
+    n = g["blocksize"].astype(np.int64)
+    P = len(n)
+    blockflag = (n == bs1).astype(np.uint8)
+    plan = plan_stream(blockflag, (bs0, bs1))
+    emit = g["emit_frames"].astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(emit)[:-1]])
+    packets = np.zeros(P, abi.PACKET_DTYPE)
+    packets["mode"] = blockflag
+    packets["window_flags"] = plan.window_flags
+    packets["emit_frames"] = emit
+    packets["pcm_off"] = off
+    used = g["floor_used"]
+    packets["floor_used"] = (used.astype(np.uint16) << np.arange(C, dtype=np.uint16)).sum(1)
+    ys_list = []
+    yo = 0
+    for p in range(P):
+        packets["ys_off"][p] = yo
+        for c in range(C):
+            if used[p, c]:
+                k = int(g["floor_nposts"][g["floor_number"][p, c]])
+                ys_list.append(g["ys"][p, c, :k].astype(np.uint16))
+                yo += k
+    packets["spec_off"] = np.concatenate([[0], np.cumsum(n // 2 * C)[:-1]])
+    streams = np.zeros(1, abi.STREAM_DTYPE)
+    streams[0] = (0, 0, P, 0, int(emit.sum()), 0)
+    batch = abi.Batch(streams, packets, np.concatenate(ys_list), g["after_residue"].astype(np.float32),
+                      int(emit.sum()) * C)
+    return setup, batch
