@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""Benchmark of the B200-native Vorbis synthesis stage (BASELINE.json metric: decoded PCM samples/s).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU decoder on the host cores
+
+A *step* is one pass of the hot path (floor1 -> coupling -> floor multiply -> IMDCT -> window/overlap-add -> PCM,
+one fused kernel) over one batch of synthetic config-2 input (BASELINE.json configs[1]: 44.1 kHz stereo, 4096
+packets per stream, mixed 256/2048 blocks, one coupling step), replicated to --streams independent streams so
+that one step reads and writes far more than the 126 MB L2.
+
+`value`: inputs already resident in HBM, CUDA-event time on the library's stream, max over ranks.
+`e2e`:   the same step through the public API with HOST buffers: descriptor validation + H2D of every arena from
+         pinned memory + kernel + D2H of the PCM into pinned memory, all inside the timed region.
+Multi-GPU: streams are independent, so every rank decodes its own shard; no collective on the data path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decoded PCM samples/sec (IMDCT+floor+OLA)"
+UNIT = "samples/s"
+BYTES_PER_SAMPLE = 8.0  # 2n B spectrum in + 2n B PCM out per channel-packet = 8 B per PCM sample
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        self.gpu = gpu_index
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_like(arr):
+    import torch
+    t = torch.empty(arr.shape, dtype=getattr(torch, str(arr.dtype)) if arr.dtype.names is None else torch.uint8,
+                    pin_memory=True)
+    out = t.numpy()
+    out[...] = arr
+    return t, out
+
+
+def pin_batch(batch):
+    """Move a batch's host arenas into pinned memory (returns the tensors that own the storage)."""
+    import numpy as np
+    import torch
+    from parseoggvorbis_b200 import abi
+    keep = []
+
+    def pin_bytes(a):
+        a = np.ascontiguousarray(a)
+        t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+        v = t.numpy().view(a.dtype).reshape(a.shape)
+        v[...] = a
+        keep.append(t)
+        return v
+
+    pb = abi.Batch(pin_bytes(batch.streams), pin_bytes(batch.packets), pin_bytes(batch.ys), pin_bytes(batch.payload),
+                   batch.pcm_floats, batch.input_kind, batch.pcm_layout)
+    return pb, keep
+
+
+def cpu_baseline_port(setup, batch, n_streams_sample):
+    """Oracle port (oracle/synth_oracle.c) on the host cores, IMDCT = the reference's own mdct_backward when
+    oracle/_ref is present. One sub-batch of whole streams per thread."""
+    import numpy as np
+    from parseoggvorbis_b200 import abi
+    from tests import oracle_binding as ob
+    cores = os.cpu_count() or 1
+    S = min(n_streams_sample, len(batch.streams))
+    threads = max(1, min(cores, S))
+    kind = "reference" if ob.reference_lib() is not None else "fast"
+    ob.lib().por_inverse_db_table()
+    # split streams [0,S) into `threads` sub-batches (views of the same arenas)
+    subs = []
+    per = (S + threads - 1) // threads
+    for t in range(threads):
+        s0, s1 = t * per, min(S, (t + 1) * per)
+        if s0 >= s1:
+            break
+        st = batch.streams[s0:s1].copy()
+        p0 = int(st["first_packet"][0]); p1 = int(st["first_packet"][-1] + st["n_packets"][-1])
+        pk = batch.packets[p0:p1].copy()
+        pk["stream"] -= s0
+        st["first_packet"] -= p0
+        base = int(st["pcm_base"][0])
+        st["pcm_base"] -= base
+        st["setup_id"] = 0
+        floats = int((st["pcm_frames"] * setup.channels).sum())
+        subs.append(abi.Batch(st, pk, batch.ys, batch.payload, floats, batch.input_kind, batch.pcm_layout))
+    samples = sum(int(s.pcm_floats) for s in subs)
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=lambda b=b: ob.synth_batch([setup], b, imdct=kind)) for b in subs]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return {"value": samples / dt, "unit": UNIT, "cores": len(subs), "kind": "port",
+            "sample": "%d of the workload's streams (%d PCM samples) through oracle/synth_oracle.c, one stream "
+                      "group per thread, %s; %.2f s" % (S, samples, "IMDCT = reference mdct_backward (oracle/_ref)"
+                                                         if kind == "reference" else "IMDCT = oracle FFT", dt)}
+
+
+def run_reference_arm(args):
+    """The reference's own CPU decoder (oracle/_ref/ref_decode_bench around OggReader::full_read_from_memory,
+    src/ParseOggVorbis.hpp:1428) on all host cores. Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_decode_bench")
+    ogg = os.path.join(ROOT, "tests", "golden", "test.stereo44khz.ogg")
+    cores = os.cpu_count() or 1
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_decode_bench not built (make -C oracle ref)"}))
+        return 0
+    per_thread = max(1, args.ref_decodes)
+    times, samples = [], 0
+    for i in range(args.warmup + args.steps):
+        out = subprocess.check_output([exe, ogg, str(cores), str(per_thread)], text=True)
+        r = json.loads(out.strip().splitlines()[-1])
+        if i >= args.warmup:
+            times.append(r["seconds"]); samples = r["samples"]
+    total_t = sum(times)
+    value = samples * len(times) / total_t
+    sample = ("full reference decode (Ogg framing + Huffman + synthesis; the reference cannot run synthesis alone) of "
+              "tests/audio/test.stereo44khz.ogg (44.1 kHz stereo, 256/2048 blocks, 182272 samples) x %d decodes on %d "
+              "threads per step" % (cores * per_thread, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "bundled fixture replicated",
+            "config": {"workload": "config1-stream x%d (CPU reference arm)" % (cores * per_thread)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=128, help="independent config-2 streams per GPU per step")
+    ap.add_argument("--packets", type=int, default=4096, help="packets per stream")
+    ap.add_argument("--distinct", type=int, default=4, help="independently generated streams (rest are replicas)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-streams", type=int, default=0, help="streams of the CPU-baseline sample (0 = one per core)")
+    ap.add_argument("--ref-decodes", type=int, default=40, help="reference arm: decodes per thread per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    from parseoggvorbis_b200 import workloads
+    from parseoggvorbis_b200.lib import SynthContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- workload: config 2, replicated; every rank decodes its own shard of independent streams (weak scaling) ----
+    setup, batch = workloads.config2(P=args.packets, streams=args.streams, distinct=min(args.distinct, args.streams),
+                                     seed=rank)
+    samples_per_step = int(batch.pcm_floats)
+    ctx = SynthContext(local)
+    batch.streams["setup_id"] = ctx.register_setup(setup)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg ----
+    bh = ctx.upload(batch)
+    ctx.sync(bh)
+    for _ in range(args.warmup):
+        ctx.run(bh)
+    ctx.sync(bh)
+    status_bad = int(np.count_nonzero(ctx.status(bh)))
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            ctx.run(bh)
+        ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * samples_per_step * args.steps / (ms_max * 1e-3)
+    kernel_ms = ms / args.steps          # this rank's fused-kernel launch duration (one launch per step)
+
+    # correctness spot check of what was just timed (first stream vs the oracle) — outside the timed region
+    check = None
+    if rank == 0:
+        from tests import oracle_binding as ob
+        from parseoggvorbis_b200 import abi
+        st = batch.streams[:1].copy(); st["setup_id"] = 0
+        pk = batch.packets[:int(st["n_packets"][0])].copy()
+        sub = abi.Batch(st, pk, batch.ys, batch.payload, int(st["pcm_frames"][0]) * setup.channels)
+        ref, _ = ob.synth_batch([setup], sub, imdct="fast")
+        got = ctx.fetch_pcm(bh)[:sub.pcm_floats]
+        check = {"max_abs_err": float(np.abs(got - ref).max()), "snr_db": float(ob.snr_db(got, ref)),
+                 "packets_with_status": status_bad}
+
+    # ---- end-to-end leg: host buffers in, host PCM out, every step ----
+    e2e = None
+    if not args.no_e2e:
+        pb, keep = pin_batch(batch)
+        out_t = torch.empty(int(batch.pcm_floats), dtype=torch.float32, pin_memory=True)
+        out_np = out_t.numpy()
+        h2d = int(pb.streams.nbytes + pb.packets.nbytes + pb.ys.nbytes + pb.payload.nbytes + 8 * len(pb.packets))
+        d2h = int(out_np.nbytes)
+        def e2e_step():
+            ctx.upload(pb, reuse=bh)
+            ctx.run(bh)
+            ctx.fetch_pcm(bh, out=out_np, sync=True)
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        tt = torch.tensor([max(wall * 1e3, dev_ms)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * samples_per_step * args.e2e_steps / (float(tt.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "ms_per_step": float(tt.item()) / args.e2e_steps}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = samples_per_step * BYTES_PER_SAMPLE / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: synthetic 44.1 kHz stereo, %d packets/stream, mixed 256/2048 blocks, "
+                                   "1 coupling step, %d streams per GPU (%d distinct, seed=rank)" %
+                                   (args.packets, args.streams, min(args.distinct, args.streams)),
+                       "samples_per_step_per_gpu": samples_per_step,
+                       "l2_policy": "inputs+outputs per step (%.2f GB) far exceed the 126 MB L2; no flush needed" %
+                                    (samples_per_step * BYTES_PER_SAMPLE / 1e9),
+                       "parallelism": "independent streams sharded across ranks, no collective"},
+            "roofline": {"bound": "hbm", "kernel": "k_fused_synth", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": samples_per_step * BYTES_PER_SAMPLE,
+                         "kernel_ms": kernel_ms},
+            "gpu_launches": int(launches), "clocks": clocks, "check": check,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_port(setup, batch, args.cpu_streams or (os.cpu_count() or 1))
+        print(json.dumps(line))
+    bh.free()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -187,6 +187,9 @@ void*       pov_ctx_stream(pov_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench accounting). */
 uint64_t    pov_ctx_launch_count(const pov_ctx* ctx);
 
+/* The 256-entry floor1_inverse_dB_table this library uses (reference: src/inverse_db_table.h:13-78). Host only. */
+void        pov_inverse_db_table(float out[256]);
+
 /* Validate + upload one stream setup; derived tables (neighbours, sort order, windows, twiddles) are built here. */
 int         pov_setup_register(pov_ctx* ctx, const pov_setup* setup, uint32_t* setup_id_out);
 int         pov_setup_entry_bits(const pov_ctx* ctx, uint32_t setup_id); /* 16 or 32; <0 on bad id */

@@ -1,0 +1,680 @@
+// C-ABI implementation (include/pov_synth.h): contexts, setup registration, batch upload / run / fetch.
+// Host code only; the kernels are in kernels_staged.cu and kernel_fused.cu.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "api_internal.h"
+#include "host_tables.h"
+#include "kernels.h"
+
+using namespace pov;
+
+// ---------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------
+int pov_fail(pov_ctx* ctx, int code, const char* fmt, ...) {
+	if(ctx) {
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+		va_end(ap);
+	}
+	return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                                       \
+	do {                                                                                                          \
+		cudaError_t e__ = (expr);                                                                                 \
+		if(e__ != cudaSuccess)                                                                                    \
+			return pov_fail(ctx, POV_ERR_CUDA, "%s:%d: CUDA error: %s (%s)", __FILE__, __LINE__, cudaGetErrorString(e__), #expr); \
+	} while(0)
+
+template <class T>
+static cudaError_t dev_upload(T** dptr, const T* h, size_t count, cudaStream_t st) {
+	*dptr = nullptr;
+	if(count == 0) return cudaSuccess;
+	cudaError_t e = cudaMalloc((void**) dptr, count * sizeof(T));
+	if(e != cudaSuccess) return e;
+	return cudaMemcpyAsync(*dptr, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+static bool is_pow2_in(uint32_t v, uint32_t lo, uint32_t hi) { return v >= lo && v <= hi && (v & (v - 1)) == 0; }
+static uint32_t ilog2u(uint32_t v) { uint32_t r = 0; while(v > 1) { v >>= 1; ++r; } return r; }
+
+// growable device buffer
+cudaError_t DevBuf::reserve(size_t bytes) {
+	if(bytes <= cap) return cudaSuccess;
+	if(ptr) cudaFree(ptr);
+	ptr = nullptr; cap = 0;
+	size_t want = bytes + bytes / 8 + 256;
+	cudaError_t e = cudaMalloc(&ptr, want);
+	if(e == cudaSuccess) cap = want;
+	return e;
+}
+void DevBuf::release() { if(ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" uint32_t pov_abi_version(void) { return POV_ABI_VERSION; }
+extern "C" void pov_inverse_db_table(float out[256]) { make_inverse_db_table(out); }
+
+extern "C" int pov_ctx_create(int device, pov_ctx** out, const char** error_out) {
+	static thread_local char errbuf[256];
+	auto fail = [&](const char* msg, cudaError_t e) {
+		snprintf(errbuf, sizeof errbuf, "pov_ctx_create: %s: %s", msg, cudaGetErrorString(e));
+		if(error_out) *error_out = errbuf;
+		return (int) POV_ERR_CUDA;
+	};
+	if(!out) return POV_ERR_ARG;
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if(e != cudaSuccess || count == 0) return fail("no CUDA device (this library has no CPU fallback)", e);
+	if(device < 0 || device >= count) return fail("device ordinal out of range", cudaErrorInvalidDevice);
+	cudaDeviceProp prop;
+	if((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+	if(prop.major != 10) {
+		snprintf(errbuf, sizeof errbuf, "pov_ctx_create: device %d is sm_%d%d; this build holds sm_100a code only", device, prop.major, prop.minor);
+		if(error_out) *error_out = errbuf;
+		return POV_ERR_CUDA;
+	}
+	if((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+	std::unique_ptr<pov_ctx> ctx(new pov_ctx());
+	ctx->device = device;
+	ctx->sm_count = prop.multiProcessorCount;
+	if((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+	float table[256];
+	make_inverse_db_table(table);
+	if((e = dev_upload((float**) &ctx->d_inv_db, table, 256, ctx->stream)) != cudaSuccess) return fail("upload inverse dB table", e);
+	if((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("sync", e);
+	const char* rl = getenv("POV_RUN_LEN");
+	ctx->run_len = rl ? (uint32_t) std::max(2, atoi(rl)) : 0;
+	ctx->err[0] = 0;
+	*out = ctx.release();
+	return POV_OK;
+}
+
+static void free_setup(SetupRec& s) {
+	cudaFree((void*) s.d_floors); cudaFree((void*) s.d_mappings); cudaFree((void*) s.d_residues);
+	cudaFree((void*) s.d_codebooks); cudaFree((void*) s.d_vq);
+}
+
+extern "C" void pov_ctx_destroy(pov_ctx* ctx) {
+	if(!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for(auto& s : ctx->setups) free_setup(s);
+	for(auto& kv : ctx->blk_tables) { cudaFree((void*) kv.second.d_rot); cudaFree((void*) kv.second.d_fft); cudaFree((void*) kv.second.d_slope); }
+	cudaFree((void*) ctx->d_setups);
+	cudaFree((void*) ctx->d_inv_db);
+	ctx->mdct_in.release(); ctx->mdct_out.release();
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" const char* pov_last_error(const pov_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" void* pov_ctx_stream(pov_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
+extern "C" uint64_t pov_ctx_launch_count(const pov_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// per-blocksize tables shared by all setups of a context
+static int get_block_tables(pov_ctx* ctx, uint32_t n, BlockTables** out) {
+	auto it = ctx->blk_tables.find(n);
+	if(it != ctx->blk_tables.end()) { *out = &it->second; return POV_OK; }
+	BlockTables t;
+	std::vector<float> rot, fft, slope;
+	make_rotation(n, rot);
+	make_fft_twiddles(n, fft);
+	make_window_slope(n / 2, slope);
+	t.h_slope = slope;
+	CUDA_TRY(ctx, dev_upload((float**) &t.d_rot, rot.data(), rot.size(), ctx->stream));
+	CUDA_TRY(ctx, dev_upload((float**) &t.d_fft, fft.data(), fft.size(), ctx->stream));
+	CUDA_TRY(ctx, dev_upload((float**) &t.d_slope, slope.data(), slope.size(), ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	auto ins = ctx->blk_tables.emplace(n, std::move(t));
+	*out = &ins.first->second;
+	return POV_OK;
+}
+
+// canonical byte image of a setup (for de-duplication: a corpus of files typically shares a handful of setups)
+static void serialize_setup(const pov_setup* s, std::string& out) {
+	auto put = [&](const void* p, size_t n) { out.append((const char*) p, n); };
+	put(&s->channels, 4); put(&s->sample_rate, 4); put(s->blocksize, 8);
+	put(&s->n_codebooks, 4); put(&s->n_floors, 4); put(&s->n_residues, 4); put(&s->n_mappings, 4); put(&s->n_modes, 4);
+	for(uint32_t i = 0; i < s->n_codebooks; ++i) {
+		const pov_codebook& c = s->codebooks[i];
+		put(&c.dim, 4); put(&c.n_entries, 4); put(&c.lookup_type, 4);
+		if(c.lookup_type != 0 && c.vq) put(c.vq, sizeof(float) * (size_t) c.dim * c.n_entries);
+	}
+	for(uint32_t i = 0; i < s->n_floors; ++i) {
+		const pov_floor1& f = s->floors[i];
+		put(&f.n_posts, 2); put(&f.multiplier, 1); put(f.xs, 2 * (size_t) std::min<uint32_t>(f.n_posts, POV_MAX_POSTS));
+	}
+	for(uint32_t i = 0; i < s->n_residues; ++i) {
+		const pov_residue& r = s->residues[i];
+		put(&r.type, 4); put(&r.begin, 4); put(&r.end, 4); put(&r.partition_size, 4); put(&r.n_class, 4);
+		put(r.books, 8 * (size_t) std::min<uint32_t>(r.n_class, POV_MAX_CLASSES));
+	}
+	for(uint32_t i = 0; i < s->n_mappings; ++i) {
+		const pov_mapping& m = s->mappings[i];
+		put(&m.n_submaps, 4); put(&m.n_couplings, 4); put(m.mux, POV_MAX_CHANNELS);
+		put(m.submap_floor, POV_MAX_SUBMAPS); put(m.submap_residue, POV_MAX_SUBMAPS);
+		put(m.coupling_mag, std::min<uint32_t>(m.n_couplings, POV_MAX_COUPLINGS));
+		put(m.coupling_ang, std::min<uint32_t>(m.n_couplings, POV_MAX_COUPLINGS));
+	}
+	for(uint32_t i = 0; i < s->n_modes; ++i) { put(&s->modes[i].blockflag, 1); put(&s->modes[i].mapping, 1); }
+}
+
+extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id_out) {
+	if(!ctx || !s || !id_out) return POV_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	if(s->abi_version != POV_ABI_VERSION) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: abi_version %u != %u", s->abi_version, POV_ABI_VERSION);
+	if(s->channels < 1) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: channels == 0 (hpp:774)");
+	if(s->channels > POV_MAX_CHANNELS) return pov_fail(ctx, POV_ERR_UNSUPPORTED, "pov_setup: %u channels > %u supported by this build", s->channels, POV_MAX_CHANNELS);
+	if(!is_pow2_in(s->blocksize[0], 64, 8192) || !is_pow2_in(s->blocksize[1], 64, 8192) || s->blocksize[0] > s->blocksize[1])
+		return pov_fail(ctx, POV_ERR_ARG, "pov_setup: blocksizes %u/%u invalid (hpp:1295-1298)", s->blocksize[0], s->blocksize[1]);
+	if(s->n_modes < 1 || s->n_modes > POV_MAX_MODES || !s->modes) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: n_modes out of range (hpp:950)");
+	if(s->n_mappings < 1 || !s->mappings || s->n_floors < 1 || !s->floors) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: needs >= 1 mapping and floor");
+	if(s->n_codebooks > POV_MAX_CODEBOOKS) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: > 256 codebooks (hpp:905)");
+	if(s->n_floors > 64 || s->n_residues > 64 || s->n_mappings > 64) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: > 64 floors/residues/mappings (hpp:923-941)");
+
+	std::string image;
+	serialize_setup(s, image);
+	for(size_t i = 0; i < ctx->setups.size(); ++i)
+		if(ctx->setups[i].image == image) { *id_out = (uint32_t) i; return POV_OK; }
+
+	SetupRec rec;
+	rec.channels = s->channels; rec.sample_rate = s->sample_rate;
+	rec.blocksize[0] = s->blocksize[0]; rec.blocksize[1] = s->blocksize[1];
+	DevSetup& d = rec.dev;
+	memset(&d, 0, sizeof d);
+	d.channels = s->channels;
+	d.blocksize[0] = s->blocksize[0]; d.blocksize[1] = s->blocksize[1];
+	d.log2bs[0] = ilog2u(s->blocksize[0]); d.log2bs[1] = ilog2u(s->blocksize[1]);
+	d.n_floors = s->n_floors; d.n_mappings = s->n_mappings; d.n_modes = s->n_modes;
+	d.n_residues = s->n_residues; d.n_codebooks = s->n_codebooks;
+
+	// codebooks
+	std::vector<DevCodebook> cbs(s->n_codebooks);
+	std::vector<float> vq_all;
+	std::vector<size_t> vq_off(s->n_codebooks, 0);
+	uint32_t max_entries = 0;
+	for(uint32_t i = 0; i < s->n_codebooks; ++i) {
+		const pov_codebook& c = s->codebooks[i];
+		if(c.dim < 1 || c.n_entries < 1) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: codebook %u has dim/entries == 0 (hpp:257,259)", i);
+		if(c.lookup_type > 2) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: codebook %u lookup_type %u (hpp:299)", i, c.lookup_type);
+		if(c.lookup_type != 0 && !c.vq) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: codebook %u has no VQ table", i);
+		cbs[i].dim = c.dim; cbs[i].n_entries = c.n_entries; cbs[i].lookup_type = c.lookup_type; cbs[i].pad = 0; cbs[i].vq = nullptr;
+		max_entries = std::max(max_entries, c.n_entries);
+		if(c.lookup_type != 0) {
+			vq_off[i] = vq_all.size();
+			vq_all.insert(vq_all.end(), c.vq, c.vq + (size_t) c.dim * c.n_entries);
+		}
+	}
+	d.entry_bits = (max_entries > 65536) ? 32 : 16;
+	rec.entry_bits = d.entry_bits;
+	// floors
+	std::vector<DevFloor> floors(s->n_floors);
+	uint32_t max_posts = 2;
+	for(uint32_t i = 0; i < s->n_floors; ++i) {
+		std::string msg;
+		if(!make_floor_tables(s->floors[i], floors[i], msg)) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: floor %u: %s", i, msg.c_str());
+		max_posts = std::max<uint32_t>(max_posts, floors[i].n_posts);
+	}
+	rec.max_posts = max_posts;
+	// residues
+	std::vector<DevResidue> residues(s->n_residues);
+	uint32_t max_res_smem = 0;
+	for(uint32_t i = 0; i < s->n_residues; ++i) {
+		const pov_residue& r = s->residues[i];
+		if(r.type > 2) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: residue %u type %u (hpp:634)", i, r.type);
+		if(r.begin > r.end) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: residue %u begin > end (hpp:638)", i);
+		if(r.partition_size < 1 || r.n_class < 1 || r.n_class > POV_MAX_CLASSES) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: residue %u partition/class out of range", i);
+		DevResidue& o = residues[i];
+		o.type = r.type; o.begin = r.begin; o.end = r.end; o.partition_size = r.partition_size; o.n_class = r.n_class;
+		memset(o.books, POV_NO_BOOK, sizeof o.books);
+		for(uint32_t k = 0; k < r.n_class * 8; ++k) {
+			const uint8_t bk = r.books[k];
+			o.books[k] = bk;
+			if(bk == POV_NO_BOOK) continue;
+			if(bk >= s->n_codebooks) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: residue %u references codebook %u of %u", i, bk, s->n_codebooks);
+			const uint32_t dim = s->codebooks[bk].dim;
+			if(r.partition_size % dim) return pov_fail(ctx, POV_ERR_UNSUPPORTED, "pov_setup: residue %u: codebook %u dim %u does not divide partition size %u", i, bk, dim, r.partition_size);
+		}
+		const uint32_t vlen = s->channels * (s->blocksize[1] / 2);
+		const uint32_t parts = vlen / r.partition_size + 1;
+		max_res_smem = std::max<uint32_t>(max_res_smem, vlen * 4 + 8 * parts * s->channels * 4 + 64);
+	}
+	rec.res_smem = max_res_smem;
+	// mappings
+	std::vector<DevMapping> maps(s->n_mappings);
+	for(uint32_t i = 0; i < s->n_mappings; ++i) {
+		const pov_mapping& m = s->mappings[i];
+		DevMapping& o = maps[i];
+		memset(&o, 0, sizeof o);
+		if(m.n_submaps < 1 || m.n_submaps > POV_MAX_SUBMAPS) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: mapping %u: n_submaps %u (hpp:781)", i, m.n_submaps);
+		if(m.n_couplings > POV_MAX_COUPLINGS) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: mapping %u: n_couplings %u (hpp:783)", i, m.n_couplings);
+		o.n_submaps = m.n_submaps; o.n_couplings = m.n_couplings;
+		for(uint32_t k = 0; k < m.n_submaps; ++k) {
+			if(m.submap_floor[k] >= s->n_floors) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: mapping %u submap %u floor out of range (hpp:807)", i, k);
+			if(s->n_residues && m.submap_residue[k] >= s->n_residues) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: mapping %u submap %u residue out of range (hpp:809)", i, k);
+			o.submap_residue[k] = m.submap_residue[k];
+		}
+		for(uint32_t c = 0; c < s->channels; ++c) {
+			if(m.mux[c] >= m.n_submaps) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: mapping %u mux[%u] out of range (hpp:799)", i, c);
+			o.mux[c] = m.mux[c];
+			o.floor_of_ch[c] = m.submap_floor[m.mux[c]];
+		}
+		for(uint32_t k = 0; k < m.n_couplings; ++k) {
+			const uint8_t mg = m.coupling_mag[k], an = m.coupling_ang[k];
+			if(mg == an || mg >= s->channels || an >= s->channels) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: mapping %u coupling %u invalid (hpp:788-790)", i, k);
+			o.coupling_mag[k] = mg; o.coupling_ang[k] = an;
+		}
+	}
+	for(uint32_t i = 0; i < s->n_modes; ++i) {
+		if(s->modes[i].mapping >= s->n_mappings) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: mode %u mapping out of range (hpp:832)", i);
+		d.mode_blockflag[i] = s->modes[i].blockflag ? 1 : 0;
+		d.mode_mapping[i] = s->modes[i].mapping;
+	}
+	rec.n_modes = s->n_modes;
+	memcpy(rec.mode_blockflag, d.mode_blockflag, sizeof rec.mode_blockflag);
+	memcpy(rec.mode_mapping, d.mode_mapping, sizeof rec.mode_mapping);
+	rec.floors_host = floors;
+	rec.maps_host = maps;
+	rec.residues_host = residues;
+	rec.cb_dim.resize(s->n_codebooks);
+	for(uint32_t i = 0; i < s->n_codebooks; ++i) rec.cb_dim[i] = s->codebooks[i].dim;
+
+	// device copies
+	BlockTables *t0 = nullptr, *t1 = nullptr;
+	int rc;
+	if((rc = get_block_tables(ctx, s->blocksize[0], &t0)) != POV_OK) return rc;
+	if((rc = get_block_tables(ctx, s->blocksize[1], &t1)) != POV_OK) return rc;
+	d.slope[0] = t0->d_slope; d.slope[1] = t1->d_slope;
+	d.rot[0] = t0->d_rot; d.rot[1] = t1->d_rot;
+	d.fft[0] = t0->d_fft; d.fft[1] = t1->d_fft;
+	CUDA_TRY(ctx, dev_upload((float**) &rec.d_vq, vq_all.data(), vq_all.size(), ctx->stream));
+	for(uint32_t i = 0; i < s->n_codebooks; ++i)
+		if(cbs[i].lookup_type != 0) cbs[i].vq = rec.d_vq + vq_off[i];
+	CUDA_TRY(ctx, dev_upload((DevCodebook**) &rec.d_codebooks, cbs.data(), cbs.size(), ctx->stream));
+	CUDA_TRY(ctx, dev_upload((DevFloor**) &rec.d_floors, floors.data(), floors.size(), ctx->stream));
+	CUDA_TRY(ctx, dev_upload((DevResidue**) &rec.d_residues, residues.data(), residues.size(), ctx->stream));
+	CUDA_TRY(ctx, dev_upload((DevMapping**) &rec.d_mappings, maps.data(), maps.size(), ctx->stream));
+	d.floors = rec.d_floors; d.mappings = rec.d_mappings; d.residues = rec.d_residues; d.codebooks = rec.d_codebooks;
+	rec.image.swap(image);
+	ctx->setups.push_back(std::move(rec));
+
+	// the device array of DevSetup is rebuilt (kernels index it by setup id)
+	std::vector<DevSetup> all(ctx->setups.size());
+	for(size_t i = 0; i < all.size(); ++i) all[i] = ctx->setups[i].dev;
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	if(ctx->d_setups) cudaFree((void*) ctx->d_setups);
+	CUDA_TRY(ctx, dev_upload((DevSetup**) &ctx->d_setups, all.data(), all.size(), ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	*id_out = (uint32_t) (ctx->setups.size() - 1);
+	return POV_OK;
+}
+
+extern "C" int pov_setup_entry_bits(const pov_ctx* ctx, uint32_t id) {
+	if(!ctx || id >= ctx->setups.size()) return -1;
+	return (int) ctx->setups[id].entry_bits;
+}
+
+extern "C" int pov_setup_get_window(const pov_ctx* ctx, uint32_t id, int blockflag, int prev, int next, float* out, uint32_t n) {
+	if(!ctx || id >= ctx->setups.size() || !out) return POV_ERR_ARG;
+	const SetupRec& s = ctx->setups[id];
+	std::vector<float> w;
+	make_window(s.blocksize[0], s.blocksize[1], blockflag, prev, next, w);
+	if(w.size() != n) return POV_ERR_ARG;
+	memcpy(out, w.data(), n * sizeof(float));
+	return POV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// batches
+// ---------------------------------------------------------------------------------------------------------------
+static void release_batch(pov_batch_handle* h) {
+	h->d_streams.release(); h->d_packets.release(); h->d_ys.release(); h->d_payload.release(); h->d_spec_off.release();
+	h->d_stage_off.release(); h->d_runs.release(); h->d_pcm.release(); h->d_status.release(); h->d_spectra.release();
+	h->st_final_ys.release(); h->st_flag.release(); h->st_floor.release(); h->st_floor_out.release();
+	h->st_env.release(); h->st_mdct.release();
+}
+
+extern "C" void pov_batch_free(pov_ctx* ctx, pov_batch_handle* h) {
+	if(!h) return;
+	if(ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+	release_batch(h);
+	delete h;
+}
+
+extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_handle** out) {
+	if(!ctx || !b || !out) return POV_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	if(b->input_kind > POV_INPUT_ENTRIES || b->pcm_layout > POV_PCM_INTERLEAVED) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: bad input_kind/pcm_layout");
+	if((b->n_streams && !b->streams) || (b->n_packets && !b->packets)) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: null arrays");
+	if(b->input_kind == POV_INPUT_DENSE && ((uintptr_t) b->payload & 3)) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: dense payload must be 4-byte aligned");
+
+	std::unique_ptr<pov_batch_handle> fresh;
+	pov_batch_handle* h = *out;
+	if(!h) { fresh.reset(new pov_batch_handle()); h = fresh.get(); }
+	h->n_streams = b->n_streams; h->n_packets = b->n_packets;
+	h->input_kind = b->input_kind; h->pcm_layout = b->pcm_layout; h->pcm_floats = b->pcm_floats;
+	h->staged_ready = false;
+
+	// ---- validation + derived arrays (one pass over the packets) ----
+	const uint32_t P = b->n_packets;
+	h->spec_off.resize(P); h->stage_off.resize(P); h->pk_n.resize(P); h->pk_setup.resize(P);
+	h->runs.clear();
+	uint32_t maxC = 1, maxbs = 64, minbs = 8192, maxposts = 2, res_smem = 0;
+	uint64_t dense_floats = 0, stage_floats = 0, expect_first = 0;
+	const uint64_t payload_floats = b->payload_bytes / 4;
+	uint32_t run_len = ctx->run_len;
+	if(run_len == 0) {
+		// aim for >= ~8 CTAs per SM when the batch is big enough, keep the halo overhead <= 1/run_len
+		const uint64_t want_runs = (uint64_t) ctx->sm_count * 8;
+		run_len = (uint32_t) std::min<uint64_t>(32, std::max<uint64_t>(8, P / std::max<uint64_t>(1, want_runs)));
+	}
+	for(uint32_t si = 0; si < b->n_streams; ++si) {
+		const pov_stream& st = b->streams[si];
+		if(st.setup_id >= ctx->setups.size()) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: stream %u: unknown setup %u", si, st.setup_id);
+		if(st.first_packet != expect_first || (uint64_t) st.first_packet + st.n_packets > P)
+			return pov_fail(ctx, POV_ERR_ARG, "pov_batch: stream %u: packets must tile the packet array in stream order", si);
+		expect_first += st.n_packets;
+		const SetupRec& su = ctx->setups[st.setup_id];
+		const uint32_t C = su.channels;
+		if(st.pcm_base + st.pcm_frames * C > b->pcm_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: stream %u: PCM region exceeds pcm_floats", si);
+		maxC = std::max(maxC, C); maxbs = std::max(maxbs, su.blocksize[1]); minbs = std::min(minbs, su.blocksize[0]);
+		maxposts = std::max(maxposts, su.max_posts); res_smem = std::max(res_smem, su.res_smem);
+		uint32_t n_prev = 0;
+		for(uint32_t k = 0; k < st.n_packets; ++k) {
+			const uint32_t p = st.first_packet + k;
+			const pov_packet& pk = b->packets[p];
+			if(pk.stream != si) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: stream field %u != %u", p, pk.stream, si);
+			if(pk.mode >= su.n_modes) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: mode %u out of range (hpp:1146)", p, pk.mode);
+			const uint32_t flag = su.mode_blockflag[pk.mode];
+			const uint32_t n = su.blocksize[flag];
+			if(pk.floor_used >> C) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: floor_used has bits beyond %u channels", p, C);
+			const uint32_t max_emit = k ? n_prev / 4 + n / 4 : 0;
+			if(pk.emit_frames > max_emit) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: emit_frames %u > %u (hpp:1026)", p, pk.emit_frames, max_emit);
+			if(pk.pcm_off + pk.emit_frames > st.pcm_frames) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: PCM chunk outside the stream's %llu frames", p, (unsigned long long) st.pcm_frames);
+			// Y lists
+			const DevMapping& mp = su.maps_host[su.mode_mapping[pk.mode]];
+			uint64_t ny = 0;
+			for(uint32_t c = 0; c < C; ++c)
+				if((pk.floor_used >> c) & 1) ny += su.floors_host[mp.floor_of_ch[c]].n_posts;
+			if(pk.ys_off + ny > b->n_ys) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: Y lists outside the Y arena", p);
+			if(b->input_kind == POV_INPUT_DENSE) {
+				if(pk.spec_off & 3) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: spec_off must be a multiple of 4 floats (16-byte TMA source)", p);
+				if(pk.spec_off + (uint64_t) C * (n / 2) > payload_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: spectra outside the payload arena", p);
+				h->spec_off[p] = pk.spec_off;
+			} else {
+				if((pk.spec_off & 3) || pk.spec_off + 4 > b->payload_bytes) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload offset invalid", p);
+				if(su.residues_host.empty()) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: setup has no residues", p);
+				h->spec_off[p] = dense_floats;
+				dense_floats += (uint64_t) C * (n / 2);
+			}
+			h->stage_off[p] = stage_floats;
+			stage_floats += (uint64_t) C * n;
+			h->pk_n[p] = n; h->pk_setup[p] = st.setup_id;
+			n_prev = n;
+		}
+		// runs of <= run_len packets, each later run re-transforming one halo packet
+		for(uint32_t k = 0; k < st.n_packets; k += run_len) {
+			DevRun r;
+			r.halo = k ? 1u : 0u;
+			r.first_packet = st.first_packet + k - r.halo;
+			r.n_packets = std::min(run_len, st.n_packets - k) + r.halo;
+			r.pad = 0;
+			h->runs.push_back(r);
+		}
+	}
+	if(expect_first != P) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: %u packets not covered by the stream table", (uint32_t) (P - expect_first));
+	if(b->input_kind == POV_INPUT_ENTRIES) {
+		// walk the payload headers on the host so that a malformed offset cannot send the kernel out of bounds
+		for(uint32_t p = 0; p < P; ++p) {
+			const SetupRec& su = ctx->setups[h->pk_setup[p]];
+			const pov_packet& pk = b->packets[p];
+			const DevMapping& mp = su.maps_host[su.mode_mapping[pk.mode]];
+			uint64_t off = pk.spec_off;
+			const uint32_t half = h->pk_n[p] / 2;
+			for(uint32_t s = 0; s < mp.n_submaps; ++s) {
+				uint32_t nch = 0;
+				for(uint32_t c = 0; c < su.channels; ++c) nch += (mp.mux[c] == s);
+				const DevResidue& rs = su.residues_host[mp.submap_residue[s]];
+				const uint32_t vch = rs.type == 2 ? 1 : nch, vlen = rs.type == 2 ? nch * half : half;
+				const uint32_t lb = std::min(rs.begin, vlen), le = std::min(rs.end, vlen);
+				const uint32_t parts = (le - lb) / rs.partition_size;
+				if(off + 4 > b->payload_bytes) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload truncated", p);
+				uint32_t ne;
+				memcpy(&ne, (const uint8_t*) b->payload + off, 4);
+				off += 4 + (((uint64_t) vch * parts + 3) & ~3ull) + (((uint64_t) ne * (su.entry_bits / 8) + 3) & ~3ull);
+				if(off > b->payload_bytes) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload truncated", p);
+			}
+		}
+	}
+	h->max_channels = maxC; h->max_blocksize = maxbs; h->min_blocksize = std::min(minbs, maxbs);
+	h->floor_cap = (maxposts + 3u) & ~3u;
+	h->res_smem = res_smem;
+	h->stage_floats = stage_floats;
+	h->dense_floats = dense_floats;
+	h->fused_ok = fused_smem_bytes(maxC, maxbs, h->floor_cap) <= 227 * 1024;
+
+	// ---- device copies ----
+	cudaStream_t st = ctx->stream;
+	auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> cudaError_t {
+		cudaError_t e = buf.reserve(std::max<size_t>(bytes, 16));
+		if(e != cudaSuccess || bytes == 0) return e;
+		return cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, st);
+	};
+	CUDA_TRY(ctx, up(h->d_streams, b->streams, sizeof(pov_stream) * b->n_streams));
+	CUDA_TRY(ctx, up(h->d_packets, b->packets, sizeof(pov_packet) * P));
+	CUDA_TRY(ctx, up(h->d_ys, b->ys, sizeof(uint16_t) * b->n_ys));
+	CUDA_TRY(ctx, up(h->d_payload, b->payload, b->payload_bytes));
+	CUDA_TRY(ctx, up(h->d_spec_off, h->spec_off.data(), sizeof(uint64_t) * P));
+	CUDA_TRY(ctx, up(h->d_runs, h->runs.data(), sizeof(DevRun) * h->runs.size()));
+	CUDA_TRY(ctx, h->d_pcm.reserve(std::max<size_t>(sizeof(float) * b->pcm_floats, 16)));
+	CUDA_TRY(ctx, h->d_status.reserve(std::max<size_t>(sizeof(uint32_t) * P, 16)));
+	CUDA_TRY(ctx, cudaMemsetAsync(h->d_status.ptr, 0, sizeof(uint32_t) * P, st));
+	if(b->input_kind == POV_INPUT_ENTRIES) CUDA_TRY(ctx, h->d_spectra.reserve(std::max<size_t>(sizeof(float) * dense_floats, 16)));
+	if(fresh) *out = fresh.release();
+	return POV_OK;
+}
+
+static DevBatchView make_view(pov_ctx* ctx, pov_batch_handle* h) {
+	DevBatchView v;
+	v.setups = ctx->d_setups;
+	v.streams = (const pov_stream*) h->d_streams.ptr;
+	v.packets = (const pov_packet*) h->d_packets.ptr;
+	v.ys = (const uint16_t*) h->d_ys.ptr;
+	v.spec_off = (const uint64_t*) h->d_spec_off.ptr;
+	if(h->input_kind == POV_INPUT_DENSE) { v.spectra = (const float*) h->d_payload.ptr; v.payload = nullptr; }
+	else { v.spectra = (const float*) h->d_spectra.ptr; v.payload = (const uint8_t*) h->d_payload.ptr; }
+	v.inv_db = ctx->d_inv_db;
+	v.pcm = (float*) h->d_pcm.ptr;
+	v.status = (uint32_t*) h->d_status.ptr;
+	v.n_streams = h->n_streams; v.n_packets = h->n_packets; v.pcm_layout = h->pcm_layout;
+	return v;
+}
+
+static int run_residue_if_needed(pov_ctx* ctx, pov_batch_handle* h, const DevBatchView& v) {
+	if(h->input_kind != POV_INPUT_ENTRIES) return POV_OK;
+	CUDA_TRY(ctx, launch_residue_apply(v, (float*) h->d_spectra.ptr, h->res_smem, ctx->stream, &ctx->launches));
+	return POV_OK;
+}
+
+static int prepare_stage_buffers(pov_ctx* ctx, pov_batch_handle* h, DevStageBuffers& sb) {
+	const size_t cps = (size_t) h->n_packets * h->max_channels;
+	CUDA_TRY(ctx, h->d_stage_off.reserve(std::max<size_t>(sizeof(uint64_t) * h->n_packets, 16)));
+	CUDA_TRY(ctx, cudaMemcpyAsync(h->d_stage_off.ptr, h->stage_off.data(), sizeof(uint64_t) * h->n_packets, cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(ctx, h->st_final_ys.reserve(std::max<size_t>(cps * POV_MAX_POSTS * 4, 16)));
+	CUDA_TRY(ctx, h->st_flag.reserve(std::max<size_t>(cps * POV_MAX_POSTS, 16)));
+	CUDA_TRY(ctx, h->st_floor.reserve(std::max<size_t>(h->stage_floats * 2, 16)));
+	CUDA_TRY(ctx, h->st_floor_out.reserve(std::max<size_t>(h->stage_floats * 4, 16)));
+	CUDA_TRY(ctx, h->st_env.reserve(std::max<size_t>(h->stage_floats * 2, 16)));
+	CUDA_TRY(ctx, h->st_mdct.reserve(std::max<size_t>(h->stage_floats * 4, 16)));
+	CUDA_TRY(ctx, cudaMemsetAsync(h->st_final_ys.ptr, 0, cps * POV_MAX_POSTS * 4, ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(h->st_flag.ptr, 0, cps * POV_MAX_POSTS, ctx->stream));
+	sb.stage_off = (const uint64_t*) h->d_stage_off.ptr;
+	sb.final_ys = (uint32_t*) h->st_final_ys.ptr;
+	sb.step2_flag = (uint8_t*) h->st_flag.ptr;
+	sb.floor = (uint16_t*) h->st_floor.ptr;
+	sb.floor_outputs = (float*) h->st_floor_out.ptr;
+	sb.after_envelope = (float*) h->st_env.ptr;
+	sb.pcm_after_mdct = (float*) h->st_mdct.ptr;
+	return POV_OK;
+}
+
+extern "C" int pov_batch_run_staged(pov_ctx* ctx, pov_batch_handle* h) {
+	if(!ctx || !h) return POV_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	DevBatchView v = make_view(ctx, h);
+	int rc = run_residue_if_needed(ctx, h, v);
+	if(rc) return rc;
+	DevStageBuffers sb;
+	if((rc = prepare_stage_buffers(ctx, h, sb)) != POV_OK) return rc;
+	CUDA_TRY(ctx, launch_staged(v, sb, h->max_channels, ctx->stream, &ctx->launches));
+	h->staged_ready = true;
+	return POV_OK;
+}
+
+extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
+	if(!ctx || !h) return POV_ERR_ARG;
+	if(!h->fused_ok) return pov_batch_run_staged(ctx, h);   // working set beyond one SM's shared memory: staged kernels
+	cudaSetDevice(ctx->device);
+	DevBatchView v = make_view(ctx, h);
+	int rc = run_residue_if_needed(ctx, h, v);
+	if(rc) return rc;
+	CUDA_TRY(ctx, launch_fused(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), h->max_channels, h->max_blocksize,
+	                           h->min_blocksize, h->floor_cap, ctx->stream, &ctx->launches));
+	return POV_OK;
+}
+
+extern "C" int pov_batch_sync(pov_ctx* ctx, pov_batch_handle* h) {
+	if(!ctx || !h) return POV_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return POV_OK;
+}
+
+extern "C" int pov_batch_fetch_pcm(pov_ctx* ctx, pov_batch_handle* h, float* out, uint64_t n_floats, int sync) {
+	if(!ctx || !h || (!out && n_floats)) return POV_ERR_ARG;
+	if(n_floats > h->pcm_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_pcm: %llu floats requested, arena holds %llu", (unsigned long long) n_floats, (unsigned long long) h->pcm_floats);
+	cudaSetDevice(ctx->device);
+	if(n_floats) CUDA_TRY(ctx, cudaMemcpyAsync(out, h->d_pcm.ptr, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	if(sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return POV_OK;
+}
+
+extern "C" void* pov_batch_pcm_dev(pov_batch_handle* h) { return h ? h->d_pcm.ptr : nullptr; }
+
+extern "C" int pov_batch_status(pov_ctx* ctx, pov_batch_handle* h, uint32_t* out, uint32_t n) {
+	if(!ctx || !h) return POV_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	std::vector<uint32_t> tmp(h->n_packets);
+	CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), h->d_status.ptr, sizeof(uint32_t) * h->n_packets, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	if(out) memcpy(out, tmp.data(), sizeof(uint32_t) * std::min<uint32_t>(n, h->n_packets));
+	for(uint32_t p = 0; p < h->n_packets; ++p) {
+		if(!tmp[p]) continue;
+		const char* what = (tmp[p] & POV_PKT_FLOOR_PREDICTED) ? "predicted <= range (hpp:536)"
+		                 : (tmp[p] & POV_PKT_FLOOR_RANGE)     ? "floor[i] < 256 (hpp:587)"
+		                                                      : "temp.size() > 0 (hpp:739,748: VQ entry out of range)";
+		return pov_fail(ctx, POV_ERR_STREAM, "audio packet %u: check failed: %s", p, what);
+	}
+	return POV_OK;
+}
+
+extern "C" int pov_batch_fetch_stage(pov_ctx* ctx, pov_batch_handle* h, uint32_t packet, uint32_t channel, int stage,
+                                     void* out, uint64_t out_bytes) {
+	if(!ctx || !h || !out) return POV_ERR_ARG;
+	if(packet >= h->n_packets) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_stage: packet out of range");
+	const SetupRec& su = ctx->setups[h->pk_setup[packet]];
+	if(channel >= su.channels) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_stage: channel out of range");
+	if(stage != POV_STAGE_AFTER_RESIDUE && !h->staged_ready) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_stage: run pov_batch_run_staged first");
+	cudaSetDevice(ctx->device);
+	const uint32_t n = h->pk_n[packet];
+	const uint64_t so = h->stage_off[packet];
+	const uint64_t slot = ((uint64_t) packet * h->max_channels + channel) * POV_MAX_POSTS;
+	const void* src = nullptr;
+	uint64_t bytes = 0;
+	std::vector<uint16_t> tmp16;
+	switch(stage) {
+		case POV_STAGE_FINAL_YS: src = (const uint32_t*) h->st_final_ys.ptr + slot; bytes = out_bytes; if(bytes > POV_MAX_POSTS * 4) bytes = 0; break;
+		case POV_STAGE_STEP2_FLAG: src = (const uint8_t*) h->st_flag.ptr + slot; bytes = out_bytes; if(bytes > POV_MAX_POSTS) bytes = 0; break;
+		case POV_STAGE_FLOOR: {
+			if(out_bytes != (uint64_t) n * 4) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_stage: size mismatch");
+			tmp16.resize(n);
+			CUDA_TRY(ctx, cudaMemcpyAsync(tmp16.data(), (const uint16_t*) h->st_floor.ptr + so + (uint64_t) channel * n, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+			for(uint32_t i = 0; i < n; ++i) ((uint32_t*) out)[i] = tmp16[i];
+			return POV_OK;
+		}
+		case POV_STAGE_FLOOR_OUTPUTS: src = (const float*) h->st_floor_out.ptr + so + (uint64_t) channel * n; bytes = (uint64_t) n * 4; break;
+		case POV_STAGE_AFTER_RESIDUE: {
+			const float* base = (h->input_kind == POV_INPUT_DENSE) ? (const float*) h->d_payload.ptr : (const float*) h->d_spectra.ptr;
+			src = base + h->spec_off[packet] + (uint64_t) channel * (n / 2); bytes = (uint64_t) n * 2; break;
+		}
+		case POV_STAGE_AFTER_ENVELOPE: src = (const float*) h->st_env.ptr + so / 2 + (uint64_t) channel * (n / 2); bytes = (uint64_t) n * 2; break;
+		case POV_STAGE_PCM_AFTER_MDCT: src = (const float*) h->st_mdct.ptr + so + (uint64_t) channel * n; bytes = (uint64_t) n * 4; break;
+		default: return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_stage: unknown stage %d", stage);
+	}
+	if(bytes == 0 || bytes != out_bytes) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_stage: size mismatch (%llu vs %llu)", (unsigned long long) out_bytes, (unsigned long long) bytes);
+	CUDA_TRY(ctx, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return POV_OK;
+}
+
+// bulk access for the dump writer: whole stage arrays in one copy
+int pov_batch_fetch_stage_all(pov_ctx* ctx, pov_batch_handle* h, StageHost& out) {
+	if(!h->staged_ready) return pov_fail(ctx, POV_ERR_ARG, "staged path has not run");
+	cudaSetDevice(ctx->device);
+	const size_t cps = (size_t) h->n_packets * h->max_channels;
+	out.final_ys.resize(cps * POV_MAX_POSTS); out.step2.resize(cps * POV_MAX_POSTS);
+	out.floor.resize(h->stage_floats); out.floor_out.resize(h->stage_floats);
+	out.env.resize(h->stage_floats / 2); out.mdct.resize(h->stage_floats);
+	const uint64_t res_floats = (h->input_kind == POV_INPUT_DENSE) ? h->d_payload.cap / 4 : h->dense_floats;
+	(void) res_floats;
+	cudaStream_t st = ctx->stream;
+	CUDA_TRY(ctx, cudaMemcpyAsync(out.final_ys.data(), h->st_final_ys.ptr, out.final_ys.size() * 4, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(out.step2.data(), h->st_flag.ptr, out.step2.size(), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(out.floor.data(), h->st_floor.ptr, out.floor.size() * 2, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(out.floor_out.data(), h->st_floor_out.ptr, out.floor_out.size() * 4, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(out.env.data(), h->st_env.ptr, out.env.size() * 4, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(out.mdct.data(), h->st_mdct.ptr, out.mdct.size() * 4, cudaMemcpyDeviceToHost, st));
+	if(h->input_kind == POV_INPUT_ENTRIES) {
+		out.residue.resize(h->dense_floats);
+		CUDA_TRY(ctx, cudaMemcpyAsync(out.residue.data(), h->d_spectra.ptr, out.residue.size() * 4, cudaMemcpyDeviceToHost, st));
+	}
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return POV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// drop-in for mdct_backward (src/mdct.h:105)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int pov_mdct_backward_batch(pov_ctx* ctx, uint32_t n, uint64_t count, const float* in, float* out) {
+	if(!ctx || (count && (!in || !out))) return POV_ERR_ARG;
+	if(!is_pow2_in(n, 64, 8192)) return pov_fail(ctx, POV_ERR_ARG, "pov_mdct_backward_batch: n = %u is not a power of two in 64..8192 (hpp:1295)", n);
+	if(count > 0x7fffffffull) return pov_fail(ctx, POV_ERR_ARG, "pov_mdct_backward_batch: count too large for one call");
+	cudaSetDevice(ctx->device);
+	BlockTables* t = nullptr;
+	int rc = get_block_tables(ctx, n, &t);
+	if(rc) return rc;
+	if(count == 0) return POV_OK;
+	CUDA_TRY(ctx, ctx->mdct_in.reserve(count * (n / 2) * sizeof(float)));
+	CUDA_TRY(ctx, ctx->mdct_out.reserve(count * n * sizeof(float)));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->mdct_in.ptr, in, count * (n / 2) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(ctx, launch_mdct_backward(nullptr, n, count, (const float*) ctx->mdct_in.ptr, (float*) ctx->mdct_out.ptr, t->d_rot, t->d_fft, ctx->stream, &ctx->launches));
+	CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->mdct_out.ptr, count * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return POV_OK;
+}

@@ -1,0 +1,82 @@
+// Host-side state behind the opaque handles of include/pov_synth.h.
+#ifndef POV_API_INTERNAL_H
+#define POV_API_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pov_internal.h"
+
+struct DevBuf {
+	void* ptr = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t bytes);
+	void release();
+};
+
+struct BlockTables {              // per blocksize n: DCT-IV rotation, FFT twiddles, rising slope of n/2 samples
+	const float2* d_rot = nullptr;
+	const float2* d_fft = nullptr;
+	const float*  d_slope = nullptr;
+	std::vector<float> h_slope;
+};
+
+struct SetupRec {
+	uint32_t channels = 0, sample_rate = 0, blocksize[2] = {0, 0};
+	uint32_t n_modes = 0, entry_bits = 16, max_posts = 2, res_smem = 0;
+	uint8_t mode_blockflag[POV_MAX_MODES] = {0};
+	uint8_t mode_mapping[POV_MAX_MODES] = {0};
+	std::vector<DevFloor> floors_host;
+	std::vector<DevMapping> maps_host;
+	std::vector<DevResidue> residues_host;
+	std::vector<uint32_t> cb_dim;
+	DevSetup dev;
+	const DevFloor* d_floors = nullptr;
+	const DevMapping* d_mappings = nullptr;
+	const DevResidue* d_residues = nullptr;
+	const DevCodebook* d_codebooks = nullptr;
+	const float* d_vq = nullptr;
+	std::string image;            // canonical bytes, for de-duplication
+};
+
+struct pov_ctx {
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	uint64_t launches = 0;
+	uint32_t run_len = 0;         // 0 = automatic
+	const float* d_inv_db = nullptr;
+	const DevSetup* d_setups = nullptr;
+	std::vector<SetupRec> setups;
+	std::map<uint32_t, BlockTables> blk_tables;
+	DevBuf mdct_in, mdct_out;
+	char err[512] = {0};
+};
+
+struct pov_batch_handle {
+	uint32_t n_streams = 0, n_packets = 0, input_kind = 0, pcm_layout = 0;
+	uint64_t pcm_floats = 0, stage_floats = 0, dense_floats = 0;
+	uint32_t max_channels = 1, max_blocksize = 64, min_blocksize = 64, floor_cap = 4, res_smem = 0;
+	bool fused_ok = true, staged_ready = false;
+	std::vector<uint64_t> spec_off, stage_off;
+	std::vector<uint32_t> pk_n, pk_setup;
+	std::vector<DevRun> runs;
+	DevBuf d_streams, d_packets, d_ys, d_payload, d_spec_off, d_stage_off, d_runs, d_pcm, d_status, d_spectra;
+	DevBuf st_final_ys, st_flag, st_floor, st_floor_out, st_env, st_mdct;
+};
+
+struct StageHost {                // whole stage arrays on the host (debug dump writer)
+	std::vector<uint32_t> final_ys;
+	std::vector<uint8_t> step2;
+	std::vector<uint16_t> floor;
+	std::vector<float> floor_out, env, mdct, residue;
+};
+
+int pov_fail(pov_ctx* ctx, int code, const char* fmt, ...);
+int pov_batch_fetch_stage_all(pov_ctx* ctx, pov_batch_handle* h, StageHost& out);
+
+#endif

@@ -1,0 +1,115 @@
+// Host-side table generation for libpov_synth.so. Every table is derived from the Vorbis I definitions the
+// reference implements; citations are relative to the reference root.
+#include "host_tables.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace pov {
+
+// src/inverse_db_table.h:13-78 holds the 256 literals of Vorbis I spec 10.1. The spec table is
+// fromdB((i-255)*0.546875), fromdB(x) = exp(x*0.11512925), printed with 8 significant digits; the float nearest
+// to that 8-digit decimal is what every decoder compiles in. Generating it the same way is bit-identical to the
+// reference's literals (pinned by tests/test_abi.py::test_inverse_db_table_matches_reference_golden).
+void make_inverse_db_table(float out[256]) {
+	for(int i = 0; i < 256; ++i) {
+		char buf[64];
+		const double v = exp((double) (i - 255) * 0.546875 * 0.11512925);
+		snprintf(buf, sizeof buf, "%.7e", v);
+		out[i] = strtof(buf, nullptr);
+	}
+}
+
+// src/ParseOggVorbis.hpp:850-853: x is rounded to float, products are formed in double, sinf takes the float
+// conversion of the double argument. The falling slope (hpp:856-859) evaluates the same expression at the
+// mirrored index, so only the rising slope is stored.
+void make_window_slope(uint32_t len, std::vector<float>& out) {
+	out.resize(len);
+	for(uint32_t i = 0; i < len; ++i) {
+		const float x = sinf((float) (M_PI_2 * ((int) i + 0.5) / (int) len));
+		out[i] = sinf((float) (M_PI_2 * x * x));
+	}
+}
+
+void make_window(uint32_t bs0, uint32_t bs1, int blockflag, int prev, int next, std::vector<float>& out) {
+	const uint32_t n = blockflag ? bs1 : bs0;
+	if(!blockflag) prev = next = 0;                    // hpp:876: flags matter for long blocks only
+	const uint32_t left = (prev ? bs1 : bs0) / 2, right = (next ? bs1 : bs0) / 2;
+	const uint32_t lb = n / 4 - left / 2, rb = n - n / 4 - right / 2;
+	std::vector<float> sl, sr;
+	make_window_slope(left, sl);
+	make_window_slope(right, sr);
+	out.assign(n, 0.f);
+	for(uint32_t i = 0; i < left; ++i) out[lb + i] = sl[i];
+	for(uint32_t i = lb + left; i < rb; ++i) out[i] = 1.f;
+	for(uint32_t i = 0; i < right; ++i) out[rb + i] = sr[right - 1 - i];
+}
+
+void make_rotation(uint32_t n, std::vector<float>& out) {
+	const uint32_t M = n / 2, Q = n / 4;
+	out.resize(2 * (size_t) Q);
+	for(uint32_t j = 0; j < Q; ++j) {
+		const double a = -M_PI * (8.0 * j + 1.0) / (8.0 * M);
+		out[2 * j] = (float) cos(a);
+		out[2 * j + 1] = (float) sin(a);
+	}
+}
+
+void make_fft_twiddles(uint32_t n, std::vector<float>& out) {
+	const uint32_t Q = n / 4;
+	out.resize(2 * (size_t) Q);
+	for(uint32_t e = 0; e < Q; ++e) {
+		const double a = -2.0 * M_PI * e / Q;
+		out[2 * e] = (float) cos(a);
+		out[2 * e + 1] = (float) sin(a);
+	}
+}
+
+// Neighbours (src/Utils.hpp:60-118) depend on the X list only, so they are found once here instead of once per
+// packet and post as in the reference (hpp:532-533). level[] orders the posts so that a post's two neighbours
+// are final before it is unwrapped; sorted_idx is the ascending-x order of hpp:458-469.
+bool make_floor_tables(const pov_floor1& in, DevFloor& out, std::string& msg) {
+	memset(&out, 0, sizeof out);
+	const int posts = in.n_posts;
+	if(posts < 2 || posts > (int) POV_MAX_POSTS) { msg = "floor1: n_posts out of range"; return false; }
+	if(in.multiplier < 1 || in.multiplier > 4) { msg = "floor1: multiplier out of range (hpp:491)"; return false; }
+	if(in.xs[0] != 0) { msg = "floor1: xs[0] must be 0 (hpp:449)"; return false; }
+	for(int i = 2; i < posts; ++i)
+		if(in.xs[i] == 0 || in.xs[i] >= in.xs[1]) { msg = "floor1: xs[i] outside (0, xs[1]) (hpp:450,455)"; return false; }
+	{
+		std::vector<uint16_t> s(in.xs, in.xs + posts);
+		std::sort(s.begin(), s.end());
+		if(std::adjacent_find(s.begin(), s.end()) != s.end()) { msg = "floor1: duplicate X values (Utils.hpp:145 asserts x0 < x1)"; return false; }
+	}
+	static const uint32_t ranges[4] = {256, 128, 86, 64};
+	out.n_posts = (uint16_t) posts;
+	out.multiplier = in.multiplier;
+	out.range = ranges[in.multiplier - 1];
+	int maxlevel = 0;
+	for(int i = 0; i < posts; ++i) {
+		out.xs[i] = in.xs[i];
+		if(i < 2) { out.level[i] = 0; continue; }
+		int lo = -1, hi = -1;
+		for(int j = 0; j < i; ++j) {
+			if(in.xs[j] < in.xs[i] && (lo < 0 || in.xs[j] > in.xs[lo])) lo = j;
+			if(in.xs[j] > in.xs[i] && (hi < 0 || in.xs[j] < in.xs[hi])) hi = j;
+		}
+		out.lo[i] = (uint8_t) lo;
+		out.hi[i] = (uint8_t) hi;
+		const int lv = 1 + std::max<int>(out.level[lo], out.level[hi]);
+		out.level[i] = (uint8_t) lv;
+		maxlevel = std::max(maxlevel, lv);
+	}
+	out.n_levels = (uint8_t) (maxlevel + 1);
+	std::vector<int> order(posts);
+	for(int i = 0; i < posts; ++i) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return in.xs[a] < in.xs[b]; });
+	for(int i = 0; i < posts; ++i) out.sorted_idx[i] = (uint8_t) order[i];
+	return true;
+}
+
+}  // namespace pov

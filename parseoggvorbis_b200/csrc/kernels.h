@@ -1,0 +1,47 @@
+// Launchers of the CUDA kernels (kernels_staged.cu, kernel_fused.cu). All pointers are device pointers.
+#ifndef POV_KERNELS_H
+#define POV_KERNELS_H
+
+#include <cuda_runtime.h>
+#include "pov_internal.h"
+
+namespace pov {
+
+struct DevBatchView {
+	const DevSetup*   setups;        // [n_setups]
+	const pov_stream* streams;       // [n_streams]
+	const pov_packet* packets;       // [n_packets]
+	const uint16_t*   ys;
+	const float*      spectra;       // dense after_residue vectors (input arena, or output of the residue kernel)
+	const uint64_t*   spec_off;      // per packet: float offset of its [C][n/2] block inside `spectra`
+	const uint8_t*    payload;       // residue payload arena (POV_INPUT_ENTRIES) or nullptr
+	const float*      inv_db;        // floor1_inverse_dB_table[256] (src/inverse_db_table.h:13-78), device copy
+	float*            pcm;
+	uint32_t*         status;        // [n_packets]
+	uint32_t n_streams, n_packets, pcm_layout;
+};
+
+// Staged (debug) path: every intermediate is materialised.
+struct DevStageBuffers {
+	const uint64_t* stage_off;   // per packet: float offset of its [C][n] block in the n-sized stage arrays
+	uint32_t* final_ys;          // [n_packets*C][POV_MAX_POSTS]
+	uint8_t*  step2_flag;        // [n_packets*C][POV_MAX_POSTS]
+	uint16_t* floor;             // n-sized
+	float*    floor_outputs;     // n-sized
+	float*    after_envelope;    // n/2-sized (offset stage_off/2)
+	float*    pcm_after_mdct;    // n-sized
+};
+
+cudaError_t launch_residue_apply(const DevBatchView& b, float* spectra_out, size_t smem_bytes, cudaStream_t st,
+                                 uint64_t* launches);
+cudaError_t launch_staged(const DevBatchView& b, const DevStageBuffers& sb, uint32_t max_channels, cudaStream_t st,
+                          uint64_t* launches);
+cudaError_t launch_fused(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t max_channels,
+                         uint32_t max_blocksize, uint32_t min_blocksize, uint32_t floor_cap, cudaStream_t st,
+                         uint64_t* launches);
+size_t fused_smem_bytes(uint32_t max_channels, uint32_t max_blocksize, uint32_t floor_cap);
+cudaError_t launch_mdct_backward(const DevSetup* dummy, uint32_t n, uint64_t count, const float* in, float* out,
+                                 const float2* rot, const float2* fft, cudaStream_t st, uint64_t* launches);
+
+}  // namespace pov
+#endif

@@ -1,0 +1,74 @@
+// Internal structures shared by the host side and the kernels of libpov_synth.so.
+// Device-side tables are flat PODs built once per setup by pov_setup_register (host_tables.cpp).
+#ifndef POV_INTERNAL_H
+#define POV_INTERNAL_H
+
+#include <stdint.h>
+#include "../../include/pov_synth.h"
+
+#define POV_MAX_CODEBOOKS 256
+
+// floor1 tables derived from the setup's X list (reference: hpp:458-469 sort, Utils.hpp:60-118 neighbours).
+struct DevFloor {
+	uint16_t n_posts;
+	uint8_t  multiplier;
+	uint8_t  n_levels;                 // depth of the neighbour dependency DAG (+1)
+	uint32_t range;                    // hpp:486-492
+	uint16_t xs[POV_MAX_POSTS];        // bitstream order
+	uint8_t  lo[POV_MAX_POSTS];        // low_neighbor index (posts >= 2)
+	uint8_t  hi[POV_MAX_POSTS];        // high_neighbor index
+	uint8_t  level[POV_MAX_POSTS];     // 0 for posts 0,1; else 1+max(level[lo],level[hi])
+	uint8_t  sorted_idx[POV_MAX_POSTS];// ascending-x order -> post index
+};
+
+struct DevMapping {
+	uint32_t n_submaps;
+	uint32_t n_couplings;
+	uint8_t  mux[POV_MAX_CHANNELS];
+	uint8_t  floor_of_ch[POV_MAX_CHANNELS];   // submap_floor[mux[c]]
+	uint8_t  submap_residue[POV_MAX_SUBMAPS];
+	uint8_t  coupling_mag[POV_MAX_COUPLINGS];
+	uint8_t  coupling_ang[POV_MAX_COUPLINGS];
+};
+
+struct DevResidue {
+	uint32_t type, begin, end, partition_size, n_class;
+	uint8_t  books[POV_MAX_CLASSES * 8];
+};
+
+struct DevCodebook {
+	uint32_t dim, n_entries, lookup_type, pad;
+	const float* vq;                   // device pointer
+};
+
+struct DevSetup {
+	uint32_t channels;
+	uint32_t blocksize[2];
+	uint32_t log2bs[2];
+	uint32_t n_floors, n_mappings, n_modes, n_residues, n_codebooks;
+	uint32_t entry_bits;               // 16 or 32
+	uint8_t  mode_blockflag[POV_MAX_MODES];
+	uint8_t  mode_mapping[POV_MAX_MODES];
+	const DevFloor*    floors;         // device arrays
+	const DevMapping*  mappings;
+	const DevResidue*  residues;
+	const DevCodebook* codebooks;
+	// Rising window slope of length blocksize[k]/2 (hpp:850-853); the falling slope is its mirror image
+	// (same argument expression, hpp:857) and everything else of a window is exactly 0 or 1.
+	const float*  slope[2];
+	// DCT-IV twiddles w[j] = exp(-i*pi*(8j+1)/(8M)), j < M/2, M = blocksize/2  (pre- and post-rotation)
+	const float2* rot[2];
+	// FFT twiddles W_Q^e = exp(-2*pi*i*e/Q), e < Q, Q = blocksize/4
+	const float2* fft[2];
+};
+
+// Work item of the fused kernel: a run of consecutive packets of one stream. The first packet of a run that is
+// not the first packet of its stream is a halo: it is transformed again only to rebuild the overlap half.
+struct DevRun {
+	uint32_t first_packet;             // global packet index where processing starts (halo included)
+	uint32_t n_packets;                // packets processed, halo included
+	uint32_t halo;                     // 1 -> first processed packet emits nothing here
+	uint32_t pad;
+};
+
+#endif

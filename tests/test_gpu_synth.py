@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden dumps and the pinned oracle.
+
+Tolerances (BASELINE.json north_star): floor1 integer stages, after_residue, after_envelope bit-exact;
+pcm_after_mdct and PCM max-abs <= 1e-5 and SNR >= 120 dB.
+"""
+import numpy as np
+import pytest
+
+from parseoggvorbis_b200 import abi, workloads
+from tests import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+TOL_ABS = 1e-5
+TOL_SNR = 120.0
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from parseoggvorbis_b200.lib import SynthContext
+    c = SynthContext(0)
+    yield c
+    c.close()
+
+
+def _assert_float_parity(test, ref, what):
+    test = np.asarray(test)
+    ref = np.asarray(ref)
+    assert test.shape == ref.shape, what
+    d = float(np.abs(test - ref).max()) if test.size else 0.0
+    assert d <= TOL_ABS, (what, d)
+    if np.any(ref):
+        s = ob.snr_db(test, ref)
+        assert s >= TOL_SNR, (what, s)
+
+
+def _iter_cp(g):
+    off_half = off_full = 0
+    C = int(g["channels"])
+    for p, n in enumerate(g["blocksize"]):
+        n = int(n)
+        for c in range(C):
+            yield p, c, n, off_half, off_full
+            off_half += n // 2
+            off_full += n
+
+
+@pytest.mark.parametrize("name", ["stereo44khz", "mono44khz"])
+def test_golden_staged_every_stage(ctx, golden, name):
+    """Config 1 (device part): every intermediate the reference dumps, from the same ys + after_residue."""
+    g = golden[name]
+    setup, batch = workloads.golden_setup_and_batch(g)
+    sid = ctx.register_setup(setup)
+    batch.streams["setup_id"] = sid
+    bh = ctx.upload(batch)
+    ctx.run_staged(bh)
+    pcm = ctx.fetch_pcm(bh).reshape(setup.channels, -1)
+    assert not ctx.status(bh).any()
+    table = np.load(__import__("os").path.join(ob.ROOT, "tests", "golden", "inverse_db_table.npy"))
+    for p, c, n, oh, of in _iter_cp(g):
+        env = ctx.fetch_stage(bh, p, c, abi.POV_STAGE_AFTER_ENVELOPE, n // 2)
+        assert np.array_equal(env, g["after_envelope"][oh:oh + n // 2]), (p, c)
+        if p % 7 == 0 or n == 256:
+            mdct = ctx.fetch_stage(bh, p, c, abi.POV_STAGE_PCM_AFTER_MDCT, n)
+            _assert_float_parity(mdct, g["pcm_after_mdct"][of:of + n], ("pcm_after_mdct", p, c))
+        if g["floor_used"][p, c]:
+            k = int(g["floor_nposts"][g["floor_number"][p, c]])
+            assert np.array_equal(ctx.fetch_stage(bh, p, c, abi.POV_STAGE_FINAL_YS, k), g["final_ys"][p, c, :k]), (p, c)
+            assert np.array_equal(ctx.fetch_stage(bh, p, c, abi.POV_STAGE_STEP2_FLAG, k).astype(bool), g["step2_flag"][p, c, :k])
+            fl = ctx.fetch_stage(bh, p, c, abi.POV_STAGE_FLOOR, n)
+            assert np.array_equal(fl, g["floor"][of:of + n]), (p, c)
+            fo = ctx.fetch_stage(bh, p, c, abi.POV_STAGE_FLOOR_OUTPUTS, n)
+            assert np.array_equal(fo.view(np.uint32), table[g["floor"][of:of + n]].view(np.uint32))
+    _assert_float_parity(pcm, g["pcm"], "pcm")
+    bh.free()
+
+
+@pytest.mark.parametrize("name", ["stereo44khz", "mono44khz"])
+def test_golden_fused_pcm(ctx, golden, name):
+    g = golden[name]
+    setup, batch = workloads.golden_setup_and_batch(g)
+    batch.streams["setup_id"] = ctx.register_setup(setup)
+    bh = ctx.upload(batch)
+    ctx.run(bh)
+    fused = ctx.fetch_pcm(bh).reshape(setup.channels, -1)
+    assert not ctx.status(bh).any()
+    _assert_float_parity(fused, g["pcm"], "pcm")
+    ctx.run_staged(bh)
+    staged = ctx.fetch_pcm(bh).reshape(setup.channels, -1)
+    assert np.array_equal(fused, staged)      # same arithmetic, different kernels
+    bh.free()
+
+
+def _check_against_oracle(ctx, setup, batch, stages=False):
+    batch.streams["setup_id"] = ctx.register_setup(setup)
+    bh = ctx.upload(batch)
+    ctx.run(bh)
+    fused = ctx.fetch_pcm(bh)
+    st = ctx.status(bh)
+    sid = batch.streams["setup_id"].copy()
+    batch.streams["setup_id"] = 0
+    if stages:
+        ref, rst, cap = ob.synth_batch([setup], batch, imdct="fast", capture=True)
+    else:
+        ref, rst = ob.synth_batch([setup], batch, imdct="fast")
+    batch.streams["setup_id"] = sid
+    assert np.array_equal(st, rst)
+    _assert_float_parity(fused, ref, "pcm vs oracle")
+    if stages:
+        ctx.run_staged(bh)
+        staged = ctx.fetch_pcm(bh)
+        assert np.array_equal(staged, fused)
+        C = setup.channels
+        n_of = np.asarray(setup.blocksize)[batch.packets["mode"].astype(int)]   # mode 0 short / 1 long in workloads
+        for p in range(0, len(batch.packets), max(1, len(batch.packets) // 40)):
+            n = int(n_of[p])
+            for c in range(C):
+                env = ctx.fetch_stage(bh, p, c, abi.POV_STAGE_AFTER_ENVELOPE, n // 2)
+                assert np.array_equal(env, cap["after_envelope"][p, c, :n // 2]), (p, c)
+                mdct = ctx.fetch_stage(bh, p, c, abi.POV_STAGE_PCM_AFTER_MDCT, n)
+                _assert_float_parity(mdct, cap["pcm_after_mdct"][p, c, :n], ("mdct", p, c))
+    bh.free()
+    return fused
+
+
+def test_config2_stereo_mixed_blocks(ctx):
+    setup, batch = workloads.config2(P=600, streams=3, distinct=3, seed=0)
+    _check_against_oracle(ctx, setup, batch, stages=True)
+
+
+def test_config3_5_1_coupling_order(ctx):
+    setup, batch = workloads.config3(P=200, streams=2, distinct=2, seed=1)
+    _check_against_oracle(ctx, setup, batch, stages=True)
+
+
+@pytest.mark.parametrize("bs", [(256, 2048), (512, 1024), (64, 8192), (128, 128), (1024, 4096)])
+def test_config4_mono_clips_blocksizes(ctx, bs):
+    setup, batch = workloads.config4(clips=12, packets_per_clip=40, blocksizes=bs)
+    _check_against_oracle(ctx, setup, batch, stages=(bs == (512, 1024)))
+
+
+def test_interleaved_layout(ctx):
+    setup, planar = workloads.config2(P=120, seed=4)
+    rng = np.random.default_rng(4)
+    plans = [workloads.plan_stream(planar.packets["mode"].copy(), setup.blocksize)]
+    inter = workloads.build_dense_batch(setup, plans, rng, pcm_layout=abi.POV_PCM_INTERLEAVED)
+    sid = ctx.register_setup(setup)
+    inter.streams["setup_id"] = sid
+    bh = ctx.upload(inter)
+    ctx.run(bh)
+    a = ctx.fetch_pcm(bh).reshape(-1, setup.channels)
+    inter.pcm_layout = abi.POV_PCM_PLANAR
+    bh2 = ctx.upload(inter)
+    ctx.run(bh2)
+    b = ctx.fetch_pcm(bh2).reshape(setup.channels, -1)
+    assert np.array_equal(a.T, b)
+    bh.free(); bh2.free()
+
+
+def test_run_length_independence(ctx, monkeypatch):
+    """Halo re-computation: PCM must not depend on how a stream is cut into runs (trimmed last packet included)."""
+    setup, _ = workloads.config2(P=8)
+    rng = np.random.default_rng(11)
+    plan = workloads.plan_stream(workloads.block_sequence(300, rng), setup.blocksize, trim_last=100)
+    batch = workloads.build_dense_batch(setup, [plan], rng)
+    out = _check_against_oracle(ctx, setup, batch)
+    from parseoggvorbis_b200.lib import SynthContext
+    for rl in ("2", "5", "64"):
+        monkeypatch.setenv("POV_RUN_LEN", rl)
+        c2 = SynthContext(0)
+        batch.streams["setup_id"] = c2.register_setup(setup)
+        bh = c2.upload(batch)
+        c2.run(bh)
+        assert np.array_equal(c2.fetch_pcm(bh), out), rl
+        bh.free(); c2.close()
+
+
+def test_mdct_backward_dropin_all_sizes(ctx):
+    rng = np.random.default_rng(9)
+    for n in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
+        x = rng.standard_normal((5, n // 2)).astype(np.float32)
+        y = ctx.mdct_backward(x)
+        for i in range(5):
+            ref = ob.imdct(x[i], "closed")
+            assert ob.snr_db(y[i], ref) >= TOL_SNR, n
+            assert np.abs(y[i] - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), n
+    if ob.reference_lib() is not None:
+        x = rng.standard_normal((3, 1024)).astype(np.float32)
+        y = ctx.mdct_backward(x)
+        for i in range(3):
+            assert ob.snr_db(y[i], ob.reference_imdct(x[i])) >= TOL_SNR
+
+
+def test_error_status_matches_reference_checks(ctx):
+    """Packets that trip the reference's fatal CHECKs (hpp:536, hpp:587) are reported per packet, not decoded."""
+    setup, batch = workloads.config2(P=40, seed=3)
+    ys = batch.ys.copy()
+    pk = batch.packets
+    # packet 5: huge coded value on a late post -> final Y far above range -> floor >= 256
+    p = 5
+    posts = 29 if pk["mode"][p] else 9
+    ys[int(pk["ys_off"][p]) + posts - 1] = 5000
+    # packet 9: first two posts maximal, third pushes predicted range check through a wrapped value
+    p2 = 9
+    ys[int(pk["ys_off"][p2]) + 2] = 60000
+    batch.ys = ys
+    sid = ctx.register_setup(setup)
+    batch.streams["setup_id"] = sid
+    bh = ctx.upload(batch)
+    ctx.run(bh)
+    st = ctx.status(bh)
+    batch.streams["setup_id"] = 0
+    _, rst = ob.synth_batch([setup], batch, imdct="fast")
+    assert st[p] != 0 and st[p2] != 0
+    assert np.array_equal(st != 0, rst != 0)
+    assert np.array_equal(st, rst)
+    from parseoggvorbis_b200.lib import PovError
+    with pytest.raises(PovError):
+        ctx.status(bh, check=True)
+    bh.free()
+
+
+def test_descriptor_validation_errors(ctx):
+    from parseoggvorbis_b200.lib import PovError
+    setup, batch = workloads.config2(P=16)
+    batch.streams["setup_id"] = ctx.register_setup(setup)
+    bad = abi.Batch(batch.streams.copy(), batch.packets.copy(), batch.ys, batch.payload, batch.pcm_floats)
+    bad.packets["mode"][3] = 7
+    with pytest.raises(PovError):
+        ctx.upload(bad)
+    bad = abi.Batch(batch.streams.copy(), batch.packets.copy(), batch.ys, batch.payload, batch.pcm_floats)
+    bad.packets["emit_frames"][1] = 5000
+    with pytest.raises(PovError):
+        ctx.upload(bad)
+    s2 = workloads.make_setup(2)
+    s2.floors[0] = abi.Floor1([0, 128, 14, 14], 4)       # duplicate X
+    with pytest.raises(PovError):
+        ctx.register_setup(s2)
