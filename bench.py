@@ -51,7 +51,7 @@ class ClockSampler:
         self.gpu = gpu_index
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -197,7 +197,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=128, help="independent config-2 streams per GPU per step")
@@ -281,7 +281,8 @@ def main():
         sub = abi.Batch(st, pk, batch.ys, batch.payload, int(st["pcm_frames"][0]) * setup.channels)
         ref, _ = ob.synth_batch([setup], sub, imdct="fast")
         got = ctx.fetch_pcm(bh)[:sub.pcm_floats]
-        check = {"max_abs_err": float(np.abs(got - ref).max()), "snr_db": float(ob.snr_db(got, ref)),
+        check = {"max_abs_err": float(np.abs(got - ref).max()), "peak": float(np.abs(ref).max()),
+                 "snr_db": float(ob.snr_db(got, ref)),
                  "packets_with_status": status_bad}
 
     # ---- end-to-end leg: host buffers in, host PCM out, every step ----

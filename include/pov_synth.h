@@ -246,6 +246,15 @@ int  pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* dat
                        uint32_t host_threads, uint64_t* frames_out, uint64_t* total_values_out,
                        double* checksum_out);
 
+/* Host-only front-end (no GPU needed): parse a whole Ogg/Vorbis file into descriptor batches, one per logical stream
+ * (Ogg framing hpp:51-102,1433-1484; headers hpp:1283-1373; per-packet entropy decode hpp:498-517, 711-757). The
+ * setup/batch returned by pov_parsed_get point into memory owned by the handle (POV_INPUT_ENTRIES, setup_id 0). */
+typedef struct pov_parsed pov_parsed;
+int      pov_ogg_parse_memory(const uint8_t* data, size_t len, pov_parsed** out, const char** error_out);
+uint32_t pov_parsed_stream_count(const pov_parsed* p);
+int      pov_parsed_get(const pov_parsed* p, uint32_t stream, pov_setup* setup_out, pov_batch* batch_out);
+void     pov_parsed_free(pov_parsed* p);
+
 /* Same signature/semantics as the reference's entry point (hpp:1493), on device 0; error string is per-thread. */
 int  pov_ogg_vorbis_full_read_from_memory(const char* data, size_t data_len, const char** error_out);
 

@@ -53,6 +53,7 @@ struct pov_ctx {
 	const DevSetup* d_setups = nullptr;
 	std::vector<SetupRec> setups;
 	std::map<uint32_t, BlockTables> blk_tables;
+	std::map<std::string, uint32_t> setup_by_key;   // raw header bytes of a parsed stream -> setup id (front end)
 	DevBuf mdct_in, mdct_out;
 	char err[512] = {0};
 };

@@ -336,6 +336,23 @@ __global__ void __launch_bounds__(256) k_ola_staged(DevBatchView b, DevStageBuff
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// sum of a PCM arena in float64 (corpus decode reports it as a checksum of everything that was delivered)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_checksum(const float* __restrict__ pcm, uint64_t n, double* __restrict__ sum) {
+	double acc = 0;
+	for(uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) acc += (double) pcm[i];
+	for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	__shared__ double part[8];
+	if((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		double t = 0;
+		for(int i = 0; i < 8; ++i) t += part[i];
+		atomicAdd(sum, t);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 cudaError_t launch_residue_apply(const DevBatchView& b, float* spectra_out, size_t smem, cudaStream_t st,
@@ -374,3 +391,11 @@ cudaError_t launch_mdct_backward(const DevSetup*, uint32_t n, uint64_t count, co
 }
 
 }  // namespace pov
+
+cudaError_t pov_checksum_launch(const float* pcm, uint64_t n, double* d_sum, cudaStream_t st, uint64_t* launches) {
+	if(n == 0) return cudaSuccess;
+	const unsigned blocks = (unsigned) ((n + 256ull * 16 - 1) / (256ull * 16) > 1184 ? 1184 : (n + 256ull * 16 - 1) / (256ull * 16));
+	pov::k_checksum<<<blocks ? blocks : 1, 256, 0, st>>>(pcm, n, d_sum);
+	if(launches) ++*launches;
+	return cudaGetLastError();
+}

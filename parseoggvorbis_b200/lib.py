@@ -24,6 +24,7 @@ SYMBOLS = [
     "pov_batch_upload", "pov_batch_run", "pov_batch_run_staged", "pov_batch_fetch_pcm", "pov_batch_pcm_dev",
     "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_mdct_backward_batch",
     "pov_ogg_vorbis_decode_memory", "pov_decoded_free", "pov_decode_corpus", "pov_ogg_vorbis_full_read_from_memory",
+    "pov_ogg_parse_memory", "pov_parsed_stream_count", "pov_parsed_get", "pov_parsed_free",
 ]
 
 
@@ -78,8 +79,50 @@ def load() -> C.CDLL:
     L.pov_decode_corpus.argtypes = [vp, u32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), u32,
                                     C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
     L.pov_ogg_vorbis_full_read_from_memory.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p)]
+    L.pov_ogg_parse_memory.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_char_p)]
+    L.pov_parsed_stream_count.argtypes = [vp]
+    L.pov_parsed_stream_count.restype = u32
+    L.pov_parsed_get.argtypes = [vp, u32, C.POINTER(abi.pov_setup), C.POINTER(abi.pov_batch)]
+    L.pov_parsed_free.argtypes = [vp]
+    L.pov_parsed_free.restype = None
     _LIB = L
     return L
+
+
+class ParsedOgg:
+    """Host-only parse of one Ogg/Vorbis file into descriptor batches (no GPU involved)."""
+
+    def __init__(self, data: bytes):
+        self.L = load()
+        self.h = C.c_void_p(None)
+        self._data = data
+        err = C.c_char_p(None)
+        rc = self.L.pov_ogg_parse_memory(data, len(data), C.byref(self.h), C.byref(err))
+        if rc != 0:
+            raise PovError(rc, (err.value or b"?").decode())
+
+    @property
+    def n_streams(self) -> int:
+        return int(self.L.pov_parsed_stream_count(self.h))
+
+    def get(self, stream: int = 0):
+        """-> (pov_setup, pov_batch) ctypes structs pointing into this handle's memory."""
+        s, b = abi.pov_setup(), abi.pov_batch()
+        rc = self.L.pov_parsed_get(self.h, stream, C.byref(s), C.byref(b))
+        if rc != 0:
+            raise PovError(rc, "pov_parsed_get")
+        return s, b
+
+    def close(self):
+        if self.h:
+            self.L.pov_parsed_free(self.h)
+            self.h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BatchHandle:

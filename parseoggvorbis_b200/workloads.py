@@ -153,8 +153,9 @@ def build_dense_batch(setup: abi.Setup, plans: Sequence[StreamPlan], rng: np.ran
         nrows = int(used[rows].sum())
         vals = gen_ys(rng, nrows, posts[cls], ranges[cls])
         # destination index of every (packet, used channel) list
-        starts = (packets["ys_off"][rows][:, None] + (np.cumsum(used[rows], 1) - used[rows]) * posts[cls])[used[rows]]
-        idx = (starts[:, None] + np.arange(posts[cls])[None, :]).ravel()
+        starts = (packets["ys_off"][rows].astype(np.int64)[:, None]
+                  + (np.cumsum(used[rows], 1) - used[rows]).astype(np.int64) * posts[cls])[used[rows]]
+        idx = (starts[:, None] + np.arange(posts[cls], dtype=np.int64)[None, :]).ravel()
         ys[idx] = vals.ravel()
     # dense spectra arena
     half_all = n_all // 2
@@ -167,7 +168,7 @@ def build_dense_batch(setup: abi.Setup, plans: Sequence[StreamPlan], rng: np.ran
             continue
         half = int(setup.blocksize[cls] // 2)
         data = gen_spectra(rng, len(rows) * C, half)
-        idx = (packets["spec_off"][rows][:, None] + np.arange(C * half)[None, :]).ravel()
+        idx = (packets["spec_off"][rows].astype(np.int64)[:, None] + np.arange(C * half, dtype=np.int64)[None, :]).ravel()
         spec[idx] = data.ravel()
     return abi.Batch(streams=streams, packets=packets, ys=ys, payload=spec, pcm_floats=pcm_base,
                      input_kind=abi.POV_INPUT_DENSE, pcm_layout=pcm_layout)

@@ -173,3 +173,26 @@ def snr_db(test, ref):
     if sig == 0:
         return float("-inf")
     return 10 * np.log10(sig / err)
+
+
+def synth_batch_raw(csetup, cbatch, imdct="fast", capture=False):
+    """Whole-batch oracle on raw ctypes structs (one setup), e.g. straight from the host front-end."""
+    kind = {"closed": 0, "fast": 1, "reference": 2}[imdct]
+    fn = _ref_imdct_cb() if kind == 2 else C.cast(None, IMDCT_FN)
+    pcm = np.zeros(int(cbatch.pcm_floats), np.float32)
+    P = int(cbatch.n_packets)
+    status = np.zeros(P, np.uint32)
+    arr = (abi.pov_setup * 1)(csetup)
+    if not capture:
+        rc = lib().por_synth_batch(arr, 1, C.byref(cbatch), kind, fn, None, _p(pcm, C.c_float), _p(status, C.c_uint32))
+        assert rc == 0, rc
+        return pcm, status
+    nmax = int(csetup.blocksize[1])
+    Cn = int(csetup.channels)
+    ares = np.zeros((P, Cn, nmax), np.float32)
+    aenv = np.zeros((P, Cn, nmax), np.float32)
+    mdct = np.zeros((P, Cn, nmax), np.float32)
+    rc = lib().por_synth_batch_ex(arr, 1, C.byref(cbatch), kind, fn, None, _p(pcm, C.c_float), _p(status, C.c_uint32),
+                                  _p(ares, C.c_float), _p(aenv, C.c_float), _p(mdct, C.c_float), C.c_uint32(nmax))
+    assert rc == 0, rc
+    return pcm, status, dict(after_residue=ares, after_envelope=aenv, pcm_after_mdct=mdct)

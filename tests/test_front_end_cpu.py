@@ -1,0 +1,120 @@
+"""Host front-end (Ogg framing, header/setup parse, Huffman + residue walk -> descriptors) against the reference's
+dumps, on the CPU: the descriptors are applied by the pinned oracle, so what is checked here is exactly what the
+host emits — coded floor Y lists, classifications and VQ entry numbers (bit-exact `after_residue`), window flags,
+emit counts and granule trimming."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from parseoggvorbis_b200 import abi, lib
+from tests import oracle_binding as ob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIX = {"stereo44khz": "test.stereo44khz.ogg", "mono44khz": "test.mono44khz.ogg"}
+
+
+def _load(name):
+    with open(os.path.join(ROOT, "tests", "golden", FIX[name]), "rb") as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("name", list(FIX))
+def test_descriptors_reproduce_reference_dump(golden, name):
+    g = golden[name]
+    po = lib.ParsedOgg(_load(name))
+    assert po.n_streams == 1
+    s, b = po.get(0)
+    Cn = int(g["channels"])
+    assert s.channels == Cn and s.sample_rate == int(g["sample_rate"])
+    assert b.n_packets == len(g["blocksize"])
+    pk = np.ctypeslib.as_array(C.cast(b.packets, C.POINTER(C.c_uint8)), shape=(b.n_packets * C.sizeof(abi.pov_packet),))
+    pk = pk.view(abi.PACKET_DTYPE)
+    assert np.array_equal(pk["emit_frames"], g["emit_frames"])
+    used = (pk["floor_used"][:, None] >> np.arange(Cn)[None, :]) & 1
+    assert np.array_equal(used.astype(bool), g["floor_used"])
+    # coded Y lists, bit-exact ("floor1 ys", the one floor field the reference's own harness compares)
+    ys = np.ctypeslib.as_array(b.ys, shape=(b.n_ys,))
+    for p in range(b.n_packets):
+        yo = int(pk["ys_off"][p])
+        for c in range(Cn):
+            if g["floor_used"][p, c]:
+                k = int(g["floor_nposts"][g["floor_number"][p, c]])
+                assert np.array_equal(ys[yo:yo + k], g["ys"][p, c, :k]), (p, c)
+                yo += k
+    # everything downstream through the oracle
+    pcm, status, cap = ob.synth_batch_raw(s, b, imdct="reference" if ob.reference_lib() is not None else "fast", capture=True)
+    assert not status.any()
+    oh = of = 0
+    for p, n in enumerate(g["blocksize"]):
+        n = int(n)
+        for c in range(Cn):
+            assert np.array_equal(cap["after_residue"][p, c, :n // 2], g["after_residue"][oh:oh + n // 2]), (p, c)
+            assert np.array_equal(cap["after_envelope"][p, c, :n // 2], g["after_envelope"][oh:oh + n // 2]), (p, c)
+            oh += n // 2
+            of += n
+    out = pcm.reshape(Cn, -1)
+    assert out.shape == g["pcm"].shape
+    assert np.abs(out - g["pcm"]).max() <= 1e-5
+    if ob.reference_lib() is not None:
+        assert np.array_equal(out, g["pcm"])
+    po.close()
+
+
+def _expect_error(data, needle=None):
+    with pytest.raises(lib.PovError) as ei:
+        lib.ParsedOgg(bytes(data))
+    assert ei.value.code == abi.POV_ERR_STREAM
+    if needle:
+        assert needle in ei.value.msg, ei.value.msg
+
+
+def test_malformed_streams_fail_like_the_reference():
+    data = bytearray(_load("mono44khz"))
+    bad = bytearray(data); bad[0] = ord("X")
+    _expect_error(bad, "capture pattern")                       # hpp:77
+    bad = bytearray(data); bad[len(bad) // 2] ^= 0x55
+    _expect_error(bad, "CRC")                                   # hpp:98
+    _expect_error(data[:len(data) - 100], "truncated")          # hpp:90
+    assert lib.ParsedOgg(bytes(data[:20])).n_streams == 0       # < 27 bytes: plain EOF (hpp:69-74)
+    assert lib.ParsedOgg(b"").n_streams == 0
+
+
+@pytest.mark.skipif(ob.reference_lib() is None, reason="oracle/_ref not built")
+def test_error_behaviour_matches_reference_library():
+    """Same inputs through the reference's own C API (hpp:1493): both accept or both reject."""
+    ref = ob.reference_lib()
+    ref.ogg_vorbis_full_read_from_memory.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p)]
+    rng = np.random.default_rng(0)
+    base = _load("mono44khz")
+    cases = [base, base[:5000], base[:27], base[:4000] + base[4100:]]
+    for _ in range(6):
+        b = bytearray(base)
+        b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        cases.append(bytes(b))
+    for data in cases:
+        err = C.c_char_p(None)
+        ref_rc = ref.ogg_vorbis_full_read_from_memory(data, len(data), C.byref(err))
+        try:
+            lib.ParsedOgg(data).close()
+            ours_rc = 0
+        except lib.PovError:
+            ours_rc = 1
+        assert (ref_rc != 0) == (ours_rc != 0), (len(data), err.value)
+
+
+def test_crc_known_answer():
+    # Ogg CRC of the first page of the bundled fixture equals the value stored in its header (hpp:92-98)
+    data = _load("stereo44khz")
+    nseg = data[26]
+    body = sum(data[27:27 + nseg])
+    page = bytearray(data[:27 + nseg + body])
+    stored = int.from_bytes(page[22:26], "little")
+    page[22:26] = b"\0\0\0\0"
+    crc = 0
+    for byte in page:     # bitwise restatement: poly 0x04c11db7, MSB first, init 0
+        crc ^= byte << 24
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x04C11DB7) & 0xFFFFFFFF if crc & 0x80000000 else (crc << 1) & 0xFFFFFFFF
+    assert crc == stored

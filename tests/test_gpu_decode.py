@@ -1,0 +1,131 @@
+"""GPU tests of the whole-file path: host front-end -> descriptors -> residue kernel -> fused/staged kernels.
+Config 1 of BASELINE.json: the bundled fixtures decoded end to end and compared with the reference's dump."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from parseoggvorbis_b200 import abi, lib
+from tests import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIX = {"stereo44khz": "test.stereo44khz.ogg", "mono44khz": "test.mono44khz.ogg"}
+
+
+def _load(name):
+    with open(os.path.join(ROOT, "tests", "golden", FIX[name]), "rb") as f:
+        return f.read()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lib.SynthContext(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", list(FIX))
+def test_decode_fixture_pcm(ctx, golden, name):
+    g = golden[name]
+    pcm, rate, npk = ctx.decode_ogg(_load(name))
+    assert rate == int(g["sample_rate"]) and npk == len(g["blocksize"])
+    assert pcm.shape == g["pcm"].shape
+    assert np.abs(pcm - g["pcm"]).max() <= 1e-5
+    assert ob.snr_db(pcm, g["pcm"]) >= 120.0
+
+
+@pytest.mark.parametrize("name", list(FIX))
+def test_debug_dump_field_by_field(ctx, golden, name, tmp_path):
+    """The dump written from the staged device path, parsed back and compared with the reference's dump:
+    integer fields and after_residue/after_envelope bit-exact, IMDCT output and PCM <= 1e-5 / >= 120 dB."""
+    from oracle.dumpfile import load_dump
+    g = golden[name]
+    path = str(tmp_path / (name + ".dbg"))
+    pcm, _, _ = ctx.decode_ogg(_load(name), debug_out=path)
+    keep = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(keep):      # bring it home for the reference's own compare-debug-out.py
+        import shutil
+        shutil.copyfile(path, os.path.join(keep, name + "_b200.dbg"))
+    d = load_dump(path)
+    Cn = int(g["channels"])
+    assert d.num_channels == Cn and d.sample_rate == int(g["sample_rate"])
+    assert d.floor_multipliers == [int(x) for x in g["floor_multipliers"]]
+    for i, xs in enumerate(d.floor_xs):
+        assert np.array_equal(xs, g["floor_xs"][i, :len(xs)])
+    assert len(d.packets) == len(g["blocksize"])
+    table = np.load(os.path.join(ROOT, "tests", "golden", "inverse_db_table.npy"))
+    oh = of = 0
+    worst = 0.0
+    for p, pk in enumerate(d.packets):
+        n = int(g["blocksize"][p])
+        assert pk.abs_total_pos == int(g["abs_total_pos"][p])
+        assert pk.expected_ending_total_pos == int(g["expected_ending_total_pos"][p])
+        for c in range(Cn):
+            f = pk.floors[c]
+            assert f.floor_number == int(g["floor_number"][p, c])
+            if g["floor_used"][p, c]:
+                k = int(g["floor_nposts"][f.floor_number])
+                assert np.array_equal(f.ys, g["ys"][p, c, :k])
+                assert np.array_equal(f.final_ys, g["final_ys"][p, c, :k])
+                assert np.array_equal(f.step2_flag, g["step2_flag"][p, c, :k])
+                assert np.array_equal(f.floor, g["floor"][of:of + n])
+                assert np.array_equal(f.floor_outputs.view(np.uint32), table[g["floor"][of:of + n]].view(np.uint32))
+            else:
+                assert f.ys is None
+            assert np.array_equal(pk.after_residue[c], g["after_residue"][oh:oh + n // 2]), (p, c)
+            assert np.array_equal(pk.after_envelope[c], g["after_envelope"][oh:oh + n // 2]), (p, c)
+            worst = max(worst, float(np.abs(pk.pcm_after_mdct[c] - g["pcm_after_mdct"][of:of + n]).max()))
+            oh += n // 2
+            of += n
+    assert worst <= 1e-5
+    out = d.pcm_concat()
+    assert np.array_equal(out, pcm)
+    assert np.abs(out - g["pcm"]).max() <= 1e-5 and ob.snr_db(out, g["pcm"]) >= 120.0
+
+
+def test_corpus_decode_matches_single_file(ctx, golden):
+    """Config 5 in miniature: replicated fixtures through the threaded front-end, sharded into chunks."""
+    files = []
+    for i in range(150):
+        files.append(_load("stereo44khz" if i % 3 else "mono44khz"))
+    frames, total, chk = ctx.decode_corpus(files, host_threads=4)
+    exp_frames = [golden["stereo44khz" if i % 3 else "mono44khz"]["pcm"].shape[1] for i in range(150)]
+    assert list(frames) == exp_frames
+    exp_total = sum(golden["stereo44khz" if i % 3 else "mono44khz"]["pcm"].size for i in range(150))
+    assert total == exp_total
+    exp_chk = sum(float(golden["stereo44khz" if i % 3 else "mono44khz"]["pcm"].astype(np.float64).sum()) for i in range(150))
+    assert abs(chk - exp_chk) <= 1e-3 * max(1.0, abs(exp_chk)) + 0.05
+
+
+def test_reference_shaped_entry_point():
+    L = lib.load()
+    data = _load("mono44khz")
+    err = C.c_char_p(None)
+    assert L.pov_ogg_vorbis_full_read_from_memory(data, len(data), C.byref(err)) == 0
+    bad = bytearray(data); bad[3000] ^= 0xFF
+    assert L.pov_ogg_vorbis_full_read_from_memory(bytes(bad), len(bad), C.byref(err)) == 1
+    assert b"check failed" in err.value
+
+
+def test_entries_batch_staged_equals_fused(ctx):
+    """POV_INPUT_ENTRIES batches straight from the host parser: residue kernel + fused == residue kernel + staged."""
+    po = lib.ParsedOgg(_load("stereo44khz"))
+    s, b = po.get(0)
+    sid = C.c_uint32(0)
+    ctx._check(ctx.L.pov_setup_register(ctx.ctx, C.byref(s), C.byref(sid)))
+    st = abi.pov_stream.from_address(C.addressof(b.streams.contents))
+    st.setup_id = sid.value
+    h = C.c_void_p(None)
+    ctx._check(ctx.L.pov_batch_upload(ctx.ctx, C.byref(b), C.byref(h)))
+    out = []
+    for run in (ctx.L.pov_batch_run, ctx.L.pov_batch_run_staged):
+        ctx._check(run(ctx.ctx, h))
+        pcm = np.empty(int(b.pcm_floats), np.float32)
+        ctx._check(ctx.L.pov_batch_fetch_pcm(ctx.ctx, h, pcm.ctypes.data_as(C.POINTER(C.c_float)), pcm.size, 1))
+        out.append(pcm)
+    assert np.array_equal(out[0], out[1])
+    st.setup_id = 0
+    ctx.L.pov_batch_free(ctx.ctx, h)
+    po.close()
