@@ -114,7 +114,7 @@ extern "C" void pov_ctx_destroy(pov_ctx* ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	for(auto& s : ctx->setups) free_setup(s);
-	for(auto& kv : ctx->blk_tables) { cudaFree((void*) kv.second.d_rot); cudaFree((void*) kv.second.d_fft); cudaFree((void*) kv.second.d_slope); }
+	for(auto& kv : ctx->blk_tables) { cudaFree((void*) kv.second.d_rot); cudaFree((void*) kv.second.d_fft); cudaFree((void*) kv.second.d_fftp); cudaFree((void*) kv.second.d_slope); }
 	cudaFree((void*) ctx->d_setups);
 	cudaFree((void*) ctx->d_inv_db);
 	ctx->mdct_in.release(); ctx->mdct_out.release();
@@ -131,13 +131,15 @@ static int get_block_tables(pov_ctx* ctx, uint32_t n, BlockTables** out) {
 	auto it = ctx->blk_tables.find(n);
 	if(it != ctx->blk_tables.end()) { *out = &it->second; return POV_OK; }
 	BlockTables t;
-	std::vector<float> rot, fft, slope;
+	std::vector<float> rot, fft, fftp, slope;
 	make_rotation(n, rot);
 	make_fft_twiddles(n, fft);
+	make_fft_pass_tables(n, fftp);
 	make_window_slope(n / 2, slope);
 	t.h_slope = slope;
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_rot, rot.data(), rot.size(), ctx->stream));
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_fft, fft.data(), fft.size(), ctx->stream));
+	CUDA_TRY(ctx, dev_upload((float**) &t.d_fftp, fftp.data(), fftp.size(), ctx->stream));
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_slope, slope.data(), slope.size(), ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	auto ins = ctx->blk_tables.emplace(n, std::move(t));
@@ -285,6 +287,12 @@ extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id
 		d.mode_blockflag[i] = s->modes[i].blockflag ? 1 : 0;
 		d.mode_mapping[i] = s->modes[i].mapping;
 	}
+	for(uint32_t i = 0; i < s->n_modes; ++i) {
+		const pov_mapping& m = s->mappings[s->modes[i].mapping];
+		const int cls = s->modes[i].blockflag ? 1 : 0;
+		for(uint32_t k = 0; k < m.n_submaps; ++k)
+			rec.posts_cls[cls] = std::max<uint32_t>(rec.posts_cls[cls], floors[m.submap_floor[k]].n_posts);
+	}
 	rec.n_modes = s->n_modes;
 	memcpy(rec.mode_blockflag, d.mode_blockflag, sizeof rec.mode_blockflag);
 	memcpy(rec.mode_mapping, d.mode_mapping, sizeof rec.mode_mapping);
@@ -302,6 +310,7 @@ extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id
 	d.slope[0] = t0->d_slope; d.slope[1] = t1->d_slope;
 	d.rot[0] = t0->d_rot; d.rot[1] = t1->d_rot;
 	d.fft[0] = t0->d_fft; d.fft[1] = t1->d_fft;
+	d.fftp[0] = t0->d_fftp; d.fftp[1] = t1->d_fftp;
 	CUDA_TRY(ctx, dev_upload((float**) &rec.d_vq, vq_all.data(), vq_all.size(), ctx->stream));
 	for(uint32_t i = 0; i < s->n_codebooks; ++i)
 		if(cbs[i].lookup_type != 0) cbs[i].vq = rec.d_vq + vq_off[i];
@@ -374,7 +383,7 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	const uint32_t P = b->n_packets;
 	h->spec_off.resize(P); h->stage_off.resize(P); h->pk_n.resize(P); h->pk_setup.resize(P);
 	h->runs.clear();
-	uint32_t maxC = 1, maxbs = 64, minbs = 8192, maxposts = 2, res_smem = 0;
+	uint32_t maxC = 1, maxbs = 64, minbs = 8192, maxposts = 2, res_smem = 0, posts_cls[2] = {2, 2};
 	uint64_t dense_floats = 0, stage_floats = 0, expect_first = 0;
 	const uint64_t payload_floats = b->payload_bytes / 4;
 	uint32_t run_len = ctx->run_len;
@@ -394,6 +403,7 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 		if(st.pcm_base + st.pcm_frames * C > b->pcm_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: stream %u: PCM region exceeds pcm_floats", si);
 		maxC = std::max(maxC, C); maxbs = std::max(maxbs, su.blocksize[1]); minbs = std::min(minbs, su.blocksize[0]);
 		maxposts = std::max(maxposts, su.max_posts); res_smem = std::max(res_smem, su.res_smem);
+		posts_cls[0] = std::max(posts_cls[0], su.posts_cls[0]); posts_cls[1] = std::max(posts_cls[1], su.posts_cls[1]);
 		uint32_t n_prev = 0;
 		for(uint32_t k = 0; k < st.n_packets; ++k) {
 			const uint32_t p = st.first_packet + k;
@@ -463,10 +473,11 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	}
 	h->max_channels = maxC; h->max_blocksize = maxbs; h->min_blocksize = std::min(minbs, maxbs);
 	h->floor_cap = (maxposts + 3u) & ~3u;
+	h->floor_cap_cls[0] = (posts_cls[0] + 3u) & ~3u; h->floor_cap_cls[1] = (posts_cls[1] + 3u) & ~3u;
 	h->res_smem = res_smem;
 	h->stage_floats = stage_floats;
 	h->dense_floats = dense_floats;
-	h->fused_ok = fused_smem_bytes(maxC, maxbs, h->floor_cap) <= 227 * 1024;
+	h->fused_ok = fused_smem_bytes(maxC, maxbs, h->min_blocksize, h->floor_cap_cls) <= 227 * 1024;
 
 	// ---- device copies ----
 	cudaStream_t st = ctx->stream;
@@ -554,7 +565,7 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
 	int rc = run_residue_if_needed(ctx, h, v);
 	if(rc) return rc;
 	CUDA_TRY(ctx, launch_fused(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), h->max_channels, h->max_blocksize,
-	                           h->min_blocksize, h->floor_cap, ctx->stream, &ctx->launches));
+	                           h->min_blocksize, h->floor_cap_cls, ctx->stream, &ctx->launches));
 	return POV_OK;
 }
 

@@ -21,6 +21,7 @@ struct DevBuf {
 struct BlockTables {              // per blocksize n: DCT-IV rotation, FFT twiddles, rising slope of n/2 samples
 	const float2* d_rot = nullptr;
 	const float2* d_fft = nullptr;
+	const float2* d_fftp = nullptr;
 	const float*  d_slope = nullptr;
 	std::vector<float> h_slope;
 };
@@ -28,6 +29,7 @@ struct BlockTables {              // per blocksize n: DCT-IV rotation, FFT twidd
 struct SetupRec {
 	uint32_t channels = 0, sample_rate = 0, blocksize[2] = {0, 0};
 	uint32_t n_modes = 0, entry_bits = 16, max_posts = 2, res_smem = 0;
+	uint32_t posts_cls[2] = {2, 2};   // largest floor (posts) reachable from short / long modes
 	uint8_t mode_blockflag[POV_MAX_MODES] = {0};
 	uint8_t mode_mapping[POV_MAX_MODES] = {0};
 	std::vector<DevFloor> floors_host;
@@ -62,6 +64,7 @@ struct pov_batch_handle {
 	uint32_t n_streams = 0, n_packets = 0, input_kind = 0, pcm_layout = 0;
 	uint64_t pcm_floats = 0, stage_floats = 0, dense_floats = 0;
 	uint32_t max_channels = 1, max_blocksize = 64, min_blocksize = 64, floor_cap = 4, res_smem = 0;
+	uint32_t floor_cap_cls[2] = {4, 4};
 	bool fused_ok = true, staged_ready = false;
 	std::vector<uint64_t> spec_off, stage_off;
 	std::vector<uint32_t> pk_n, pk_setup;

@@ -178,6 +178,122 @@ __device__ __forceinline__ void pass_last_to_D(const float2* __restrict__ T, int
 	}
 }
 
+// ---- per-pass packed twiddle tables (host: make_fft_pass_tables) ------------------------------------------------
+template <int Q> struct PassTables {
+	static constexpr int R0 = FftGeom<Q>::kFirstRadix;
+	static constexpr int kFirstSize = (R0 == 8) ? 0 : Q;             // (Q/R0) butterflies x R0 factors
+	static constexpr int kL1 = (R0 == 8) ? Q : Q / R0;               // length of the first radix-8 pass
+	static __host__ __device__ constexpr int offset(int L) {         // float2 offset of the radix-8 pass of length L
+		int o = kFirstSize;
+		for(int l = kL1; l > L; l /= 8) o += l;                       // each radix-8 table holds (l/8)*8 = l factors
+		return o;
+	}
+};
+
+template <int Q, int L>
+__device__ __forceinline__ void pass_radix8_p(float2* __restrict__ T, int t, const float2* __restrict__ TWP) {
+	constexpr int s = L / 8, ps = s + s / 8;                         // s % 8 == 0 for L >= 64
+	const int blk = t / s, j = t - blk * s;
+	const int base = blk * L + j;
+	float2* p = T + base + (base >> 3);
+	float2 a[8];
+#pragma unroll
+	for(int m = 0; m < 8; ++m) a[m] = p[m * ps];
+	dft8(a);
+	constexpr int kOff = PassTables<Q>::offset(L);
+	const float4* tw = reinterpret_cast<const float4*>(TWP + kOff + j * 8);
+	const float4 w01 = __ldg(tw), w23 = __ldg(tw + 1), w45 = __ldg(tw + 2), w67 = __ldg(tw + 3);
+	a[1] = cmul(a[1], make_float2(w01.z, w01.w));
+	a[2] = cmul(a[2], make_float2(w23.x, w23.y));
+	a[3] = cmul(a[3], make_float2(w23.z, w23.w));
+	a[4] = cmul(a[4], make_float2(w45.x, w45.y));
+	a[5] = cmul(a[5], make_float2(w45.z, w45.w));
+	a[6] = cmul(a[6], make_float2(w67.x, w67.y));
+	a[7] = cmul(a[7], make_float2(w67.z, w67.w));
+#pragma unroll
+	for(int k = 0; k < 8; ++k) p[k * ps] = a[k];
+}
+
+template <int Q>
+__device__ __forceinline__ void pass_first_small_p(float2* __restrict__ T, int t, const float2* __restrict__ TWP) {
+	constexpr int R = FftGeom<Q>::kFirstRadix;
+	if(R == 4) {
+		constexpr int s = Q / 4, ps = s + s / 8;
+#pragma unroll
+		for(int u = 0; u < 2; ++u) {
+			const int j = t + u * (Q / 8);
+			float2* p = T + j + (j >> 3);
+			float2 a0 = p[0], a1 = p[ps], a2 = p[2 * ps], a3 = p[3 * ps];
+			dft4(a0, a1, a2, a3);
+			const float4* tw = reinterpret_cast<const float4*>(TWP + j * 4);
+			const float4 w01 = __ldg(tw), w23 = __ldg(tw + 1);
+			a1 = cmul(a1, make_float2(w01.z, w01.w));
+			a2 = cmul(a2, make_float2(w23.x, w23.y));
+			a3 = cmul(a3, make_float2(w23.z, w23.w));
+			p[0] = a0; p[ps] = a1; p[2 * ps] = a2; p[3 * ps] = a3;
+		}
+	} else if(R == 2) {
+		constexpr int s = Q / 2, ps = s + s / 8;
+#pragma unroll
+		for(int u = 0; u < 4; ++u) {
+			const int j = t + u * (Q / 8);
+			float2* p = T + j + (j >> 3);
+			float2 a0 = p[0], a1 = p[ps];
+			dft2(a0, a1);
+			const float4 w01 = __ldg(reinterpret_cast<const float4*>(TWP + j * 2));
+			a1 = cmul(a1, make_float2(w01.z, w01.w));
+			p[0] = a0; p[ps] = a1;
+		}
+	}
+}
+
+template <int Q, int L>
+__device__ __forceinline__ void passes_radix8_p(float2* T, int nf, const float2* TWP) {
+	if constexpr(L >= 64) {
+		for(int w = threadIdx.x; w < nf * FftGeom<Q>::kItems; w += blockDim.x) {
+			const int f = w / FftGeom<Q>::kItems, t = w - f * FftGeom<Q>::kItems;
+			pass_radix8_p<Q, L>(T + f * FftGeom<Q>::kStride, t, TWP);
+		}
+		__syncthreads();
+		passes_radix8_p<Q, L / 8>(T, nf, TWP);
+	}
+}
+
+// All passes but the last (block-wide, contains __syncthreads()), packed-table version.
+template <int Q>
+__device__ __forceinline__ void fft_passes_except_last_p(float2* T, int nf, const float2* TWP) {
+	if constexpr(FftGeom<Q>::kFirstRadix != 8) {
+		for(int w = threadIdx.x; w < nf * FftGeom<Q>::kItems; w += blockDim.x) {
+			const int f = w / FftGeom<Q>::kItems, t = w - f * FftGeom<Q>::kItems;
+			pass_first_small_p<Q>(T + f * FftGeom<Q>::kStride, t, TWP);
+		}
+		__syncthreads();
+	}
+	passes_radix8_p<Q, PassTables<Q>::kL1>(T, nf, TWP);
+}
+
+// Last pass + post-rotation, index arithmetic folded: positions 8t..8t+7 live at T[9t + m].
+template <int Q>
+__device__ __forceinline__ void pass_last_to_D_p(const float2* __restrict__ T, int t, const float2* __restrict__ rot,
+                                                 float* __restrict__ Dst) {
+	constexpr int M = 2 * Q;
+	float2 a[8];
+	const float2* p = T + 9 * t;
+#pragma unroll
+	for(int m = 0; m < 8; ++m) a[m] = p[m];
+	dft8(a);
+	const int k0 = freq_of_pos<Q>(8 * t);
+	const float2* r = rot + k0;
+	float* d0 = Dst + 2 * k0;
+	float* d1 = Dst + (M - 1 - 2 * k0);
+#pragma unroll
+	for(int m = 0; m < 8; ++m) {
+		const float2 c = cmul(a[m], __ldg(r + m * (Q / 8)));
+		d0[m * (Q / 4)] = c.x;
+		d1[-m * (Q / 4)] = -c.y;
+	}
+}
+
 // Frame sample y[m] (m < n = 2M) from the D array of that frame.
 __device__ __forceinline__ float frame_from_D(const float* __restrict__ D, int M, int m) {
 	if(m < M / 2) return D[m + M / 2];

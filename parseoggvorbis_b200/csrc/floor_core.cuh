@@ -144,4 +144,189 @@ __device__ __forceinline__ void floor1_render_warp(const FloorScratch& S, uint32
 	for(uint32_t x = max(xl, b0) + lane; x < b1; x += 32) sink(x, yl);
 }
 
+// ===============================================================================================================
+// Fast path used by the fused kernel.
+// ===============================================================================================================
+
+// floor(e / d) for e < 2^23 via one float multiply by rinv ~= 1/d and a +/-1 fix-up (exact: e is exactly
+// representable, the product is off by far less than 1); larger e (malformed streams only) divide exactly.
+__device__ __forceinline__ uint32_t div_floor_u(uint32_t e, uint32_t d, float rinv) {
+	if(e >= (1u << 23)) return e / d;
+	int q = (int) ((float) e * rinv);
+	const int r = (int) e - q * (int) d;
+	if(r < 0) --q; else if(r >= (int) d) ++q;
+	return (uint32_t) q;
+}
+
+// ===============================================================================================================
+// v3 curve representation: packed segment records + one segment index per 4-bin cell, evaluated with an exact
+// 32.32 fixed-point slope (no division per bin).
+//
+//   y(x) = y0 +/- floor(k * |dy| / dx),  k = x - x0 < dx < 2^16
+//   m = ceil(2^32 * |dy| / dx)  =>  floor(k*m / 2^32) == floor(k*|dy|/dx): the excess k*eps/2^32 (< dx/2^32 < 1/dx)
+//   can never carry the fractional part (<= 1 - 1/dx) over the next integer.
+// ===============================================================================================================
+struct __align__(16) SegRec {
+	uint32_t x01;     // x0 | x1 << 16   (x1 = 0xFFFF for the flat tail)
+	uint32_t y0s;     // y0 | (descending ? 1u << 31 : 0)
+	uint32_t m_lo;    // 32.32 slope magnitude
+	uint32_t m_hi;
+};
+
+// Per-curve block in shared memory: header (16 B) | SegRec[cap] | uint8 idx[cells], cells = n/8 (4-bin cells over n/2 bins)
+struct CurveV3 {
+	uint32_t* hdr;      // [0] = mode: 0 curve, 1 multiply by 1.0 (channel untouched), 2 multiply by 0.0 (hpp:1159,1247)
+	SegRec*   rec;
+	uint8_t*  idx;
+	static __host__ __device__ constexpr uint32_t bytes(uint32_t cap, uint32_t cells) { return 16u + cap * 16u + ((cells + 15u) & ~15u); }
+	__device__ __forceinline__ void bind(unsigned char* base, uint32_t cap) {
+		hdr = reinterpret_cast<uint32_t*>(base);
+		rec = reinterpret_cast<SegRec*>(base + 16);
+		idx = base + 16 + cap * 16;
+	}
+};
+
+// Builds the records + cell index from the flagged posts (sx/sy = ascending-x compacted posts held one per lane for
+// nseg <= 32, or in shared arrays for larger floors). Lanes cooperate; cells is a multiple of 4.
+__device__ __forceinline__ void curve_build_warp(const CurveV3& Cv, uint32_t nseg, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                                                 bool have, uint32_t base_s, uint32_t cells, int lane, bool zero_cells) {
+	// this lane's segment s = base_s + lane: from (x0,y0) to (x1,y1); the last one is the flat tail
+	if(zero_cells) for(uint32_t w = lane; w < cells / 4; w += 32) reinterpret_cast<uint32_t*>(Cv.idx)[w] = 0;
+	__syncwarp();
+	if(have) {
+		const uint32_t s = base_s + lane;
+		const bool last = (s + 1 == nseg);
+		SegRec r;
+		if(last) { r.x01 = x0 | (0xFFFFu << 16); r.y0s = y0; r.m_lo = 0; r.m_hi = 0; }
+		else {
+			const bool down = y1 < y0;
+			const uint32_t ady = down ? y0 - y1 : y1 - y0, adx = x1 - x0;
+			const uint64_t m = (((uint64_t) ady << 32) + adx - 1) / adx;
+			r.x01 = x0 | (x1 << 16); r.y0s = y0 | (down ? 0x80000000u : 0u);
+			r.m_lo = (uint32_t) m; r.m_hi = (uint32_t) (m >> 32);
+		}
+		Cv.rec[s] = r;
+		// first cell whose first bin is >= x0; write only if no later segment claims the same cell
+		const uint32_t cell = (x0 + 3) >> 2;
+		const uint32_t ncell = last ? 0xFFFFFFFFu : ((x1 + 3) >> 2);
+		if(cell < cells && ncell != cell) Cv.idx[cell] = (uint8_t) s;
+	}
+}
+
+// inclusive max-scan of the cell index (each cell ends up holding the segment that contains its first bin)
+__device__ __forceinline__ void curve_scan_cells_warp(const CurveV3& Cv, uint32_t cells, int lane) {
+	__syncwarp();
+	const uint32_t per = (cells + 31) / 32;
+	const uint32_t b = lane * per, e = min(b + per, cells);
+	uint32_t run = 0;
+	for(uint32_t i = b; i < e; ++i) run = max(run, (uint32_t) Cv.idx[i]);
+	uint32_t incl = run;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o) incl = max(incl, v);
+	}
+	uint32_t carry = __shfl_up_sync(0xffffffffu, incl, 1);
+	if(lane == 0) carry = 0;
+	run = carry;
+	for(uint32_t i = b; i < e; ++i) { run = max(run, (uint32_t) Cv.idx[i]); Cv.idx[i] = (uint8_t) run; }
+	__syncwarp();
+}
+
+// Unwrap (hpp:521-559) + build for floors with <= 32 posts. All 32 lanes call. Returns POV_PKT_* bits (warp-uniform),
+// including the hpp:587 range check over the n bins the reference renders.
+__device__ __forceinline__ uint32_t floor1_curve_warp32(const DevFloor* __restrict__ F, const uint16_t* __restrict__ ys,
+                                                        const CurveV3& Cv, uint32_t cells, uint32_t n, int lane) {
+	const int posts = F->n_posts;
+	const uint32_t range = F->range;
+	const bool have = lane < posts;
+	uint32_t cur = have ? ys[lane] : 0u;
+	const uint32_t val = cur;
+	const int lvl = have ? F->level[lane] : 0;
+	const int lo = have ? F->lo[lane] : 0, hi = have ? F->hi[lane] : 0;
+	const uint32_t dxn = have ? F->dxn[lane] : 0u, adx = have ? F->adx[lane] : 1u;
+	const float rinv = have ? F->rinv[lane] : 1.f;
+	uint32_t flags = 0, bad = 0;
+	const int levels = F->n_levels;
+	for(int lv = 1; lv < levels; ++lv) {
+		const uint32_t y0 = __shfl_sync(0xffffffffu, cur, lo), y1 = __shfl_sync(0xffffffffu, cur, hi);
+		if(lvl == lv) {
+			const bool up = y1 >= y0;
+			const uint32_t ady = up ? (y1 - y0) : (y0 - y1);
+			const uint32_t off = div_floor_u(ady * dxn, adx, rinv);
+			const uint32_t predicted = up ? y0 + off : y0 - off;
+			if(predicted > range) bad |= POV_PKT_FLOOR_PREDICTED;
+			const uint32_t high_room = range - predicted, low_room = predicted;
+			const uint32_t room = min(high_room, low_room) * 2;
+			uint32_t fin = predicted;
+			if(val != 0) {
+				flags |= (1u << lo) | (1u << hi) | (1u << lane);
+				if(val >= room) fin = (high_room > low_room) ? val - low_room + predicted : predicted - val + high_room - 1;
+				else fin = (val & 1) ? predicted - (val + 1) / 2 : predicted + val / 2;
+			}
+			cur = fin;
+		}
+	}
+	flags = __reduce_or_sync(0xffffffffu, flags) | 3u;
+	// compaction in ascending-x order: lane = sorted position -> lane = segment
+	const int si = have ? F->sorted_idx[lane] : 0;
+	const uint32_t fy = __shfl_sync(0xffffffffu, cur, si);
+	const bool f = have && ((flags >> si) & 1u);
+	const uint32_t mask = __ballot_sync(0xffffffffu, f);
+	const uint32_t nseg = __popc(mask);
+	const uint32_t pos = __popc(mask & ((1u << lane) - 1u));
+	const uint32_t myx = f ? (uint32_t) F->xs[si] : 0u;
+	const uint32_t myy = f ? min(fy * (uint32_t) F->multiplier, 0xFFFFu) : 0u;
+	// lane s takes over flagged post s and s+1 (staged through the record area, which is rewritten right after)
+	uint32_t* stage = reinterpret_cast<uint32_t*>(Cv.rec);
+	__syncwarp();
+	if(f) stage[pos * 4] = myx | (myy << 16);
+	__syncwarp();
+	const bool seg = (uint32_t) lane < nseg;
+	const uint32_t pa = seg ? stage[lane * 4] : 0u, pb = ((uint32_t) lane + 1 < nseg) ? stage[(lane + 1) * 4] : 0u;
+	__syncwarp();
+	const uint32_t x0 = pa & 0xFFFFu, y0 = pa >> 16, x1 = pb & 0xFFFFu, y1 = pb >> 16;
+	// hpp:587 range check: maxima sit at rendered end points (segments are monotone); the segment cut by bin n-1 needs y(n-1)
+	bool over = false;
+	if(seg) {
+		if(x0 < n && y0 >= 256) over = true;
+		if((uint32_t) lane + 1 < nseg && x0 < n && x1 > n - 1) {
+			const bool down = y1 < y0;
+			const uint32_t ady = down ? y0 - y1 : y1 - y0, dx = x1 - x0;
+			const uint32_t q = div_floor_u((n - 1 - x0) * ady, dx, 1.0f / (float) dx);
+			if((down ? y0 - q : y0 + q) >= 256) over = true;
+		}
+	}
+	if(__any_sync(0xffffffffu, over)) bad |= POV_PKT_FLOOR_RANGE;
+	if(lane == 0) Cv.hdr[0] = 0;
+	curve_build_warp(Cv, nseg, x0, y0, x1, y1, seg, 0, cells, lane, true);
+	curve_scan_cells_warp(Cv, cells, lane);
+	return __reduce_or_sync(0xffffffffu, bad);
+}
+
+// Two consecutive bins x, x+1 (x even) of the curve as inverse-dB table values.
+__device__ __forceinline__ float2 curve_pair(const CurveV3& Cv, uint32_t x, const float* __restrict__ invdb) {
+	uint32_t s = Cv.idx[x >> 2];
+	uint4 r = *reinterpret_cast<const uint4*>(&Cv.rec[s]);
+	while(x >= (r.x >> 16)) r = *reinterpret_cast<const uint4*>(&Cv.rec[++s]);
+	float2 out;
+	{
+		const uint32_t k = x - (r.x & 0xFFFFu);
+		const uint32_t q = __umulhi(k, r.z) + k * r.w;
+		const uint32_t y0 = r.y & 0xFFFFu;
+		const uint32_t y = (r.y >> 31) ? y0 - q : y0 + q;
+		out.x = invdb[y & 255];
+	}
+	const uint32_t xb = x + 1;
+	while(xb >= (r.x >> 16)) r = *reinterpret_cast<const uint4*>(&Cv.rec[++s]);
+	{
+		const uint32_t k = xb - (r.x & 0xFFFFu);
+		const uint32_t q = __umulhi(k, r.z) + k * r.w;
+		const uint32_t y0 = r.y & 0xFFFFu;
+		const uint32_t y = (r.y >> 31) ? y0 - q : y0 + q;
+		out.y = invdb[y & 255];
+	}
+	return out;
+}
+
 }  // namespace pov

@@ -69,6 +69,32 @@ void make_fft_twiddles(uint32_t n, std::vector<float>& out) {
 	}
 }
 
+// Layout must match PassTables<Q> in fft_core.cuh: [first small-radix pass][radix-8 pass L1][radix-8 pass L1/8]...
+// radix-4 first pass: Q/4 butterflies x 4 factors (W^0, W^j, W^2j, W^3j); radix-2 first pass: Q/2 x 2 (W^0, W^j);
+// radix-8 pass of length L (>= 64): L/8 butterflies x 8 factors W_L^(j*k).
+void make_fft_pass_tables(uint32_t n, std::vector<float>& out) {
+	const uint32_t Q = n / 4;
+	uint32_t log2q = 0;
+	while((1u << log2q) < Q) ++log2q;
+	const uint32_t r0 = (log2q % 3 == 0) ? 8 : (log2q % 3 == 1) ? 2 : 4;
+	out.clear();
+	auto put = [&](double num, double den) {
+		const double a = -2.0 * M_PI * num / den;
+		out.push_back((float) cos(a));
+		out.push_back((float) sin(a));
+	};
+	uint32_t L = Q;
+	if(r0 != 8) {
+		for(uint32_t j = 0; j < Q / r0; ++j)
+			for(uint32_t k = 0; k < r0; ++k) put((double) j * k, (double) Q);
+		L = Q / r0;
+	}
+	for(; L >= 64; L /= 8)
+		for(uint32_t j = 0; j < L / 8; ++j)
+			for(uint32_t k = 0; k < 8; ++k) put((double) j * k, (double) L);
+	if(out.empty()) { out.push_back(1.f); out.push_back(0.f); }
+}
+
 // Neighbours (src/Utils.hpp:60-118) depend on the X list only, so they are found once here instead of once per
 // packet and post as in the reference (hpp:532-533). level[] orders the posts so that a post's two neighbours
 // are final before it is unwrapped; sorted_idx is the ascending-x order of hpp:458-469.
@@ -100,6 +126,9 @@ bool make_floor_tables(const pov_floor1& in, DevFloor& out, std::string& msg) {
 		}
 		out.lo[i] = (uint8_t) lo;
 		out.hi[i] = (uint8_t) hi;
+		out.dxn[i] = (uint16_t) (in.xs[i] - in.xs[lo]);
+		out.adx[i] = (uint16_t) (in.xs[hi] - in.xs[lo]);
+		out.rinv[i] = 1.0f / (float) out.adx[i];
 		const int lv = 1 + std::max<int>(out.level[lo], out.level[hi]);
 		out.level[i] = (uint8_t) lv;
 		maxlevel = std::max(maxlevel, lv);

@@ -18,6 +18,8 @@ void make_window(uint32_t bs0, uint32_t bs1, int blockflag, int prev, int next, 
 // DCT-IV rotation w[j] = exp(-i*pi*(8j+1)/(8M)), j < M/2, M = n/2; FFT twiddles W_Q^e, Q = n/4
 void make_rotation(uint32_t n, std::vector<float>& out_re_im);
 void make_fft_twiddles(uint32_t n, std::vector<float>& out_re_im);
+// per-pass packed twiddles (layout: fft_core.cuh PassTables<Q>)
+void make_fft_pass_tables(uint32_t n, std::vector<float>& out_re_im);
 // floor1 derived tables. Returns false (with msg) when the X list is not usable.
 bool make_floor_tables(const pov_floor1& in, DevFloor& out, std::string& msg);
 

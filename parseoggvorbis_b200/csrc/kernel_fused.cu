@@ -7,8 +7,8 @@
 //
 // Why fused: unfused, every channel-packet of blocksize n moves 2n B of spectrum in, 4n B of frame out, 4n B
 // of frame back in and 2n B of PCM out. Here HBM sees the spectrum once (TMA bulk copy into shared memory,
-// double buffered) and the PCM once (coalesced stores): 4n B per channel-packet = 8 B per PCM sample, the
-// algorithmic minimum of SURVEY.md §8(d). Everything in between lives in shared memory and registers.
+// double buffered) and the PCM once (coalesced 128-bit stores): 4n B per channel-packet = 8 B per PCM sample,
+// the algorithmic minimum of SURVEY.md §8(d). Everything in between lives in shared memory and registers.
 //
 // Work decomposition: one CTA per *run* = up to K consecutive packets of one stream, all channels. The overlap
 // of consecutive frames is carried in shared memory (the D array of the previous frame); the first packet of a
@@ -64,31 +64,44 @@ struct StepInfo {
 struct FusedParams {
 	DevBatchView b;
 	const DevRun* runs;
-	uint32_t floor_cap;      // posts capacity of the per-warp floor scratch (multiple of 4)
+	uint32_t floor_cap[2];   // posts capacity (multiple of 4) of a curve block, per blocksize class
+	uint32_t scratch_cap;    // posts capacity of the per-warp unwrap scratch (only allocated when > 32)
 	uint32_t group_short;    // max short packets per step
-	uint32_t slot_floats;    // floats of one raw/floor buffer set = C_max * blocksize1/2
+	uint32_t slot_floats;    // floats of one spectra buffer = C_max * blocksize1/2
+	uint32_t curve_bytes;    // size of the curve-block region
 };
 
-// Elementwise stage for C channels (compile time): coupling + floor multiply + DCT-IV pre-rotation.
-// Item = (packet g of the step, pair q): complex points j1 = q and j2 = Q-1-q, which together consume the four
-// bins 2q, 2q+1, M-2-2q, M-1-2q of every channel (two aligned float2 loads per array).
+// Elementwise stage for C channels (compile time): floor curve evaluation + coupling + floor multiply + DCT-IV
+// pre-rotation. Item = (packet g of the step, pair q): complex points j1 = q and j2 = Q-1-q, which together consume
+// the four bins 2q, 2q+1, M-2-2q, M-1-2q of every channel (two aligned float2 loads per spectrum).
 template <int C>
-__device__ __forceinline__ void stage_spectral(const float* __restrict__ raw, const float* __restrict__ flo, float2* __restrict__ T,
-                                               int npk, int Q, int tstride, const float2* __restrict__ rot,
+__device__ __forceinline__ void stage_spectral(const float* __restrict__ raw, unsigned char* __restrict__ curves, uint32_t curve_stride,
+                                               uint32_t floor_cap, const float* __restrict__ invdb, float2* __restrict__ T,
+                                               int npk, int log2pairs, const float2* __restrict__ rot,
                                                const DevMapping* __restrict__ mp) {
-	const int M = 2 * Q, pairs = Q / 2;
-	const int ncoup = (int) mp->n_couplings;
-	for(int it = threadIdx.x; it < npk * pairs; it += blockDim.x) {
-		const int g = it / pairs, q = it - g * pairs;
+	const int pairs = 1 << log2pairs, Q = 2 * pairs, M = 2 * Q;
+	const int tstride = Q + Q / 8;
+	const int ncoup = (C > 1) ? (int) mp->n_couplings : 0;
+	for(int it = threadIdx.x; it < (npk << log2pairs); it += blockDim.x) {
+		const int g = it >> log2pairs, q = it & (pairs - 1);
+		const float* R0 = raw + (size_t) (g * C) * M;
 		float x0[C], x1[C], x2[C], x3[C];
 #pragma unroll
 		for(int c = 0; c < C; ++c) {
-			const float* R = raw + (size_t) (g * C + c) * M;
-			const float2 a = *reinterpret_cast<const float2*>(R + 2 * q);
-			const float2 d = *reinterpret_cast<const float2*>(R + M - 2 - 2 * q);
+			const float2 a = *reinterpret_cast<const float2*>(R0 + c * M + 2 * q);
+			const float2 d = *reinterpret_cast<const float2*>(R0 + c * M + M - 2 - 2 * q);
 			x0[c] = a.x; x1[c] = a.y; x2[c] = d.x; x3[c] = d.y;
 		}
-		if(C > 1) {
+		if(C == 2) {
+			// two channels can only be coupled with each other: no channel search needed
+			for(int k = ncoup - 1; k >= 0; --k) {
+				if(mp->coupling_mag[k] == 0) {
+					uncouple_f(x0[0], x0[C - 1]); uncouple_f(x1[0], x1[C - 1]); uncouple_f(x2[0], x2[C - 1]); uncouple_f(x3[0], x3[C - 1]);
+				} else {
+					uncouple_f(x0[C - 1], x0[0]); uncouple_f(x1[C - 1], x1[0]); uncouple_f(x2[C - 1], x2[0]); uncouple_f(x3[C - 1], x3[0]);
+				}
+			}
+		} else if(C > 2) {
 			for(int k = ncoup - 1; k >= 0; --k) {
 				const int m = mp->coupling_mag[k], a = mp->coupling_ang[k];
 				float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -106,68 +119,156 @@ __device__ __forceinline__ void stage_spectral(const float* __restrict__ raw, co
 			}
 		}
 		const float2 w1 = __ldg(&rot[q]), w2 = __ldg(&rot[Q - 1 - q]);
+		float2* T0 = T + (size_t) (g * C) * tstride;
+		const int p1 = q + (q >> 3), p2 = (Q - 1 - q) + ((Q - 1 - q) >> 3);
 #pragma unroll
 		for(int c = 0; c < C; ++c) {
-			const float* F = flo + (size_t) (g * C + c) * M;
-			const float2 fa = *reinterpret_cast<const float2*>(F + 2 * q);
-			const float2 fd = *reinterpret_cast<const float2*>(F + M - 2 - 2 * q);
-			// hpp:1252 residue *= floor (one rounding each; F holds 1.0 / 0.0 for channels without a curve)
+			CurveV3 Cv;
+			Cv.bind(curves + (size_t) (g * C + c) * curve_stride, floor_cap);
+			float2 fa, fd;
+			const uint32_t mode = Cv.hdr[0];
+			if(mode == 0) {
+				fa = curve_pair(Cv, (uint32_t) (2 * q), invdb);
+				fd = curve_pair(Cv, (uint32_t) (M - 2 - 2 * q), invdb);
+			} else {
+				const float fill = (mode == 1) ? 1.f : 0.f;
+				fa = make_float2(fill, fill); fd = fa;
+			}
+			// hpp:1252 residue *= floor (one rounding each)
 			const float y0 = __fmul_rn(x0[c], fa.x), y1 = __fmul_rn(x1[c], fa.y);
 			const float y2 = __fmul_rn(x2[c], fd.x), y3 = __fmul_rn(x3[c], fd.y);
-			float2* Tf = T + (size_t) (g * C + c) * tstride;
-			Tf[tpad(q)] = cmul(make_float2(y0, y3), w1);
-			Tf[tpad(Q - 1 - q)] = cmul(make_float2(y2, y1), w2);
+			T0[c * tstride + p1] = cmul(make_float2(y0, y3), w1);
+			T0[c * tstride + p2] = cmul(make_float2(y2, y1), w2);
 		}
 	}
 }
 
+// Last pass + post-rotation with the D array split in halves: lo = D[0..M/2) (second half of the frame, needed by the
+// NEXT packet), hi = D[M/2..M) (first half of the frame, consumed by this packet's overlap-add).
 template <int Q>
-__device__ __forceinline__ void stage_fft(float2* T, float* D, int nf, const float2* rot, const float2* W) {
-	fft_passes_except_last<Q>(T, nf, W);
-	for(int w = threadIdx.x; w < nf * FftGeom<Q>::kItems; w += blockDim.x) {
-		const int f = w / FftGeom<Q>::kItems, t = w - f * FftGeom<Q>::kItems;
-		pass_last_to_D<Q>(T + (size_t) f * FftGeom<Q>::kStride, t, rot, D + (size_t) f * 2 * Q);
+__device__ __forceinline__ void pass_last_split(const float2* __restrict__ T, int t, const float2* __restrict__ rot,
+                                                float* __restrict__ lo, float* __restrict__ hi) {
+	constexpr int M = 2 * Q;
+	float2 a[8];
+	const float2* p = T + 9 * t;
+#pragma unroll
+	for(int m = 0; m < 8; ++m) a[m] = p[m];
+	dft8(a);
+	const int k0 = freq_of_pos<Q>(8 * t);           // k0 < Q/8; k = k0 + m*Q/8
+	const float2* r = rot + k0;
+#pragma unroll
+	for(int m = 0; m < 8; ++m) {
+		const float2 c = cmul(a[m], __ldg(r + m * (Q / 8)));
+		// D[2k] = Re, D[M-1-2k] = -Im;  2k < M/2  <=>  m < 4
+		if(m < 4) { lo[2 * k0 + m * (Q / 4)] = c.x; hi[(M / 2 - 1 - 2 * k0) - m * (Q / 4)] = -c.y; }
+		else      { hi[2 * k0 + m * (Q / 4) - M / 2] = c.x; lo[(M - 1 - 2 * k0) - m * (Q / 4)] = -c.y; }
 	}
 }
 
-__device__ __forceinline__ void slope_lengths_f(const DevSetup& su, uint32_t flag, uint32_t wflags, int& left, int& right) {
-	left = (int) ((flag && (wflags & 1)) ? su.blocksize[1] : su.blocksize[0]) / 2;    // hpp:844-847
-	right = (int) ((flag && (wflags & 2)) ? su.blocksize[1] : su.blocksize[0]) / 2;
+template <int Q>
+__device__ __forceinline__ void stage_fft(float2* T, float* Dlo, float* Dhi, int nf, const float2* rot, const float2* TWP) {
+	fft_passes_except_last_p<Q>(T, nf, TWP);
+	for(int w = threadIdx.x; w < nf * FftGeom<Q>::kItems; w += blockDim.x) {
+		const int f = w / FftGeom<Q>::kItems, t = w - f * FftGeom<Q>::kItems;
+		pass_last_split<Q>(T + (size_t) f * FftGeom<Q>::kStride, t, rot, Dlo + (size_t) f * Q, Dhi + (size_t) f * Q);
+	}
 }
 
-__global__ void __launch_bounds__(512) k_fused_synth(FusedParams P) {
+__device__ __forceinline__ float4 rev_neg(float4 v) { return make_float4(-v.w, -v.z, -v.y, -v.x); }
+__device__ __forceinline__ float4 rev4(float4 v) { return make_float4(v.w, v.z, v.y, v.x); }
+__device__ __forceinline__ float4 neg4(float4 v) { return make_float4(-v.x, -v.y, -v.z, -v.w); }
+
+// Geometry of one emitting packet for the overlap-add stage (all block-uniform).
+struct OlaGeom {
+	int Hp, H;          // quarter sizes: Hp = n_prev/4, H = n/4 (= length of the lo / hi halves of D)
+	int shift;          // index in the current frame of the chunk's first sample: n/4 - n_prev/4
+	int lb, lc;         // current frame: left slope begins at lb, has length lc
+	int rbp, pr;        // previous frame, relative to its second half: falling slope begins at rbp, has length pr
+	const float* slL;   // rising slope table of length lc
+	const float* slR;   // rising slope table of length pr (read mirrored)
+};
+
+// Four consecutive output samples j..j+3 (j % 4 == 0):
+//   out = (0 + prev[n_prev/2 + j] * w_prev) + cur[j + shift] * w_cur        (hpp:1008-1017 in gather form)
+// plo = lo half of the previous frame's D, chi = hi half of the current frame's D.
+// Every region boundary is a multiple of 16, so the four samples always share one case.
+__device__ __forceinline__ float4 ola_quad(const OlaGeom& G, const float* __restrict__ plo, const float* __restrict__ chi, int j) {
+	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+	if(j < G.rbp + G.pr) {                             // previous frame present and its window non-zero (rbp+pr <= 2*Hp)
+		// second half of the previous frame: -D[Hp-1-i] for i < Hp, -D[i-Hp] beyond
+		const float4 y = (j < G.Hp) ? rev_neg(*reinterpret_cast<const float4*>(plo + G.Hp - 4 - j))
+		                            : neg4(*reinterpret_cast<const float4*>(plo + j - G.Hp));
+		float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+		if(j >= G.rbp) w = rev4(__ldg(reinterpret_cast<const float4*>(G.slR + G.pr - 4 - (j - G.rbp))));
+		acc.x = __fadd_rn(acc.x, __fmul_rn(y.x, w.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(y.y, w.y));
+		acc.z = __fadd_rn(acc.z, __fmul_rn(y.z, w.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(y.w, w.w));
+	}
+	const int ic = j + G.shift;
+	if(ic >= G.lb) {                                    // current frame present and its window non-zero (ic < 2H always)
+		// first half of the current frame: D[H+i] for i < H, -D[3H-1-i] beyond
+		const float4 y = (ic < G.H) ? *reinterpret_cast<const float4*>(chi + ic)
+		                            : rev_neg(*reinterpret_cast<const float4*>(chi + 2 * G.H - 4 - ic));
+		float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+		if(ic < G.lb + G.lc) w = __ldg(reinterpret_cast<const float4*>(G.slL + ic - G.lb));
+		acc.x = __fadd_rn(acc.x, __fmul_rn(y.x, w.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(y.y, w.y));
+		acc.z = __fadd_rn(acc.z, __fmul_rn(y.z, w.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(y.w, w.w));
+	}
+	return acc;
+}
+
+// scalar version for ragged tails / unaligned destinations / interleaved output
+__device__ __forceinline__ float ola_one(const OlaGeom& G, const float* __restrict__ plo, const float* __restrict__ chi, int j) {
+	float acc = 0.f;
+	if(j < G.rbp + G.pr) {
+		const float y = (j < G.Hp) ? -plo[G.Hp - 1 - j] : -plo[j - G.Hp];
+		const float w = (j >= G.rbp) ? __ldg(G.slR + G.pr - 1 - (j - G.rbp)) : 1.f;
+		acc = __fadd_rn(acc, __fmul_rn(y, w));
+	}
+	const int ic = j + G.shift;
+	if(ic >= G.lb) {
+		const float y = (ic < G.H) ? chi[ic] : -chi[2 * G.H - 1 - ic];
+		const float w = (ic < G.lb + G.lc) ? __ldg(G.slL + ic - G.lb) : 1.f;
+		acc = __fadd_rn(acc, __fmul_rn(y, w));
+	}
+	return acc;
+}
+
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParams P) {
 	extern __shared__ __align__(128) unsigned char smem[];
-	__shared__ __align__(8) uint64_t s_bar[2];
+	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ float s_invdb[256];
+	__shared__ uint8_t s_mode_flag[POV_MAX_MODES], s_mode_map[POV_MAX_MODES];
 
 	const DevBatchView& b = P.b;
 	const DevRun run = P.runs[blockIdx.x];
 	const pov_packet pk0 = b.packets[run.first_packet];
 	const pov_stream st = b.streams[pk0.stream];
-	const DevSetup& su = b.setups[st.setup_id];
-	const int C = (int) su.channels;
-	const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const DevSetup* __restrict__ su = &b.setups[st.setup_id];
+	const int C = (int) su->channels;
+	const int nwarps = kThreads >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t bs0 = su->blocksize[0], bs1 = su->blocksize[1];
+	const DevFloor* __restrict__ floors = su->floors;
+	const DevMapping* __restrict__ mappings = su->mappings;
 
-	// ---- shared memory carve-up (floats): raw[2][slot] | floor[slot] | T[1.125*slot] | D[2][slot] | floor scratch
+	// ---- shared memory carve-up (floats): raw[slot] | T[1.125*slot] | Dlo[2][slot/2] | Dhi[slot/2] | curves | scratch
 	const uint32_t slot = P.slot_floats;
 	float* raw = reinterpret_cast<float*>(smem);
-	float* flo = raw + 2 * (size_t) slot;
-	float2* T = reinterpret_cast<float2*>(flo + slot);
-	float* D = reinterpret_cast<float*>(T) + (size_t) slot + slot / 8;
-	unsigned char* fscr = reinterpret_cast<unsigned char*>(D + 2 * (size_t) slot);
-	FloorScratch S;
-	S.bind(fscr + (size_t) warp * floor_scratch_stride(P.floor_cap), P.floor_cap);
+	float2* T = reinterpret_cast<float2*>(raw + slot);
+	float* Dlo = reinterpret_cast<float*>(T) + (size_t) slot + slot / 8;
+	float* Dhi = Dlo + slot;
+	unsigned char* curves = reinterpret_cast<unsigned char*>(Dhi + slot / 2);
+	unsigned char* fscr = curves + P.curve_bytes;    // per-warp unwrap scratch, only when scratch_cap > 32
 
-	for(int i = threadIdx.x; i < 256; i += blockDim.x) s_invdb[i] = __ldg(&b.inv_db[i]);
+	for(int i = threadIdx.x; i < 256; i += kThreads) s_invdb[i] = __ldg(&b.inv_db[i]);
+	for(int i = threadIdx.x; i < (int) POV_MAX_MODES; i += kThreads) { s_mode_flag[i] = su->mode_blockflag[i]; s_mode_map[i] = su->mode_mapping[i]; }
 	if(threadIdx.x == 0) {
-		mbar_init(&s_bar[0], 1);
-		mbar_init(&s_bar[1], 1);
+		mbar_init(&s_bar, 1);
 		mbar_fence_init();
 	}
 	__syncthreads();
 
 	const uint32_t run_end = run.first_packet + run.n_packets;
-	const uint32_t bs0 = su.blocksize[0], bs1 = su.blocksize[1];
 	const uint32_t gshort = (bs0 == bs1) ? 1u : P.group_short;
 
 	auto make_step = [&](uint32_t first) {
@@ -177,110 +278,123 @@ __global__ void __launch_bounds__(512) k_fused_synth(FusedParams P) {
 		s.flag = 0;
 		if(first >= run_end) return s;
 		const uint32_t mode = b.packets[first].mode;
-		s.flag = su.mode_blockflag[mode];
+		s.flag = s_mode_flag[mode];
 		s.count = 1;
 		if(!s.flag && bs0 != bs1)   // group consecutive short packets of the same mode (same mapping, same floors)
 			while(s.count < gshort && first + s.count < run_end && b.packets[first + s.count].mode == mode) ++s.count;
 		return s;
 	};
-	auto issue_loads = [&](const StepInfo& s, int buf) {     // one elected thread: TMA bulk copies of the step's spectra
-		const uint32_t half = su.blocksize[s.flag] / 2;
+	auto issue_loads = [&](const StepInfo& s) {     // one elected thread: TMA bulk copies of the step's spectra
+		const uint32_t half = (s.flag ? bs1 : bs0) / 2;
 		const uint32_t bytes = (uint32_t) C * half * 4u;
-		mbar_expect_tx(&s_bar[buf], bytes * s.count);
+		mbar_expect_tx(&s_bar, bytes * s.count);
 		for(uint32_t g = 0; g < s.count; ++g)
-			tma_bulk_g2s(raw + (size_t) buf * slot + (size_t) g * C * half, b.spectra + b.spec_off[s.first + g], bytes, &s_bar[buf]);
+			tma_bulk_g2s(raw + (size_t) g * C * half, b.spectra + b.spec_off[s.first + g], bytes, &s_bar);
 	};
 
 	StepInfo cur = make_step(run.first_packet);
-	if(threadIdx.x == 0 && cur.count) issue_loads(cur, 0);
-	uint32_t phase[2] = {0, 0};
-	// overlap carried from the previous step: last packet's D array and geometry
+	if(threadIdx.x == 0 && cur.count) issue_loads(cur);
+	uint32_t phase = 0;
+	// overlap carried from the previous packet: the lo half of its D array and its geometry
 	int prev_valid = 0, prev_n = 0, prev_right = 0;
-	const float* prevD = nullptr;    // D of the previous packet, channel 0 (channels are prev_n/2 apart)
+	const float* prev_lo = nullptr;    // channel 0; channels are prev_n/4 apart
 	int step_idx = 0;
 
 	while(cur.count) {
 		const int buf = step_idx & 1;
 		const StepInfo nxt = make_step(cur.first + cur.count);
-		if(threadIdx.x == 0 && nxt.count) issue_loads(nxt, buf ^ 1);   // prefetch: raw[buf^1] was consumed a step ago
-
 		const uint32_t flag = cur.flag;
-		const int n = (int) su.blocksize[flag], M = n / 2, Q = n / 4;
+		const int n = (int) (flag ? bs1 : bs0), M = n / 2, Q = n / 4;
+		const int log2Q = 31 - __clz(Q);
 		const int npk = (int) cur.count, nf = npk * C;
-		const DevMapping* mp = &su.mappings[su.mode_mapping[b.packets[cur.first].mode]];
-		float* rawb = raw + (size_t) buf * slot;
-		float* Dcur = D + (size_t) buf * slot;
+		const uint32_t mode0 = b.packets[cur.first].mode;
+		const DevMapping* mp = &mappings[s_mode_map[mode0]];
+		float* Dlo_cur = Dlo + (size_t) buf * (slot / 2);
+		const uint32_t cells = (uint32_t) M / 4;
+		const uint32_t fcap = P.floor_cap[flag];
+		const uint32_t curve_stride = CurveV3::bytes(fcap, cells);
 
-		// ---- stage 1: floor curves, one warp per (packet, channel) [x bin slices when warps outnumber curves] ----
-		{
-			const int nsl = (nf < nwarps) ? nwarps / nf : 1;
-			for(int w = warp; w < nf * nsl; w += nwarps) {
-				const int f = w / nsl, sl = w - f * nsl;
-				const int g = f / C, c = f - g * C;
-				const uint32_t p = cur.first + g;
-				const pov_packet pk = b.packets[p];
-				const DevMapping* mpp = &su.mappings[su.mode_mapping[pk.mode]];
-				uint32_t used = pk.floor_used, prop = used;
-				for(uint32_t k = 0; k < mpp->n_couplings; ++k) {   // hpp:1174-1180
-					const uint32_t m = mpp->coupling_mag[k], a = mpp->coupling_ang[k];
+		// ---- stage 1: floor unwrap + curve records, one warp per (packet, channel) curve ----
+		for(int f = warp; f < nf; f += nwarps) {
+			const int g = f / C, c = f - g * C;
+			const uint32_t p = cur.first + g;
+			const pov_packet pk = b.packets[p];
+			CurveV3 Cv;
+			Cv.bind(curves + (size_t) f * curve_stride, fcap);
+			const uint32_t used = pk.floor_used;
+			if(!((used >> c) & 1)) {
+				// no curve decoded: the reference multiplies by its zero-initialised floor buffer if the channel became
+				// "used" through coupling (hpp:1159,1247) and leaves the residue untouched otherwise
+				uint32_t prop = used;
+				for(uint32_t k = 0; k < mp->n_couplings; ++k) {   // hpp:1174-1180
+					const uint32_t m = mp->coupling_mag[k], a = mp->coupling_ang[k];
 					if(((prop >> m) | (prop >> a)) & 1) prop |= (1u << m) | (1u << a);
 				}
-				float* Fo = flo + (size_t) f * M;
-				const int b0 = (M * sl) / nsl, b1 = (M * (sl + 1)) / nsl;
-				if(!((used >> c) & 1)) {
-					// no curve decoded: the reference multiplies by its zero-initialised floor buffer if the channel
-					// became "used" through coupling (hpp:1159,1247), and leaves the residue untouched otherwise
-					const float fill = ((prop >> c) & 1) ? 0.f : 1.f;
-					for(int x = b0 + lane; x < b1; x += 32) Fo[x] = fill;
-					continue;
-				}
-				const DevFloor* F = &su.floors[mpp->floor_of_ch[c]];
-				uint64_t yo = pk.ys_off;
-				for(int cc = 0; cc < c; ++cc)
-					if((used >> cc) & 1) yo += su.floors[mpp->floor_of_ch[cc]].n_posts;
-				uint32_t stt = floor1_unwrap_warp(F, b.ys + yo, S, lane);
-				if(sl == 0) {
-					stt |= floor1_range_check_warp(S, (uint32_t) n, lane);
-					if(stt && lane == 0) atomicOr(&b.status[p], stt);
-				}
-				floor1_render_warp(S, (uint32_t) b0, (uint32_t) b1, lane, [&](uint32_t x, uint32_t y) { Fo[x] = s_invdb[y & 255]; });
+				if(lane == 0) Cv.hdr[0] = ((prop >> c) & 1) ? 2u : 1u;
+				continue;
 			}
+			const DevFloor* F = &floors[mp->floor_of_ch[c]];
+			uint64_t yo = pk.ys_off;
+			for(int cc = 0; cc < c; ++cc)
+				if((used >> cc) & 1) yo += floors[mp->floor_of_ch[cc]].n_posts;
+			uint32_t stt;
+			if(F->n_posts <= 32) {
+				stt = floor1_curve_warp32(F, b.ys + yo, Cv, cells, (uint32_t) n, lane);
+			} else {
+				FloorScratch W;
+				W.bind(fscr + (size_t) warp * floor_scratch_stride(P.scratch_cap), P.scratch_cap);
+				stt = floor1_unwrap_warp(F, b.ys + yo, W, lane);
+				stt |= floor1_range_check_warp(W, (uint32_t) n, lane);
+				const uint32_t ns = *W.nseg;
+				if(lane == 0) Cv.hdr[0] = 0;
+				for(uint32_t base = 0; base < ns; base += 32) {
+					const uint32_t s = base + lane;
+					const bool have = s < ns;
+					const uint32_t x0 = have ? W.segx[s] : 0u, y0 = have ? W.segy[s] : 0u;
+					const uint32_t x1 = (s + 1 < ns) ? W.segx[s + 1] : 0u, y1 = (s + 1 < ns) ? W.segy[s + 1] : 0u;
+					curve_build_warp(Cv, ns, x0, y0, x1, y1, have, base, cells, lane, base == 0);
+				}
+				curve_scan_cells_warp(Cv, cells, lane);
+			}
+			if(stt && lane == 0) atomicOr(&b.status[p], stt);
 		}
-		// ---- wait for this step's spectra (TMA), then everyone sees floor + raw ----
-		mbar_wait(&s_bar[buf], phase[buf]);
-		phase[buf] ^= 1;
+		// ---- wait for this step's spectra (TMA), then everyone sees curves + raw ----
+		mbar_wait(&s_bar, phase);
+		phase ^= 1;
 		__syncthreads();
 
-		// ---- stage 2: coupling + floor multiply + pre-rotation -> T ----
+		// ---- stage 2: floor evaluation + coupling + floor multiply + pre-rotation -> T ----
 		{
-			const int tstride = Q + Q / 8;
-			const float2* rot = su.rot[flag];
+			const float2* rot = su->rot[flag];
+			const int lp = log2Q - 1;
 			switch(C) {
-				case 1: stage_spectral<1>(rawb, flo, T, npk, Q, tstride, rot, mp); break;
-				case 2: stage_spectral<2>(rawb, flo, T, npk, Q, tstride, rot, mp); break;
-				case 3: stage_spectral<3>(rawb, flo, T, npk, Q, tstride, rot, mp); break;
-				case 4: stage_spectral<4>(rawb, flo, T, npk, Q, tstride, rot, mp); break;
-				case 5: stage_spectral<5>(rawb, flo, T, npk, Q, tstride, rot, mp); break;
-				case 6: stage_spectral<6>(rawb, flo, T, npk, Q, tstride, rot, mp); break;
-				case 7: stage_spectral<7>(rawb, flo, T, npk, Q, tstride, rot, mp); break;
-				default: stage_spectral<8>(rawb, flo, T, npk, Q, tstride, rot, mp); break;
+				case 1: stage_spectral<1>(raw, curves, curve_stride, fcap, s_invdb, T, npk, lp, rot, mp); break;
+				case 2: stage_spectral<2>(raw, curves, curve_stride, fcap, s_invdb, T, npk, lp, rot, mp); break;
+				case 3: stage_spectral<3>(raw, curves, curve_stride, fcap, s_invdb, T, npk, lp, rot, mp); break;
+				case 4: stage_spectral<4>(raw, curves, curve_stride, fcap, s_invdb, T, npk, lp, rot, mp); break;
+				case 5: stage_spectral<5>(raw, curves, curve_stride, fcap, s_invdb, T, npk, lp, rot, mp); break;
+				case 6: stage_spectral<6>(raw, curves, curve_stride, fcap, s_invdb, T, npk, lp, rot, mp); break;
+				case 7: stage_spectral<7>(raw, curves, curve_stride, fcap, s_invdb, T, npk, lp, rot, mp); break;
+				default: stage_spectral<8>(raw, curves, curve_stride, fcap, s_invdb, T, npk, lp, rot, mp); break;
 			}
 		}
 		__syncthreads();
+		// the spectra buffer and the curve blocks are free again: prefetch the next step's spectra behind stages 3-4
+		if(threadIdx.x == 0 && nxt.count) issue_loads(nxt);
 
-		// ---- stage 3: FFT passes + post-rotation -> D ----
+		// ---- stage 3: FFT passes + post-rotation -> D (lo / hi halves) ----
 		{
-			const float2* rot = su.rot[flag];
-			const float2* W = su.fft[flag];
+			const float2* rot = su->rot[flag];
+			const float2* TWP = su->fftp[flag];
 			switch(Q) {
-				case 16:   stage_fft<16>(T, Dcur, nf, rot, W); break;
-				case 32:   stage_fft<32>(T, Dcur, nf, rot, W); break;
-				case 64:   stage_fft<64>(T, Dcur, nf, rot, W); break;
-				case 128:  stage_fft<128>(T, Dcur, nf, rot, W); break;
-				case 256:  stage_fft<256>(T, Dcur, nf, rot, W); break;
-				case 512:  stage_fft<512>(T, Dcur, nf, rot, W); break;
-				case 1024: stage_fft<1024>(T, Dcur, nf, rot, W); break;
-				default:   stage_fft<2048>(T, Dcur, nf, rot, W); break;
+				case 16:   stage_fft<16>(T, Dlo_cur, Dhi, nf, rot, TWP); break;
+				case 32:   stage_fft<32>(T, Dlo_cur, Dhi, nf, rot, TWP); break;
+				case 64:   stage_fft<64>(T, Dlo_cur, Dhi, nf, rot, TWP); break;
+				case 128:  stage_fft<128>(T, Dlo_cur, Dhi, nf, rot, TWP); break;
+				case 256:  stage_fft<256>(T, Dlo_cur, Dhi, nf, rot, TWP); break;
+				case 512:  stage_fft<512>(T, Dlo_cur, Dhi, nf, rot, TWP); break;
+				case 1024: stage_fft<1024>(T, Dlo_cur, Dhi, nf, rot, TWP); break;
+				default:   stage_fft<2048>(T, Dlo_cur, Dhi, nf, rot, TWP); break;
 			}
 		}
 		__syncthreads();
@@ -289,88 +403,119 @@ __global__ void __launch_bounds__(512) k_fused_synth(FusedParams P) {
 		for(int g = 0; g < npk; ++g) {
 			const uint32_t p = cur.first + g;
 			const pov_packet pk = b.packets[p];
-			int lc, rc;
-			slope_lengths_f(su, flag, pk.window_flags, lc, rc);
-			const float* Dc = Dcur + (size_t) g * C * M;
-			const bool emits = prev_valid && pk.emit_frames > 0 && p != st.first_packet && !(run.halo && p == run.first_packet);
+			// hpp:844-847: short blocks always use blocksize0 slopes; long blocks follow their own prev/next flags
+			const int lc = (int) ((flag && (pk.window_flags & 1)) ? bs1 : bs0) / 2;
+			const int rc = (int) ((flag && (pk.window_flags & 2)) ? bs1 : bs0) / 2;
+			const float* cur_lo = Dlo_cur + (size_t) g * C * Q;
+			const float* cur_hi = Dhi + (size_t) g * C * Q;
+			const bool emits = prev_valid && pk.emit_frames > 0 && p != st.first_packet;
 			if(emits) {
-				const int np = prev_n, Mp = np / 2;
-				const float* slL = su.slope[lc == (int) bs1 / 2 ? 1 : 0];
-				const float* slR = su.slope[prev_right == (int) bs1 / 2 ? 1 : 0];
-				const int shift = n / 4 - np / 4;
-				const int lb = n / 4 - lc / 2;
-				const int rb = np - np / 4 - prev_right / 2;
+				OlaGeom G;
+				G.Hp = prev_n / 4; G.H = Q;
+				G.shift = Q - prev_n / 4;
+				G.lc = lc; G.lb = Q - lc / 2;
+				G.pr = prev_right; G.rbp = prev_n / 4 - prev_right / 2;
+				G.slL = su->slope[lc == (int) bs1 / 2 ? 1 : 0];
+				G.slR = su->slope[prev_right == (int) bs1 / 2 ? 1 : 0];
 				const uint32_t emit = pk.emit_frames;
-				const uint32_t total = emit * (uint32_t) C;
 				const bool planar = (b.pcm_layout == POV_PCM_PLANAR);
-				for(uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
-					uint32_t c, j;
-					if(planar) { c = e / emit; j = e - c * emit; } else { j = e / (uint32_t) C; c = e - j * (uint32_t) C; }
-					float acc = 0.f;
-					const int ip = Mp + (int) j;
-					if(ip < np) {
-						float wv;
-						if(ip < rb) wv = 1.f;
-						else if(ip < rb + prev_right) wv = __ldg(&slR[prev_right - 1 - (ip - rb)]);
-						else wv = 0.f;
-						acc = __fadd_rn(acc, __fmul_rn(frame_from_D(prevD + (size_t) c * Mp, Mp, ip), wv));
+				const uint64_t chan_base = st.pcm_base + pk.pcm_off;
+				if(planar && (emit & 3u) == 0 && ((chan_base | st.pcm_frames) & 3ull) == 0) {
+					// 128-bit path: one thread per 4 consecutive frames of one channel
+					const uint32_t quads = emit >> 2;
+					for(int c = 0; c < C; ++c) {
+						const float* plo = prev_lo + (size_t) c * G.Hp;
+						const float* chi = cur_hi + (size_t) c * Q;
+						float* dst = b.pcm + chan_base + (uint64_t) c * st.pcm_frames;
+						for(uint32_t qd = threadIdx.x; qd < quads; qd += kThreads)
+							*reinterpret_cast<float4*>(dst + 4 * qd) = ola_quad(G, plo, chi, (int) (4 * qd));
 					}
-					const int ic = (int) j + shift;
-					if(ic >= 0 && ic < n) {
-						float wv;
-						if(ic < lb) wv = 0.f;
-						else if(ic < lb + lc) wv = __ldg(&slL[ic - lb]);
-						else wv = 1.f;      // ic < M always: the right slope of the current frame is never reached here
-						acc = __fadd_rn(acc, __fmul_rn(frame_from_D(Dc + (size_t) c * M, M, ic), wv));
+				} else {
+					const uint32_t total = emit * (uint32_t) C;
+					for(uint32_t e = threadIdx.x; e < total; e += kThreads) {
+						uint32_t c, j;
+						if(planar) { c = e / emit; j = e - c * emit; } else { j = e / (uint32_t) C; c = e - j * (uint32_t) C; }
+						const float v = ola_one(G, prev_lo + (size_t) c * G.Hp, cur_hi + (size_t) c * Q, (int) j);
+						const uint64_t fidx = pk.pcm_off + j;
+						const uint64_t o = planar ? st.pcm_base + (uint64_t) c * st.pcm_frames + fidx : st.pcm_base + fidx * (uint64_t) C + c;
+						b.pcm[o] = v;
 					}
-					const uint64_t fidx = pk.pcm_off + j;
-					const uint64_t o = planar ? st.pcm_base + (uint64_t) c * st.pcm_frames + fidx : st.pcm_base + fidx * (uint64_t) C + c;
-					b.pcm[o] = acc;
 				}
 			}
-			prev_valid = 1; prev_n = n; prev_right = rc; prevD = Dc;
+			prev_valid = 1; prev_n = n; prev_right = rc; prev_lo = cur_lo;
 		}
-		// No barrier needed here: the next step only writes flo/T/raw before its own barriers, D[buf^1] not before
-		// three barriers from now.
+		// No barrier needed here: the next step writes curves/T before its own barriers; Dhi and Dlo[buf^1] are not
+		// written again before two more barriers.
 		cur = nxt;
 		++step_idx;
 	}
 }
 
-cudaError_t launch_fused(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t max_channels,
-                         uint32_t max_blocksize, uint32_t min_blocksize, uint32_t floor_cap, cudaStream_t st, uint64_t* launches) {
-	if(n_runs == 0) return cudaSuccess;
-	FusedParams P;
-	P.b = b;
-	P.runs = runs;
-	P.floor_cap = floor_cap;
-	P.group_short = max_blocksize / min_blocksize;
-	if(P.group_short > 8) P.group_short = 8;
-	if(P.group_short < 1) P.group_short = 1;
-	P.slot_floats = max_channels * (max_blocksize / 2);
-	// one 8-point work item per thread per pass for the long block: C * n/32 threads, within [128, 512]
-	uint32_t threads = max_channels * (max_blocksize / 32);
-	threads = (threads + 31u) & ~31u;
-	if(threads < 128) threads = 128;
-	if(threads > 512) threads = 512;
-	const size_t floats = (size_t) P.slot_floats * 2 + P.slot_floats + (P.slot_floats + P.slot_floats / 8) + (size_t) P.slot_floats * 2;
-	const size_t smem = floats * sizeof(float) + (size_t) (threads / 32) * floor_scratch_stride(floor_cap) + 128;
-	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-	cudaError_t e = cudaFuncSetAttribute(k_fused_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	if(e != cudaSuccess) return e;
-	k_fused_synth<<<n_runs, threads, smem, st>>>(P);
-	if(launches) ++*launches;
-	return cudaGetLastError();
+static uint32_t fused_threads(uint32_t max_channels, uint32_t max_blocksize) {
+	// one 8-point work item per thread per pass for the long block: C * n/32 threads -> 128, 256 or 512
+	const uint32_t want = max_channels * (max_blocksize / 32);
+	if(want <= 128) return 128;
+	if(want <= 256) return 256;
+	return 512;
 }
 
-size_t fused_smem_bytes(uint32_t max_channels, uint32_t max_blocksize, uint32_t floor_cap) {
-	uint32_t threads = max_channels * (max_blocksize / 32);
-	threads = (threads + 31u) & ~31u;
-	if(threads < 128) threads = 128;
-	if(threads > 512) threads = 512;
-	const size_t slot = (size_t) max_channels * (max_blocksize / 2);
-	const size_t floats = slot * 2 + slot + (slot + slot / 8) + slot * 2;
-	return floats * sizeof(float) + (size_t) (threads / 32) * floor_scratch_stride(floor_cap) + 128;
+static void fused_layout(uint32_t max_channels, uint32_t max_blocksize, uint32_t min_blocksize, const uint32_t floor_cap[2],
+                         FusedParams& P, uint32_t& threads, size_t& smem) {
+	threads = fused_threads(max_channels, max_blocksize);
+	uint32_t group = max_blocksize / min_blocksize;
+	if(group > 8) group = 8;
+	if(group < 1) group = 1;
+	P.group_short = group;
+	P.floor_cap[0] = floor_cap[0]; P.floor_cap[1] = floor_cap[1];
+	P.scratch_cap = floor_cap[0] > floor_cap[1] ? floor_cap[0] : floor_cap[1];
+	P.slot_floats = max_channels * (max_blocksize / 2);
+	const size_t long_bytes = (size_t) max_channels * CurveV3::bytes(floor_cap[1], max_blocksize / 8);
+	const size_t short_bytes = (size_t) group * max_channels * CurveV3::bytes(floor_cap[0], min_blocksize / 8);
+	// a setup with blocksize0 == blocksize1 runs every packet as a "short" step of one packet with the long geometry
+	const size_t same_bytes = (size_t) max_channels * CurveV3::bytes(P.scratch_cap, max_blocksize / 8);
+	size_t cb = long_bytes > short_bytes ? long_bytes : short_bytes;
+	if(same_bytes > cb) cb = same_bytes;
+	P.curve_bytes = (uint32_t) ((cb + 15) & ~(size_t) 15);
+	const size_t slot = P.slot_floats;
+	const size_t floats = slot + (slot + slot / 8) + slot + slot / 2;       // raw | T | Dlo[2] | Dhi
+	smem = floats * sizeof(float) + P.curve_bytes + 128;
+	if(P.scratch_cap > 32) smem += (size_t) (threads / 32) * floor_scratch_stride(P.scratch_cap);
+}
+
+size_t fused_smem_bytes(uint32_t max_channels, uint32_t max_blocksize, uint32_t min_blocksize, const uint32_t floor_cap[2]) {
+	FusedParams P;
+	uint32_t threads;
+	size_t smem;
+	fused_layout(max_channels, max_blocksize, min_blocksize, floor_cap, P, threads, smem);
+	return smem;
+}
+
+cudaError_t launch_fused(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t max_channels,
+                         uint32_t max_blocksize, uint32_t min_blocksize, const uint32_t floor_cap[2], cudaStream_t st, uint64_t* launches) {
+	if(n_runs == 0) return cudaSuccess;
+	FusedParams P;
+	uint32_t threads;
+	size_t smem;
+	fused_layout(max_channels, max_blocksize, min_blocksize, floor_cap, P, threads, smem);
+	P.b = b;
+	P.runs = runs;
+	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+	cudaError_t e;
+	if(threads == 128) {
+		e = cudaFuncSetAttribute(k_fused_synth<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		if(e != cudaSuccess) return e;
+		k_fused_synth<128, 6><<<n_runs, 128, smem, st>>>(P);
+	} else if(threads == 256) {
+		e = cudaFuncSetAttribute(k_fused_synth<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		if(e != cudaSuccess) return e;
+		k_fused_synth<256, 3><<<n_runs, 256, smem, st>>>(P);
+	} else {
+		e = cudaFuncSetAttribute(k_fused_synth<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		if(e != cudaSuccess) return e;
+		k_fused_synth<512, 1><<<n_runs, 512, smem, st>>>(P);
+	}
+	if(launches) ++*launches;
+	return cudaGetLastError();
 }
 
 }  // namespace pov

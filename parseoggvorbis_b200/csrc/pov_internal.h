@@ -19,6 +19,10 @@ struct DevFloor {
 	uint8_t  hi[POV_MAX_POSTS];        // high_neighbor index
 	uint8_t  level[POV_MAX_POSTS];     // 0 for posts 0,1; else 1+max(level[lo],level[hi])
 	uint8_t  sorted_idx[POV_MAX_POSTS];// ascending-x order -> post index
+	// prediction constants of post i (>= 2): predicted = y_lo +/- floor(|y_hi-y_lo| * dxn / adx)   (Utils.hpp:122-137)
+	uint16_t dxn[POV_MAX_POSTS];       // xs[i] - xs[lo]
+	uint16_t adx[POV_MAX_POSTS];       // xs[hi] - xs[lo]
+	float    rinv[POV_MAX_POSTS];      // 1.0f / adx
 };
 
 struct DevMapping {
@@ -60,6 +64,9 @@ struct DevSetup {
 	const float2* rot[2];
 	// FFT twiddles W_Q^e = exp(-2*pi*i*e/Q), e < Q, Q = blocksize/4
 	const float2* fft[2];
+	// The same twiddles laid out per pass for the fused kernel: for every DIF pass (first small-radix pass, then
+	// the radix-8 passes with L >= 64) the 8 (or 4 / 1) factors of butterfly j are contiguous (fft_core.cuh PassTables)
+	const float2* fftp[2];
 };
 
 // Work item of the fused kernel: a run of consecutive packets of one stream. The first packet of a run that is
