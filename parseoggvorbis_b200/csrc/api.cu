@@ -98,7 +98,7 @@ extern "C" int pov_ctx_create(int device, pov_ctx** out, const char** error_out)
 	if((e = dev_upload((float**) &ctx->d_inv_db, table, 256, ctx->stream)) != cudaSuccess) return fail("upload inverse dB table", e);
 	if((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("sync", e);
 	const char* rl = getenv("POV_RUN_LEN");
-	ctx->run_len = rl ? (uint32_t) std::max(2, atoi(rl)) : 0;
+	ctx->run_len = rl ? (uint32_t) std::min(64, std::max(2, atoi(rl))) : 0;   // the fused kernel keeps <= 65 descriptors per run
 	ctx->err[0] = 0;
 	*out = ctx.release();
 	return POV_OK;
@@ -114,7 +114,7 @@ extern "C" void pov_ctx_destroy(pov_ctx* ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	for(auto& s : ctx->setups) free_setup(s);
-	for(auto& kv : ctx->blk_tables) { cudaFree((void*) kv.second.d_rot); cudaFree((void*) kv.second.d_fft); cudaFree((void*) kv.second.d_fftp); cudaFree((void*) kv.second.d_slope); }
+	for(auto& kv : ctx->blk_tables) { cudaFree((void*) kv.second.d_rot); cudaFree((void*) kv.second.d_fft); cudaFree((void*) kv.second.d_fftp); cudaFree((void*) kv.second.d_fft8); cudaFree((void*) kv.second.d_slope); }
 	cudaFree((void*) ctx->d_setups);
 	cudaFree((void*) ctx->d_inv_db);
 	ctx->mdct_in.release(); ctx->mdct_out.release();
@@ -131,15 +131,19 @@ static int get_block_tables(pov_ctx* ctx, uint32_t n, BlockTables** out) {
 	auto it = ctx->blk_tables.find(n);
 	if(it != ctx->blk_tables.end()) { *out = &it->second; return POV_OK; }
 	BlockTables t;
-	std::vector<float> rot, fft, fftp, slope;
+	std::vector<float> rot, fft, fftp, fft8, slope;
 	make_rotation(n, rot);
 	make_fft_twiddles(n, fft);
 	make_fft_pass_tables(n, fftp);
+	make_fft_r8_tables(n, fft8);
+	make_rotation_consts(n, t.c1, t.c6);
+	t.fft8_count = (uint32_t) (fft8.size() / 2);
 	make_window_slope(n / 2, slope);
 	t.h_slope = slope;
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_rot, rot.data(), rot.size(), ctx->stream));
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_fft, fft.data(), fft.size(), ctx->stream));
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_fftp, fftp.data(), fftp.size(), ctx->stream));
+	CUDA_TRY(ctx, dev_upload((float**) &t.d_fft8, fft8.data(), fft8.size(), ctx->stream));
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_slope, slope.data(), slope.size(), ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	auto ins = ctx->blk_tables.emplace(n, std::move(t));
@@ -311,6 +315,11 @@ extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id
 	d.rot[0] = t0->d_rot; d.rot[1] = t1->d_rot;
 	d.fft[0] = t0->d_fft; d.fft[1] = t1->d_fft;
 	d.fftp[0] = t0->d_fftp; d.fftp[1] = t1->d_fftp;
+	d.fft8[0] = t0->d_fft8; d.fft8[1] = t1->d_fft8;
+	d.fft8_count[0] = t0->fft8_count; d.fft8_count[1] = t1->fft8_count;
+	d.rotc1[0] = make_float2(t0->c1[0], t0->c1[1]); d.rotc1[1] = make_float2(t1->c1[0], t1->c1[1]);
+	d.rotc6[0] = make_float2(t0->c6[0], t0->c6[1]); d.rotc6[1] = make_float2(t1->c6[0], t1->c6[1]);
+	rec.table_float2 = t0->fft8_count + t1->fft8_count + s->blocksize[0] / 8 + s->blocksize[1] / 8;
 	CUDA_TRY(ctx, dev_upload((float**) &rec.d_vq, vq_all.data(), vq_all.size(), ctx->stream));
 	for(uint32_t i = 0; i < s->n_codebooks; ++i)
 		if(cbs[i].lookup_type != 0) cbs[i].vq = rec.d_vq + vq_off[i];
@@ -384,6 +393,8 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	h->spec_off.resize(P); h->stage_off.resize(P); h->pk_n.resize(P); h->pk_setup.resize(P);
 	h->runs.clear();
 	uint32_t maxC = 1, maxbs = 64, minbs = 8192, maxposts = 2, res_smem = 0, posts_cls[2] = {2, 2};
+	bool only_std = true;
+	uint32_t table_float2 = 0;
 	uint64_t dense_floats = 0, stage_floats = 0, expect_first = 0;
 	const uint64_t payload_floats = b->payload_bytes / 4;
 	uint32_t run_len = ctx->run_len;
@@ -403,6 +414,8 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 		if(st.pcm_base + st.pcm_frames * C > b->pcm_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: stream %u: PCM region exceeds pcm_floats", si);
 		maxC = std::max(maxC, C); maxbs = std::max(maxbs, su.blocksize[1]); minbs = std::min(minbs, su.blocksize[0]);
 		maxposts = std::max(maxposts, su.max_posts); res_smem = std::max(res_smem, su.res_smem);
+		if(su.blocksize[0] != 256 || su.blocksize[1] != 2048) only_std = false;
+		table_float2 = std::max(table_float2, su.table_float2);
 		posts_cls[0] = std::max(posts_cls[0], su.posts_cls[0]); posts_cls[1] = std::max(posts_cls[1], su.posts_cls[1]);
 		uint32_t n_prev = 0;
 		for(uint32_t k = 0; k < st.n_packets; ++k) {
@@ -475,9 +488,11 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	h->floor_cap = (maxposts + 3u) & ~3u;
 	h->floor_cap_cls[0] = (posts_cls[0] + 3u) & ~3u; h->floor_cap_cls[1] = (posts_cls[1] + 3u) & ~3u;
 	h->res_smem = res_smem;
+	h->only_256_2048 = only_std && b->n_streams > 0;
+	h->table_float2 = table_float2;
 	h->stage_floats = stage_floats;
 	h->dense_floats = dense_floats;
-	h->fused_ok = fused_smem_bytes(maxC, maxbs, h->min_blocksize, h->floor_cap_cls) <= 227 * 1024;
+	h->fused_ok = fused_smem_bytes(maxC, maxbs, h->min_blocksize, h->floor_cap_cls, h->table_float2) <= 227 * 1024;
 
 	// ---- device copies ----
 	cudaStream_t st = ctx->stream;
@@ -565,7 +580,7 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
 	int rc = run_residue_if_needed(ctx, h, v);
 	if(rc) return rc;
 	CUDA_TRY(ctx, launch_fused(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), h->max_channels, h->max_blocksize,
-	                           h->min_blocksize, h->floor_cap_cls, ctx->stream, &ctx->launches));
+	                           h->min_blocksize, h->floor_cap_cls, h->table_float2, h->only_256_2048, ctx->stream, &ctx->launches));
 	return POV_OK;
 }
 

@@ -22,6 +22,9 @@ struct BlockTables {              // per blocksize n: DCT-IV rotation, FFT twidd
 	const float2* d_rot = nullptr;
 	const float2* d_fft = nullptr;
 	const float2* d_fftp = nullptr;
+	const float2* d_fft8 = nullptr;
+	uint32_t fft8_count = 0;
+	float c1[2] = {1, 0}, c6[2] = {1, 0};
 	const float*  d_slope = nullptr;
 	std::vector<float> h_slope;
 };
@@ -30,6 +33,7 @@ struct SetupRec {
 	uint32_t channels = 0, sample_rate = 0, blocksize[2] = {0, 0};
 	uint32_t n_modes = 0, entry_bits = 16, max_posts = 2, res_smem = 0;
 	uint32_t posts_cls[2] = {2, 2};   // largest floor (posts) reachable from short / long modes
+	uint32_t table_float2 = 0;        // float2 slots of the fused kernel's shared-memory tables for this setup
 	uint8_t mode_blockflag[POV_MAX_MODES] = {0};
 	uint8_t mode_mapping[POV_MAX_MODES] = {0};
 	std::vector<DevFloor> floors_host;
@@ -65,7 +69,8 @@ struct pov_batch_handle {
 	uint64_t pcm_floats = 0, stage_floats = 0, dense_floats = 0;
 	uint32_t max_channels = 1, max_blocksize = 64, min_blocksize = 64, floor_cap = 4, res_smem = 0;
 	uint32_t floor_cap_cls[2] = {4, 4};
-	bool fused_ok = true, staged_ready = false;
+	uint32_t table_float2 = 0;
+	bool fused_ok = true, staged_ready = false, only_256_2048 = false;
 	std::vector<uint64_t> spec_off, stage_off;
 	std::vector<uint32_t> pk_n, pk_setup;
 	std::vector<DevRun> runs;

@@ -294,6 +294,43 @@ __device__ __forceinline__ void pass_last_to_D_p(const float2* __restrict__ T, i
 	}
 }
 
+// ---- compact radix-8 tables held in SHARED memory by the fused kernel (host: make_fft_r8_tables) -----------------
+template <int Q> struct Tw8Tables {
+	static constexpr int kL1 = PassTables<Q>::kL1;
+	static __host__ __device__ constexpr int offset(int L) {         // float2 offset of the pass of length L
+		int o = 0;
+		for(int l = kL1; l > L; l /= 8) o += l / 2;                   // (l/8) butterflies x 4 factors
+		return o;
+	}
+};
+
+// Radix-8 pass with the factors W^j..W^4j read from shared memory and W^5j..W^7j formed by one multiplication each.
+template <int Q, int L>
+__device__ __forceinline__ void pass_radix8_s(float2* __restrict__ T, int t, const float2* __restrict__ tw8) {
+	constexpr int s = L / 8, ps = s + s / 8;
+	const int blk = t / s, j = t - blk * s;
+	const int base = blk * L + j;
+	float2* p = T + base + (base >> 3);
+	float2 a[8];
+#pragma unroll
+	for(int m = 0; m < 8; ++m) a[m] = p[m * ps];
+	constexpr int kOff = Tw8Tables<Q>::offset(L);
+	const float4* tw = reinterpret_cast<const float4*>(tw8 + kOff + j * 4);
+	const float4 w12 = tw[0], w34 = tw[1];
+	dft8(a);
+	const float2 w1 = make_float2(w12.x, w12.y), w2 = make_float2(w12.z, w12.w);
+	const float2 w3 = make_float2(w34.x, w34.y), w4 = make_float2(w34.z, w34.w);
+	a[1] = cmul(a[1], w1);
+	a[2] = cmul(a[2], w2);
+	a[3] = cmul(a[3], w3);
+	a[4] = cmul(a[4], w4);
+	a[5] = cmul(a[5], cmul(w4, w1));
+	a[6] = cmul(a[6], cmul(w4, w2));
+	a[7] = cmul(a[7], cmul(w4, w3));
+#pragma unroll
+	for(int k = 0; k < 8; ++k) p[k * ps] = a[k];
+}
+
 // Frame sample y[m] (m < n = 2M) from the D array of that frame.
 __device__ __forceinline__ float frame_from_D(const float* __restrict__ D, int M, int m) {
 	if(m < M / 2) return D[m + M / 2];

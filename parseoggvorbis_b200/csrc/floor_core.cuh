@@ -201,7 +201,9 @@ __device__ __forceinline__ void curve_build_warp(const CurveV3& Cv, uint32_t nse
 		else {
 			const bool down = y1 < y0;
 			const uint32_t ady = down ? y0 - y1 : y1 - y0, adx = x1 - x0;
-			const uint64_t m = (((uint64_t) ady << 32) + adx - 1) / adx;
+			// any m in [v, v+1), v = 2^32*ady/adx, is exact (see header); the rounded-up double quotient (<= 2^-12 above v)
+			// plus 0 or the ceil conversion stays inside that interval
+			const uint64_t m = __double2ull_ru(__ddiv_ru((double) ady * 4294967296.0, (double) adx));
 			r.x01 = x0 | (x1 << 16); r.y0s = y0 | (down ? 0x80000000u : 0u);
 			r.m_lo = (uint32_t) m; r.m_hi = (uint32_t) (m >> 32);
 		}
@@ -213,23 +215,37 @@ __device__ __forceinline__ void curve_build_warp(const CurveV3& Cv, uint32_t nse
 	}
 }
 
-// inclusive max-scan of the cell index (each cell ends up holding the segment that contains its first bin)
+// inclusive max-scan of the cell index (each cell ends up holding the segment that contains its first bin).
+// Four cells per 32-bit word, byte-wise SIMD max (__vmaxu4); cells % 4 == 0.
+__device__ __forceinline__ uint32_t bytes_prefix_max(uint32_t v) {      // little-endian: byte i = max(byte 0..i)
+	v = __vmaxu4(v, v << 8);
+	v = __vmaxu4(v, v << 16);
+	return v;
+}
 __device__ __forceinline__ void curve_scan_cells_warp(const CurveV3& Cv, uint32_t cells, int lane) {
 	__syncwarp();
-	const uint32_t per = (cells + 31) / 32;
-	const uint32_t b = lane * per, e = min(b + per, cells);
-	uint32_t run = 0;
-	for(uint32_t i = b; i < e; ++i) run = max(run, (uint32_t) Cv.idx[i]);
-	uint32_t incl = run;
+	uint32_t* w = reinterpret_cast<uint32_t*>(Cv.idx);
+	const uint32_t words = cells / 4;
+	for(uint32_t base = 0, carry = 0; base < words; base += 64) {     // two words per lane per round
+		const uint32_t i0 = base + 2 * lane;
+		uint32_t a = (i0 < words) ? w[i0] : 0u, b = (i0 + 1 < words) ? w[i0 + 1] : 0u;
+		a = bytes_prefix_max(a);
+		b = bytes_prefix_max(b);
+		b = __vmaxu4(b, (a >> 24) * 0x01010101u);
+		uint32_t tot = b >> 24, incl = tot;
 #pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-		if(lane >= o) incl = max(incl, v);
+		for(int o = 1; o < 32; o <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+			if(lane >= o) incl = max(incl, v);
+		}
+		uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
+		if(lane == 0) before = 0;
+		before = max(before, carry);
+		const uint32_t bc = before * 0x01010101u;
+		if(i0 < words) w[i0] = __vmaxu4(a, bc);
+		if(i0 + 1 < words) w[i0 + 1] = __vmaxu4(b, bc);
+		carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
 	}
-	uint32_t carry = __shfl_up_sync(0xffffffffu, incl, 1);
-	if(lane == 0) carry = 0;
-	run = carry;
-	for(uint32_t i = b; i < e; ++i) { run = max(run, (uint32_t) Cv.idx[i]); Cv.idx[i] = (uint8_t) run; }
 	__syncwarp();
 }
 
@@ -327,6 +343,24 @@ __device__ __forceinline__ float2 curve_pair(const CurveV3& Cv, uint32_t x, cons
 		out.y = invdb[y & 255];
 	}
 	return out;
+}
+
+// Four consecutive bins x..x+3 (x % 4 == 0: the first bin of an index cell) as inverse-dB table values.
+__device__ __forceinline__ float4 curve_quad(const CurveV3& Cv, uint32_t x, const float* __restrict__ invdb) {
+	uint32_t s = Cv.idx[x >> 2];
+	uint4 r = *reinterpret_cast<const uint4*>(&Cv.rec[s]);
+	float out[4];
+#pragma unroll
+	for(int bb = 0; bb < 4; ++bb) {
+		const uint32_t xb = x + bb;
+		if(bb > 0) while(xb >= (r.x >> 16)) r = *reinterpret_cast<const uint4*>(&Cv.rec[++s]);
+		const uint32_t k = xb - (r.x & 0xFFFFu);
+		const uint32_t q = __umulhi(k, r.z) + k * r.w;
+		const uint32_t y0 = r.y & 0xFFFFu;
+		const uint32_t y = (r.y >> 31) ? y0 - q : y0 + q;
+		out[bb] = invdb[y & 255];
+	}
+	return make_float4(out[0], out[1], out[2], out[3]);
 }
 
 }  // namespace pov

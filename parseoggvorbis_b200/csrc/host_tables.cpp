@@ -95,6 +95,30 @@ void make_fft_pass_tables(uint32_t n, std::vector<float>& out) {
 	if(out.empty()) { out.push_back(1.f); out.push_back(0.f); }
 }
 
+// Layout must match Tw8Tables<Q> in fft_core.cuh: radix-8 passes in execution order (L = L1, L1/8, ... >= 64), per
+// butterfly j the four factors W_L^(j*1..4).
+void make_fft_r8_tables(uint32_t n, std::vector<float>& out) {
+	const uint32_t Q = n / 4;
+	uint32_t log2q = 0;
+	while((1u << log2q) < Q) ++log2q;
+	const uint32_t r0 = (log2q % 3 == 0) ? 8 : (log2q % 3 == 1) ? 2 : 4;
+	out.clear();
+	for(uint32_t L = (r0 == 8) ? Q : Q / r0; L >= 64; L /= 8)
+		for(uint32_t j = 0; j < L / 8; ++j)
+			for(uint32_t k = 1; k <= 4; ++k) {
+				const double a = -2.0 * M_PI * (double) (j * k) / (double) L;
+				out.push_back((float) cos(a));
+				out.push_back((float) sin(a));
+			}
+	if(out.empty()) { out.assign(8, 0.f); }
+}
+
+void make_rotation_consts(uint32_t n, float c1[2], float c6[2]) {
+	const double M = n / 2;
+	c1[0] = (float) cos(-M_PI / M); c1[1] = (float) sin(-M_PI / M);
+	c6[0] = (float) cos(M_PI * 6.0 / (8.0 * M)); c6[1] = (float) sin(M_PI * 6.0 / (8.0 * M));
+}
+
 // Neighbours (src/Utils.hpp:60-118) depend on the X list only, so they are found once here instead of once per
 // packet and post as in the reference (hpp:532-533). level[] orders the posts so that a post's two neighbours
 // are final before it is unwrapped; sorted_idx is the ascending-x order of hpp:458-469.

@@ -20,6 +20,9 @@ void make_rotation(uint32_t n, std::vector<float>& out_re_im);
 void make_fft_twiddles(uint32_t n, std::vector<float>& out_re_im);
 // per-pass packed twiddles (layout: fft_core.cuh PassTables<Q>)
 void make_fft_pass_tables(uint32_t n, std::vector<float>& out_re_im);
+// compact radix-8 pass tables (layout: fft_core.cuh Tw8Tables<Q>) and the rotation helper constants
+void make_fft_r8_tables(uint32_t n, std::vector<float>& out_re_im);
+void make_rotation_consts(uint32_t n, float c1[2], float c6[2]);
 // floor1 derived tables. Returns false (with msg) when the X list is not usable.
 bool make_floor_tables(const pov_floor1& in, DevFloor& out, std::string& msg);
 

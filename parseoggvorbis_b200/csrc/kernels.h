@@ -37,9 +37,11 @@ cudaError_t launch_residue_apply(const DevBatchView& b, float* spectra_out, size
 cudaError_t launch_staged(const DevBatchView& b, const DevStageBuffers& sb, uint32_t max_channels, cudaStream_t st,
                           uint64_t* launches);
 cudaError_t launch_fused(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t max_channels,
-                         uint32_t max_blocksize, uint32_t min_blocksize, const uint32_t floor_cap[2], cudaStream_t st,
-                         uint64_t* launches);
-size_t fused_smem_bytes(uint32_t max_channels, uint32_t max_blocksize, uint32_t min_blocksize, const uint32_t floor_cap[2]);
+                         uint32_t max_blocksize, uint32_t min_blocksize, const uint32_t floor_cap[2], uint32_t table_float2,
+                         bool only_256_2048,
+                         cudaStream_t st, uint64_t* launches);
+size_t fused_smem_bytes(uint32_t max_channels, uint32_t max_blocksize, uint32_t min_blocksize, const uint32_t floor_cap[2],
+                        uint32_t table_float2);
 cudaError_t launch_mdct_backward(const DevSetup* dummy, uint32_t n, uint64_t count, const float* in, float* out,
                                  const float2* rot, const float2* fft, cudaStream_t st, uint64_t* launches);
 

@@ -67,6 +67,13 @@ struct DevSetup {
 	// The same twiddles laid out per pass for the fused kernel: for every DIF pass (first small-radix pass, then
 	// the radix-8 passes with L >= 64) the 8 (or 4 / 1) factors of butterfly j are contiguous (fft_core.cuh PassTables)
 	const float2* fftp[2];
+	// Compact tables the fused kernel copies into shared memory: for every radix-8 pass with L >= 64 the factors
+	// W_L^j, W_L^2j, W_L^3j, W_L^4j of butterfly j (the other three are one multiplication away), fft8_count float2 each
+	const float2* fft8[2];
+	uint32_t fft8_count[2];
+	// rotation helpers: rotc1 = exp(-i*pi/M) (rot[j+1] = rot[j]*rotc1), rotc6 = exp(+i*pi*6/(8M))
+	// (rot[Q-1-j] = -i * conj(rot[j]) * rotc6)
+	float2 rotc1[2], rotc6[2];
 };
 
 // Work item of the fused kernel: a run of consecutive packets of one stream. The first packet of a run that is

@@ -125,7 +125,7 @@ def test_entries_batch_staged_equals_fused(ctx):
         pcm = np.empty(int(b.pcm_floats), np.float32)
         ctx._check(ctx.L.pov_batch_fetch_pcm(ctx.ctx, h, pcm.ctypes.data_as(C.POINTER(C.c_float)), pcm.size, 1))
         out.append(pcm)
-    assert np.array_equal(out[0], out[1])
+    assert np.abs(out[0] - out[1]).max() <= 1e-5 and ob.snr_db(out[0], out[1]) >= 120.0
     st.setup_id = 0
     ctx.L.pov_batch_free(ctx.ctx, h)
     po.close()

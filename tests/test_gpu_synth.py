@@ -90,7 +90,9 @@ def test_golden_fused_pcm(ctx, golden, name):
     _assert_float_parity(fused, g["pcm"], "pcm")
     ctx.run_staged(bh)
     staged = ctx.fetch_pcm(bh).reshape(setup.channels, -1)
-    assert np.array_equal(fused, staged)      # same arithmetic, different kernels
+    # the staged path rounds its twiddles straight from float64 tables, the fused kernel derives part of them by
+    # one extra float32 multiplication: same algorithm, last-ulp differences
+    _assert_float_parity(fused, staged, "fused vs staged")
     bh.free()
 
 
@@ -112,7 +114,7 @@ def _check_against_oracle(ctx, setup, batch, stages=False):
     if stages:
         ctx.run_staged(bh)
         staged = ctx.fetch_pcm(bh)
-        assert np.array_equal(staged, fused)
+        _assert_float_parity(fused, staged, "fused vs staged")
         C = setup.channels
         n_of = np.asarray(setup.blocksize)[batch.packets["mode"].astype(int)]   # mode 0 short / 1 long in workloads
         for p in range(0, len(batch.packets), max(1, len(batch.packets) // 40)):
