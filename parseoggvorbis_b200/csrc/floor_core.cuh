@@ -251,7 +251,7 @@ __device__ __forceinline__ void curve_scan_cells_warp(const CurveV3& Cv, uint32_
 
 // Unwrap (hpp:521-559) + build for floors with <= 32 posts. All 32 lanes call. Returns POV_PKT_* bits (warp-uniform),
 // including the hpp:587 range check over the n bins the reference renders.
-__device__ __forceinline__ uint32_t floor1_curve_warp32(const DevFloor* __restrict__ F, const uint16_t* __restrict__ ys,
+static __device__ __noinline__ uint32_t floor1_curve_warp32(const DevFloor* __restrict__ F, const uint16_t* __restrict__ ys,
                                                         const CurveV3& Cv, uint32_t cells, uint32_t n, int lane) {
 	const int posts = F->n_posts;
 	const uint32_t range = F->range;
@@ -346,7 +346,7 @@ __device__ __forceinline__ float2 curve_pair(const CurveV3& Cv, uint32_t x, cons
 }
 
 // Four consecutive bins x..x+3 (x % 4 == 0: the first bin of an index cell) as inverse-dB table values.
-__device__ __forceinline__ float4 curve_quad(const CurveV3& Cv, uint32_t x, const float* __restrict__ invdb) {
+static __device__ __noinline__ float4 curve_quad(const CurveV3& Cv, uint32_t x, const float* __restrict__ invdb) {
 	uint32_t s = Cv.idx[x >> 2];
 	uint4 r = *reinterpret_cast<const uint4*>(&Cv.rec[s]);
 	float out[4];

@@ -70,6 +70,7 @@ struct FusedParams {
 	uint32_t slot_floats;    // floats of one spectra buffer = C_max * blocksize1/2
 	uint32_t curve_bytes;    // size of the curve-block region
 	uint32_t table_float2;   // float2 slots of the shared-memory twiddle/rotation tables
+	uint32_t dbg_skip;       // timing experiments only (POV_DBG_SKIP): 1 floor, 2 spectral, 4 fft, 8 ola, 16 tma
 };
 
 // Compact per-packet descriptor kept in shared memory for the whole run (loaded once in the prologue), so that the
@@ -248,6 +249,66 @@ __device__ __forceinline__ void stage_fft(float2* T, float* Dlo, float* Dhi, int
 	}
 }
 
+// floors with more than 32 posts: shared-memory unwrap (floor_core.cuh floor1_unwrap_warp) + record build in chunks
+static __device__ __noinline__ uint32_t floor1_curve_generic(const DevFloor* F, const uint16_t* ys, const CurveV3& Cv, uint32_t cells, uint32_t n,
+                                                      int lane, unsigned char* scratch, uint32_t scratch_cap) {
+	FloorScratch W;
+	W.bind(scratch, scratch_cap);
+	uint32_t stt = floor1_unwrap_warp(F, ys, W, lane);
+	stt |= floor1_range_check_warp(W, n, lane);
+	const uint32_t ns = *W.nseg;
+	if(lane == 0) Cv.hdr[0] = 0;
+	for(uint32_t base = 0; base < ns; base += 32) {
+		const uint32_t sg = base + lane;
+		const bool have = sg < ns;
+		const uint32_t x0 = have ? W.segx[sg] : 0u, y0 = have ? W.segy[sg] : 0u;
+		const uint32_t x1 = (sg + 1 < ns) ? W.segx[sg + 1] : 0u, y1 = (sg + 1 < ns) ? W.segy[sg + 1] : 0u;
+		curve_build_warp(Cv, ns, x0, y0, x1, y1, have, base, cells, lane, base == 0);
+	}
+	curve_scan_cells_warp(Cv, cells, lane);
+	return stt;
+}
+
+// floor1 unwrap + curve records of one (packet, channel) curve of a step, by one warp. Out of line on purpose: it is
+// reached from three places and the kernel is instruction-cache bound.
+struct FloorTaskArgs {
+	const uint16_t* ys; uint32_t* status; const DevFloor* floors; const DevMapping* mappings; const uint8_t* mode_map;
+	const PktCtx* pk; unsigned char* curves; unsigned char* fscr;
+	uint32_t floor_cap[2], scratch_cap, bs[2]; int C;
+};
+static __device__ __noinline__ void floor_task_fn(const FloorTaskArgs& A, uint32_t first, uint32_t flag, uint32_t mode, int f, int warp, int lane) {
+	const int C = A.C;
+	const int n = (int) A.bs[flag ? 1 : 0];
+	const uint32_t cells = (uint32_t) n / 8;
+	const uint32_t fcap = A.floor_cap[flag ? 1 : 0];
+	const uint32_t curve_stride = CurveV3::bytes(fcap, cells);
+	const DevMapping* mp = &A.mappings[A.mode_map[mode]];
+	const int g = f / C, c = f - g * C;
+	CurveV3 Cv;
+	Cv.bind(A.curves + (size_t) f * curve_stride, fcap);
+	const PktCtx& pc = A.pk[first + g];
+	const uint32_t used = pc.used;
+	if(!((used >> c) & 1)) {
+		// no curve decoded: the reference multiplies by its zero-initialised floor buffer if the channel became
+		// "used" through coupling (hpp:1159,1247) and leaves the residue untouched otherwise
+		uint32_t prop = used;
+		for(uint32_t k = 0; k < mp->n_couplings; ++k) {   // hpp:1174-1180
+			const uint32_t m = mp->coupling_mag[k], a = mp->coupling_ang[k];
+			if(((prop >> m) | (prop >> a)) & 1) prop |= (1u << m) | (1u << a);
+		}
+		if(lane == 0) Cv.hdr[0] = ((prop >> c) & 1) ? 2u : 1u;
+		return;
+	}
+	const DevFloor* F = &A.floors[mp->floor_of_ch[c]];
+	uint64_t yo = pc.ys_off;
+	for(int cc = 0; cc < c; ++cc)
+		if((used >> cc) & 1) yo += A.floors[mp->floor_of_ch[cc]].n_posts;
+	uint32_t stt;
+	if(F->n_posts <= 32) stt = floor1_curve_warp32(F, A.ys + yo, Cv, cells, (uint32_t) n, lane);
+	else stt = floor1_curve_generic(F, A.ys + yo, Cv, cells, (uint32_t) n, lane, A.fscr + (size_t) warp * floor_scratch_stride(A.scratch_cap), A.scratch_cap);
+	if(stt && lane == 0) atomicOr(&A.status[first + g], stt);
+}
+
 // Geometry of one emitting packet for the overlap-add stage (all block-uniform).
 struct OlaGeom {
 	int Hp, H;          // quarter sizes: Hp = n_prev/4, H = n/4 (= length of the lo / hi halves of D)
@@ -388,61 +449,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParam
 		const uint32_t half = (sx.flag ? bs1 : bs0) / 2;
 		const uint32_t bytes = (uint32_t) C * half * 4u;
 		mbar_expect_tx(&s_bar, bytes * sx.count);
+#pragma unroll 1
 		for(uint32_t g = 0; g < sx.count; ++g)
 			tma_bulk_g2s(raw + (size_t) g * C * half, b.spectra + b.spec_off[run.first_packet + sx.first + g], bytes, &s_bar);
 	};
-	// floor1 unwrap + curve records of one (packet, channel) curve of step sx, by one warp
-	auto floor_task = [&](const StepCtx& sx, int f) {
-		const uint32_t flag = sx.flag;
-		const int n = (int) (flag ? bs1 : bs0);
-		const uint32_t cells = (uint32_t) n / 8;
-		const uint32_t fcap = flag ? P.floor_cap[1] : P.floor_cap[0];
-		const uint32_t curve_stride = CurveV3::bytes(fcap, cells);
-		const DevMapping* mp = &mappings[s_mode_map[sx.mode]];
-		const int g = f / C, c = f - g * C;
-		CurveV3 Cv;
-		Cv.bind(curves + (size_t) f * curve_stride, fcap);
-		const PktCtx& pc = s_pk[sx.first + g];
-		const uint32_t used = pc.used;
-		if(!((used >> c) & 1)) {
-			// no curve decoded: the reference multiplies by its zero-initialised floor buffer if the channel became
-			// "used" through coupling (hpp:1159,1247) and leaves the residue untouched otherwise
-			uint32_t prop = used;
-			for(uint32_t k = 0; k < mp->n_couplings; ++k) {   // hpp:1174-1180
-				const uint32_t m = mp->coupling_mag[k], a = mp->coupling_ang[k];
-				if(((prop >> m) | (prop >> a)) & 1) prop |= (1u << m) | (1u << a);
-			}
-			if(lane == 0) Cv.hdr[0] = ((prop >> c) & 1) ? 2u : 1u;
-			return;
-		}
-		const DevFloor* F = &floors[mp->floor_of_ch[c]];
-		uint64_t yo = pc.ys_off;
-		for(int cc = 0; cc < c; ++cc)
-			if((used >> cc) & 1) yo += floors[mp->floor_of_ch[cc]].n_posts;
-		uint32_t stt;
-		if(F->n_posts <= 32) {
-			stt = floor1_curve_warp32(F, b.ys + yo, Cv, cells, (uint32_t) n, lane);
-		} else {
-			FloorScratch W;
-			W.bind(fscr + (size_t) warp * floor_scratch_stride(P.scratch_cap), P.scratch_cap);
-			stt = floor1_unwrap_warp(F, b.ys + yo, W, lane);
-			stt |= floor1_range_check_warp(W, (uint32_t) n, lane);
-			const uint32_t ns = *W.nseg;
-			if(lane == 0) Cv.hdr[0] = 0;
-			for(uint32_t base = 0; base < ns; base += 32) {
-				const uint32_t sg = base + lane;
-				const bool have = sg < ns;
-				const uint32_t x0 = have ? W.segx[sg] : 0u, y0 = have ? W.segy[sg] : 0u;
-				const uint32_t x1 = (sg + 1 < ns) ? W.segx[sg + 1] : 0u, y1 = (sg + 1 < ns) ? W.segy[sg + 1] : 0u;
-				curve_build_warp(Cv, ns, x0, y0, x1, y1, have, base, cells, lane, base == 0);
-			}
-			curve_scan_cells_warp(Cv, cells, lane);
-		}
-		if(stt && lane == 0) atomicOr(&b.status[run.first_packet + sx.first + g], stt);
-	};
+	FloorTaskArgs fa;
+	fa.ys = b.ys; fa.status = b.status + run.first_packet; fa.floors = floors; fa.mappings = mappings; fa.mode_map = s_mode_map;
+	fa.pk = s_pk; fa.curves = curves; fa.fscr = fscr;
+	fa.floor_cap[0] = P.floor_cap[0]; fa.floor_cap[1] = P.floor_cap[1]; fa.scratch_cap = P.scratch_cap;
+	fa.bs[0] = bs0; fa.bs[1] = bs1; fa.C = C;
+	auto floor_task = [&](const StepCtx& sx, int f) { if(!(P.dbg_skip & 1)) floor_task_fn(fa, sx.first, sx.flag, sx.mode, f, warp, lane); };
 
 	StepCtx cur = make_step(0);
-	if(threadIdx.x == 0 && cur.count) issue_loads(cur);
+	if(threadIdx.x == 0 && cur.count && !(P.dbg_skip & 16)) issue_loads(cur);
 	// prologue: curves of the first step (later steps get theirs during the previous step's overlap-add stage)
 	for(int f = warp; f < (int) cur.count * C; f += nwarps) floor_task(cur, f);
 	uint32_t phase = 0;
@@ -469,12 +488,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParam
 
 		// ---- wait for this step's spectra (TMA): one warp polls, the barrier releases everyone; it also publishes the
 		//      curve blocks of this step, which were built during the previous step's stage 4 (or the prologue) ----
-		if(warp == 0) mbar_wait(&s_bar, phase);
+		if(warp == 0 && !(P.dbg_skip & 16)) mbar_wait(&s_bar, phase);
 		phase ^= 1;
 		__syncthreads();
 
 		// ---- stage 2: floor evaluation + coupling + floor multiply + pre-rotation -> T ----
-		{
+		if(!(P.dbg_skip & 2)) {
 			const float2* rot = flag ? s_rot[1] : s_rot[0];
 			const float2 c1 = flag ? rc1[1] : rc1[0], c6 = flag ? rc6[1] : rc6[0];
 			const int lq = log2Q - 2;
@@ -494,10 +513,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParam
 		}
 		__syncthreads();
 		// the spectra buffer is free again: prefetch the next step's spectra behind stages 3-4
-		if(threadIdx.x == 0 && nxt.count) issue_loads(nxt);
+		if(threadIdx.x == 0 && nxt.count && !(P.dbg_skip & 16)) issue_loads(nxt);
 
 		// ---- stage 3: FFT passes + post-rotation -> D (lo / hi halves) ----
-		{
+		if(!(P.dbg_skip & 4)) {
 			const float2* rot = flag ? s_rot[1] : s_rot[0];
 			const float2* tw8 = flag ? s_tw8[1] : s_tw8[0];
 			const float2* TWP = su->fftp[flag];
@@ -539,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParam
 			const float* cur_lo = Dlo_cur + (size_t) g * C * Q;
 			const float* cur_hi = Dhi + (size_t) g * C * Q;
 			const bool emits = prev_valid && emit > 0 && (run.first_packet + (uint32_t) (first + g)) != st.first_packet;
-			if(emits && ola_n > 0) {
+			if(emits && ola_n > 0 && !(P.dbg_skip & 8)) {
 				OlaGeom G;
 				G.Hp = prev_n / 4; G.H = Q;
 				G.shift = Q - prev_n / 4;
@@ -646,6 +665,7 @@ cudaError_t launch_fused(const DevBatchView& b, const DevRun* runs, uint32_t n_r
 	fused_layout(max_channels, max_blocksize, min_blocksize, floor_cap, table_float2, P, threads, smem);
 	P.b = b;
 	P.runs = runs;
+	{ const char* e = getenv("POV_DBG_SKIP"); P.dbg_skip = e ? (uint32_t) atoi(e) : 0; }
 	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 	cudaError_t e;
 	if(threads == 128) e = only_256_2048 ? launch_variant<128, 5, true>(P, n_runs, smem, st) : launch_variant<128, 5, false>(P, n_runs, smem, st);
