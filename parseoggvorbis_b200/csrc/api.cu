@@ -97,6 +97,8 @@ extern "C" int pov_ctx_create(int device, pov_ctx** out, const char** error_out)
 	make_inverse_db_table(table);
 	if((e = dev_upload((float**) &ctx->d_inv_db, table, 256, ctx->stream)) != cudaSuccess) return fail("upload inverse dB table", e);
 	if((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("sync", e);
+	if((e = cudaMalloc((void**) &ctx->d_counter, 256)) != cudaSuccess) return fail("cudaMalloc work counter", e);
+	if(const char* k = getenv("POV_KERNEL")) ctx->kernel_choice = !strcmp(k, "fused") ? 1 : !strcmp(k, "warp") ? 2 : 0;
 	const char* rl = getenv("POV_RUN_LEN");
 	ctx->run_len = rl ? (uint32_t) std::min(64, std::max(2, atoi(rl))) : 0;   // the fused kernel keeps <= 65 descriptors per run
 	ctx->err[0] = 0;
@@ -106,7 +108,7 @@ extern "C" int pov_ctx_create(int device, pov_ctx** out, const char** error_out)
 
 static void free_setup(SetupRec& s) {
 	cudaFree((void*) s.d_floors); cudaFree((void*) s.d_mappings); cudaFree((void*) s.d_residues);
-	cudaFree((void*) s.d_codebooks); cudaFree((void*) s.d_vq);
+	cudaFree((void*) s.d_codebooks); cudaFree((void*) s.d_vq); cudaFree((void*) s.d_fast);
 }
 
 extern "C" void pov_ctx_destroy(pov_ctx* ctx) {
@@ -117,6 +119,7 @@ extern "C" void pov_ctx_destroy(pov_ctx* ctx) {
 	for(auto& kv : ctx->blk_tables) { cudaFree((void*) kv.second.d_rot); cudaFree((void*) kv.second.d_fft); cudaFree((void*) kv.second.d_fftp); cudaFree((void*) kv.second.d_fft8); cudaFree((void*) kv.second.d_slope); }
 	cudaFree((void*) ctx->d_setups);
 	cudaFree((void*) ctx->d_inv_db);
+	cudaFree((void*) ctx->d_counter);
 	ctx->mdct_in.release(); ctx->mdct_out.release();
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -178,6 +181,74 @@ static void serialize_setup(const pov_setup* s, std::string& out) {
 		put(m.coupling_ang, std::min<uint32_t>(m.n_couplings, POV_MAX_COUPLINGS));
 	}
 	for(uint32_t i = 0; i < s->n_modes; ++i) { put(&s->modes[i].blockflag, 1); put(&s->modes[i].mapping, 1); }
+}
+
+// Compact tables of the warp-autonomous kernel. Returns false when the setup is outside what kernel_warp.cu handles
+// (those batches run on the CTA-per-run fused kernel instead).
+static bool build_fast_tables(const pov_setup* s, const std::vector<DevFloor>& floors, const std::vector<DevMapping>& maps,
+                              const uint32_t posts_cls[2], FastTables& ft, uint32_t& short_cap) {
+	memset(&ft, 0, sizeof ft);
+	if(s->blocksize[0] != 256 || s->blocksize[1] != 2048) return false;
+	if(s->channels > POV_MAX_CHANNELS || s->n_floors > POV_FAST_MAX_FLOORS || s->n_mappings > POV_FAST_MAX_MAPPINGS) return false;
+	if(posts_cls[0] > 32 || posts_cls[1] > 32) return false;
+	short_cap = (posts_cls[0] + 3u) & ~3u;
+	if(short_cap < 4) short_cap = 4;
+	ft.channels = s->channels;
+	ft.short_posts_cap = short_cap;
+	for(uint32_t i = 0; i < s->n_floors; ++i) {
+		const DevFloor& f = floors[i];
+		FastFloor& o = ft.floors[i];
+		if(f.n_posts > 32) {            // only reachable floors matter, but an unreachable big floor is not worth a special case
+			bool used = false;
+			for(uint32_t m = 0; m < s->n_mappings && !used; ++m)
+				for(uint32_t c = 0; c < s->channels; ++c) if(maps[m].floor_of_ch[c] == i) used = true;
+			if(used) return false;
+			continue;
+		}
+		o.n_posts = f.n_posts; o.n_levels = f.n_levels; o.range = f.range; o.multiplier = f.multiplier;
+		for(uint32_t k = 0; k < f.n_posts; ++k) {
+			if(f.xs[k] > POV_FAST_MAX_X) return false;
+			const uint32_t sidx = f.sorted_idx[k];
+			o.post[k][0] = (uint32_t) f.lo[k] | ((uint32_t) f.hi[k] << 8) | ((uint32_t) f.level[k] << 16) | (sidx << 24);
+			o.post[k][1] = (uint32_t) f.dxn[k] | ((uint32_t) f.adx[k] << 16);
+			o.post[k][2] = (k >= 2) ? (uint32_t) ((0x100000000ull + f.adx[k] - 1) / f.adx[k]) : 0u;
+			o.post[k][3] = f.xs[sidx];
+		}
+	}
+	for(uint32_t m = 0; m < s->n_mappings; ++m) {
+		const DevMapping& mp = maps[m];
+		if(mp.n_couplings > POV_FAST_MAX_STEPS) return false;
+		ft.ncoup[m] = (uint8_t) mp.n_couplings;
+		for(uint32_t k = 0; k < mp.n_couplings; ++k) { ft.cmag[m][k] = mp.coupling_mag[k]; ft.cang[m][k] = mp.coupling_ang[k]; }
+		for(uint32_t c = 0; c < s->channels; ++c) {
+			ft.floor_of_ch[m][c] = mp.floor_of_ch[c];
+			// Steps are applied k = n-1 .. 0 (hpp:1214). Walking them backwards in time (k = 0 .. n-1) from the final value of
+			// channel c collects the steps that can reach it and the channels whose residue vectors it needs.
+			uint32_t need = 1u << c;
+			std::vector<uint32_t> steps;
+			for(uint32_t k = 0; k < mp.n_couplings; ++k) {
+				const uint32_t mg = mp.coupling_mag[k], an = mp.coupling_ang[k];
+				if((need >> mg) & 1u || (need >> an) & 1u) { need |= (1u << mg) | (1u << an); steps.push_back(k); }
+			}
+			FastCouple& fc = ft.couple[m][c];
+			uint8_t local[POV_MAX_CHANNELS];
+			memset(local, 0xff, sizeof local);
+			fc.nl = 0;
+			fc.ch[fc.nl] = (uint8_t) c; local[c] = fc.nl++;
+			for(uint32_t x = 0; x < s->channels; ++x)
+				if(x != c && ((need >> x) & 1u)) {
+					if(fc.nl >= POV_FAST_MAX_DEPS) return false;
+					fc.ch[fc.nl] = (uint8_t) x; local[x] = fc.nl++;
+				}
+			fc.nsteps = (uint8_t) steps.size();
+			for(size_t i = 0; i < steps.size(); ++i) {         // application order = descending k
+				const uint32_t k = steps[steps.size() - 1 - i];
+				fc.sm[i] = local[mp.coupling_mag[k]]; fc.sa[i] = local[mp.coupling_ang[k]];
+			}
+		}
+	}
+	for(uint32_t i = 0; i < s->n_modes; ++i) { ft.mode_flag[i] = s->modes[i].blockflag ? 1 : 0; ft.mode_map[i] = s->modes[i].mapping; }
+	return warp_kernel_smem_bytes(short_cap, nullptr, nullptr, nullptr) <= 227 * 1024;
 }
 
 extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id_out) {
@@ -328,6 +399,12 @@ extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id
 	CUDA_TRY(ctx, dev_upload((DevResidue**) &rec.d_residues, residues.data(), residues.size(), ctx->stream));
 	CUDA_TRY(ctx, dev_upload((DevMapping**) &rec.d_mappings, maps.data(), maps.size(), ctx->stream));
 	d.floors = rec.d_floors; d.mappings = rec.d_mappings; d.residues = rec.d_residues; d.codebooks = rec.d_codebooks;
+	{
+		FastTables ft;
+		rec.fast_ok = build_fast_tables(s, floors, maps, rec.posts_cls, ft, rec.fast_short_cap);
+		if(rec.fast_ok) CUDA_TRY(ctx, dev_upload((FastTables**) &rec.d_fast, &ft, 1, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // ft lives on this stack frame
+	}
 	rec.image.swap(image);
 	ctx->setups.push_back(std::move(rec));
 
@@ -397,8 +474,23 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	uint32_t table_float2 = 0;
 	uint64_t dense_floats = 0, stage_floats = 0, expect_first = 0;
 	const uint64_t payload_floats = b->payload_bytes / 4;
+	// the persistent warp kernel handles batches whose streams all share one supported setup
+	bool warp_ok = b->n_streams > 0 && ctx->kernel_choice != 1;
+	for(uint32_t si = 0; si < b->n_streams && warp_ok; ++si) {
+		const uint32_t id = b->streams[si].setup_id;
+		if(id >= ctx->setups.size() || id != b->streams[0].setup_id || !ctx->setups[id].fast_ok) warp_ok = false;
+	}
+	h->warp_ok = warp_ok;
+	h->warp_setup = warp_ok ? b->streams[0].setup_id : 0;
 	uint32_t run_len = ctx->run_len;
-	if(run_len == 0) {
+	if(warp_ok) {
+		// work items = runs x channels, taken dynamically by sm_count*16 warps: aim for >= 8 items per warp, keep the
+		// halo overhead (one re-transformed packet per run) small; a run holds <= 32 packet descriptors, halo included
+		const uint64_t C = ctx->setups[h->warp_setup].channels;
+		const uint64_t want_items = (uint64_t) ctx->sm_count * 16 * 8;
+		const uint64_t auto_len = std::min<uint64_t>(31, std::max<uint64_t>(8, (uint64_t) P * C / want_items));
+		run_len = run_len ? std::min<uint32_t>(run_len, 31) : (uint32_t) auto_len;
+	} else if(run_len == 0) {
 		// aim for >= ~8 CTAs per SM when the batch is big enough, keep the halo overhead <= 1/run_len
 		const uint64_t want_runs = (uint64_t) ctx->sm_count * 8;
 		run_len = (uint32_t) std::min<uint64_t>(32, std::max<uint64_t>(8, P / std::max<uint64_t>(1, want_runs)));
@@ -574,11 +666,18 @@ extern "C" int pov_batch_run_staged(pov_ctx* ctx, pov_batch_handle* h) {
 
 extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
 	if(!ctx || !h) return POV_ERR_ARG;
-	if(!h->fused_ok) return pov_batch_run_staged(ctx, h);   // working set beyond one SM's shared memory: staged kernels
+	if(ctx->kernel_choice == 2 && !h->warp_ok) return pov_fail(ctx, POV_ERR_UNSUPPORTED, "POV_KERNEL=warp: this batch is outside what the warp kernel supports");
+	if(!h->warp_ok && !h->fused_ok) return pov_batch_run_staged(ctx, h);   // working set beyond one SM's shared memory: staged kernels
 	cudaSetDevice(ctx->device);
 	DevBatchView v = make_view(ctx, h);
 	int rc = run_residue_if_needed(ctx, h, v);
 	if(rc) return rc;
+	if(h->warp_ok) {
+		const SetupRec& su = ctx->setups[h->warp_setup];
+		CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), su.channels, su.d_fast, su.fast_short_cap,
+		                          su.dev.slope, su.dev.rot, su.dev.fft8, ctx->d_counter, ctx->sm_count, ctx->stream, &ctx->launches));
+		return POV_OK;
+	}
 	CUDA_TRY(ctx, launch_fused(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), h->max_channels, h->max_blocksize,
 	                           h->min_blocksize, h->floor_cap_cls, h->table_float2, h->only_256_2048, ctx->stream, &ctx->launches));
 	return POV_OK;

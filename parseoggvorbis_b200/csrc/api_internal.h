@@ -46,6 +46,10 @@ struct SetupRec {
 	const DevResidue* d_residues = nullptr;
 	const DevCodebook* d_codebooks = nullptr;
 	const float* d_vq = nullptr;
+	// warp-autonomous kernel (kernel_warp.cu): eligible setups carry their compact tables
+	bool fast_ok = false;
+	uint32_t fast_short_cap = 4;
+	const FastTables* d_fast = nullptr;
 	std::string image;            // canonical bytes, for de-duplication
 };
 
@@ -55,6 +59,8 @@ struct pov_ctx {
 	cudaStream_t stream = nullptr;
 	uint64_t launches = 0;
 	uint32_t run_len = 0;         // 0 = automatic
+	int kernel_choice = 0;        // POV_KERNEL: 0 automatic, 1 force the CTA-per-run fused kernel, 2 require the warp kernel
+	uint32_t* d_counter = nullptr; // work counter of the persistent kernel
 	const float* d_inv_db = nullptr;
 	const DevSetup* d_setups = nullptr;
 	std::vector<SetupRec> setups;
@@ -71,6 +77,8 @@ struct pov_batch_handle {
 	uint32_t floor_cap_cls[2] = {4, 4};
 	uint32_t table_float2 = 0;
 	bool fused_ok = true, staged_ready = false, only_256_2048 = false;
+	bool warp_ok = false;         // every stream uses one setup that kernel_warp.cu supports
+	uint32_t warp_setup = 0;
 	std::vector<uint64_t> spec_off, stage_off;
 	std::vector<uint32_t> pk_n, pk_setup;
 	std::vector<DevRun> runs;

@@ -1,0 +1,693 @@
+// Production path for the common 256/2048 setups: a persistent, warp-autonomous synthesis kernel.
+//
+//   floor1 unwrap/render -> nonzero propagate -> inverse coupling -> floor multiply -> inverse MDCT
+//   -> window -> overlap-add -> PCM
+// (reference: VorbisStream::parse_audio stages 4.3.2-4.3.7 + VorbisStreamDecodeState, src/ParseOggVorbis.hpp:
+//  521-591, 1174-1180, 1213-1268, 1008-1059; the IMDCT contract is src/mdct.h:105.)
+//
+// Design (see DESIGN.md "kernel_warp"):
+//   * One CTA per SM, 16 warps, resident for the whole launch. Every table a packet needs (inverse-dB table, window
+//     slopes, FFT twiddles, DCT-IV rotations, floor neighbour tables, coupling programs) is brought
+//     into shared memory ONCE per CTA with TMA bulk copies and shared by all warps.
+//   * The unit of work is (run of <= 31 consecutive packets of one stream, one channel), taken from a global atomic
+//     counter. ONE WARP owns it from the coded floor posts to the PCM stores: there is no CTA-wide barrier after the
+//     prologue, only __syncwarp. A warp that needs other channels for the inverse coupling simply loads them too
+//     (they are L1/L2 hits: the sibling warp reads the same lines), so warps never exchange data.
+//   * The Q = n/4 point complex FFT of a long block lives in registers: 16 points per lane, three radix-8 passes,
+//     two transposes through a warp-private shared buffer whose layouts make every access conflict free.
+//     Spectra are read straight from HBM with 64-bit loads arranged so that the two bins a pre-rotated point needs
+//     arrive in the same lane (points j and Q-1-j are handled together); the post-rotation uses the same pairing to
+//     emit the D array with 64-bit stores.
+//   * Overlap-add exploits the TDAC symmetry: one lane produces samples j..j+3 and n/2-4-j..n/2-1-j from the same four
+//     128-bit shared loads, halving the shared-memory traffic of the window stage.
+// HBM traffic is the algorithmic minimum: every spectrum is read once, every PCM sample written once (+ one halo
+// packet per run).
+#include "kernels.h"
+#include "fft_core.cuh"
+#include <stdlib.h>
+
+namespace pov {
+namespace wk {
+
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kRegionF2 = 576;          // float2 slots of one FFT work region (long: 8*72, short: 8 FFTs * 72)
+constexpr int kPktCap = 32;             // packets per run, halo included
+constexpr uint32_t FULL = 0xffffffffu;
+
+struct __align__(16) WPkt { uint32_t meta, emit; uint64_t ys_off, pcm_off, spec_off; };   // 32 bytes
+
+struct Params {
+	DevBatchView b;
+	const DevRun* runs;
+	uint32_t n_runs, n_items, C;
+	uint32_t* counter;
+	const FastTables* tabs;
+	const float* slope[2];
+	const float2* rot[2];
+	const float2* tw8[2];
+	uint32_t group_short;        // short packets per step (<= 8)
+	uint32_t curve_bytes;        // per-warp curve area
+	uint32_t short_curve_stride; // bytes of one short-block curve block
+};
+
+// ---- shared memory map (bytes) -----------------------------------------------------------------------------------
+constexpr int kOffTabs   = 0;
+constexpr int kOffInvDb  = kOffTabs + (int) sizeof(FastTables);
+constexpr int kOffSlope0 = kOffInvDb + 1024;
+constexpr int kOffSlope1 = kOffSlope0 + 128 * 4;
+constexpr int kOffTw1    = kOffSlope1 + 1024 * 4;
+constexpr int kOffTw0    = kOffTw1 + 288 * 8;
+constexpr int kOffRot1   = kOffTw0 + 32 * 8;
+constexpr int kOffRot0   = kOffRot1 + 512 * 8;
+constexpr int kOffBar    = kOffRot0 + 64 * 8;
+constexpr int kOffWarps  = kOffBar + 16;
+static_assert(kOffWarps % 16 == 0, "warp areas must stay 16-byte aligned");
+constexpr int kWarpFixedBytes = 2 * kRegionF2 * 8 + kPktCap * (int) sizeof(WPkt);
+
+// ---- mbarrier / TMA bulk copy (SASS: UBLKCP + SYNCS) ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"WAIT_LOOP:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra.uni WAIT_DONE;\n\t"
+		"bra.uni WAIT_LOOP;\n\t"
+		"WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void uncouple_f(float& m, float& a) {   // hpp:1220-1239, branch-free
+	const float mv = m, av = a;
+	const float t = (mv > 0.f) ? av : -av;
+	const bool p = av > 0.f;
+	const float diff = mv - t, sum = mv + t;
+	a = p ? diff : mv;
+	m = p ? mv : sum;
+}
+__device__ __forceinline__ void uncouple2(float2& m, float2& a) { uncouple_f(m.x, a.x); uncouple_f(m.y, a.y); }
+// The same step when only one of the two results is needed (the last step of a channel's coupling program):
+//   new magnitude = a > 0 ? m : m + t,  new angle = a > 0 ? m - t : m,  t = m > 0 ? a : -a
+__device__ __forceinline__ float uncouple_mag(float m, float a) {
+	const float v = fminf(a, 0.f);
+	return m + ((m > 0.f) ? v : -v);
+}
+__device__ __forceinline__ float uncouple_ang(float m, float a) {
+	const float v = fmaxf(a, 0.f);
+	return m - ((m > 0.f) ? v : -v);
+}
+
+// ---- floor curve block (warp private, shared memory) ------------------------------------------------------------
+// 8-byte segment record:  x = x0 | x1 << 11 | y0 << 22  (x1 = 2047: flat tail),  y = slope | descending << 31,
+//   slope = ceil(2^20 * |dy| / dx)   =>   y(x) = y0 +/- floor((x - x0) * |dy| / dx) = y0 +/- umulhi((x - x0) << 12, slope)
+// Exact: with k = x - x0 < dx <= 2^10 the excess k * (slope - 2^20 |dy|/dx) / 2^20 < dx / 2^20 <= 1/dx can never carry the
+// fractional part of k*|dy|/dx (<= 1 - 1/dx) over the next integer. |dy| <= 1023 keeps the slope below 2^30. Curves that
+// violate these bounds also violate hpp:587 and are reported through the packet status word (samples unspecified, as in
+// the reference, which aborts the stream there).
+// Block layout: uint2 rec[cap] | uint8 idx[cells], cells = n/4: idx[c] = record that contains bin 2c.
+__device__ __forceinline__ uint32_t bytes_prefix_max(uint32_t v) {      // little-endian: byte i = max(byte 0..i)
+	v = __vmaxu4(v, v << 8);
+	v = __vmaxu4(v, v << 16);
+	return v;
+}
+
+// floor1 step 1 (amplitude unwrap, hpp:521-559) + step 2 set-up (hpp:563-585) for one curve by one warp.
+// Returns POV_PKT_* bits (warp uniform).
+__device__ __noinline__ uint32_t build_curve(const FastFloor* __restrict__ F, const uint16_t* __restrict__ ysp, unsigned char* __restrict__ curve,
+                                             uint32_t rec_cap, uint32_t cells, uint32_t n, int lane) {
+	const int posts = (int) F->n_posts;
+	const uint32_t range = F->range;
+	const bool have = lane < posts;
+	const uint4 t = *reinterpret_cast<const uint4*>(F->post[lane]);
+	uint32_t cur = have ? (uint32_t) __ldg(ysp + lane) : 0u;
+	const uint32_t val = cur;
+	const int lo = (int) (t.x & 0xffu), hi = (int) ((t.x >> 8) & 0xffu), lvl = (int) ((t.x >> 16) & 0xffu), si = (int) (t.x >> 24);
+	uint32_t flags = 0, bad = 0;
+	const int levels = (int) F->n_levels;
+	for(int lv = 1; lv < levels; ++lv) {
+		const uint32_t y0 = __shfl_sync(FULL, cur, lo), y1 = __shfl_sync(FULL, cur, hi);
+		if(lvl == lv) {
+			const bool up = y1 >= y0;
+			const uint32_t ady = up ? (y1 - y0) : (y0 - y1);
+			// floor(ady * dxn / adx) by multiplication with ceil(2^32/adx): exact while ady * dxn * adx < 2^32 (ady < 2^12)
+			const uint32_t e = ady * (t.y & 0xffffu);
+			const uint32_t off = (ady < 4096u) ? __umulhi(e, t.z) : e / (t.y >> 16);
+			const uint32_t predicted = up ? y0 + off : y0 - off;
+			if(predicted > range) bad |= POV_PKT_FLOOR_PREDICTED;
+			const uint32_t high_room = range - predicted, low_room = predicted;
+			const uint32_t room = min(high_room, low_room) * 2;
+			uint32_t fin = predicted;
+			if(val != 0) {
+				flags |= (1u << lo) | (1u << hi) | (1u << lane);
+				if(val >= room) fin = (high_room > low_room) ? val - low_room + predicted : predicted - val + high_room - 1;
+				else fin = (val & 1) ? predicted - (val + 1) / 2 : predicted + val / 2;
+			}
+			cur = fin;
+		}
+	}
+	flags = __reduce_or_sync(FULL, flags) | 3u;
+	// lane = position in ascending-x order
+	const uint32_t fy = __shfl_sync(FULL, cur, si);
+	const bool f = have && ((flags >> si) & 1u);
+	const uint32_t mask = __ballot_sync(FULL, f);
+	const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+	const uint32_t x0 = t.w & 0xffffu;
+	const uint32_t y0 = min(fy * F->multiplier, 0xFFFFu);
+	const uint32_t above = (lane == 31) ? 0u : (mask & ~((2u << lane) - 1u));
+	const bool last = above == 0u;
+	const int nlane = last ? lane : (__ffs((int) above) - 1);
+	const uint32_t pn = __shfl_sync(FULL, x0 | (y0 << 16), nlane);
+	const uint32_t x1 = pn & 0xffffu, y1 = pn >> 16;
+	// hpp:587 CHECK(floor[i] < 256) over the n bins the reference renders: segments are monotone, so the maxima are at
+	// rendered end points; a segment cut by bin n-1 needs y(n-1)
+	bool over = false;
+	if(f) {
+		if(x0 < n && y0 >= 256u) over = true;
+		if(!last && x0 < n && x1 > n - 1) {
+			const bool down = y1 < y0;
+			const uint32_t ady = down ? y0 - y1 : y1 - y0, dx = x1 - x0;
+			const uint32_t q = (uint32_t) (((uint64_t) (n - 1 - x0) * ady) / dx);
+			if((down ? y0 - q : y0 + q) >= 256u) over = true;
+		}
+	}
+	if(__any_sync(FULL, over)) bad |= POV_PKT_FLOOR_RANGE;
+
+	uint2* rec = reinterpret_cast<uint2*>(curve);
+	uint8_t* idx = curve + rec_cap * 8u;
+	if((uint32_t) lane < cells / 16u) reinterpret_cast<uint4*>(idx)[lane] = make_uint4(0, 0, 0, 0);
+	__syncwarp();
+	if(f) {
+		const uint32_t yc0 = min(y0, 1023u), yc1 = min(y1, 1023u);
+		uint2 r;
+		if(last) r = make_uint2(x0 | (2047u << 11) | (yc0 << 22), 0u);
+		else {
+			const bool down = yc1 < yc0;
+			const uint32_t ady = down ? yc0 - yc1 : yc1 - yc0, adx = x1 - x0;
+			r = make_uint2(x0 | (x1 << 11) | (yc0 << 22), (((ady << 20) + adx - 1u) / adx) | (down ? 0x80000000u : 0u));
+		}
+		rec[rank] = r;
+		// first 2-bin cell whose first bin is >= x0; only the last claimant of a cell writes
+		const uint32_t cell = (x0 + 1) >> 1;
+		const uint32_t ncell = last ? 0xFFFFFFFFu : ((x1 + 1) >> 1);
+		if(cell < cells && ncell != cell) idx[cell] = (uint8_t) rank;
+	}
+	__syncwarp();
+	// inclusive max-scan over the cell bytes: four words per lane
+	{
+		const uint32_t words = cells / 4;
+		const bool mine = (uint32_t) (4 * lane) < words;
+		uint4 w = mine ? reinterpret_cast<const uint4*>(idx)[lane] : make_uint4(0, 0, 0, 0);
+		w.x = bytes_prefix_max(w.x);
+		w.y = __vmaxu4(bytes_prefix_max(w.y), (w.x >> 24) * 0x01010101u);
+		w.z = __vmaxu4(bytes_prefix_max(w.z), (w.y >> 24) * 0x01010101u);
+		w.w = __vmaxu4(bytes_prefix_max(w.w), (w.z >> 24) * 0x01010101u);
+		uint32_t incl = w.w >> 24;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			const uint32_t v = __shfl_up_sync(FULL, incl, o);
+			if(lane >= o) incl = max(incl, v);
+		}
+		uint32_t before = __shfl_up_sync(FULL, incl, 1);
+		if(lane == 0) before = 0;
+		const uint32_t bc = before * 0x01010101u;
+		if(mine) reinterpret_cast<uint4*>(idx)[lane] = make_uint4(__vmaxu4(w.x, bc), __vmaxu4(w.y, bc), __vmaxu4(w.z, bc), __vmaxu4(w.w, bc));
+	}
+	__syncwarp();
+	return __reduce_or_sync(FULL, bad);
+}
+
+// Two consecutive bins x, x+1 (x even) of a curve as inverse-dB table values (hpp:586-589).
+__device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, const uint8_t* __restrict__ idx, uint32_t x,
+                                             const float* __restrict__ invdb) {
+	const uint32_t s = idx[x >> 1];
+	uint2 r = rec[s];
+	float2 out;
+	{
+		const uint32_t k = x - (r.x & 0x7ffu);
+		const uint32_t q = __umulhi(k << 12, r.y & 0x7fffffffu);
+		const uint32_t y0 = r.x >> 22;
+		const uint32_t y = ((int) r.y < 0) ? y0 - q : y0 + q;
+		out.x = invdb[y & 255u];
+	}
+	if(x + 1 >= ((r.x >> 11) & 0x7ffu)) r = rec[s + 1];
+	{
+		const uint32_t k = x + 1 - (r.x & 0x7ffu);
+		const uint32_t q = __umulhi(k << 12, r.y & 0x7fffffffu);
+		const uint32_t y0 = r.x >> 22;
+		const uint32_t y = ((int) r.y < 0) ? y0 - q : y0 + q;
+		out.y = invdb[y & 255u];
+	}
+	return out;
+}
+
+// ---- FFT geometry ----------------------------------------------------------------------------------------------------
+// The spectral stage leaves the pre-rotated points in natural order (point j at slot j of the FFT's buffer). Then
+// Q = 512 = 8*8*8: j = 64 j2 + 8 j1 + j0, k = k0 + 8 k1 + 64 k2
+//   pass 1 (over j2): lane l owns butterflies (j1,j0) = l and 63-l         in: j + 64 j2        out A1[k0*72 + 8 j1 + j0]
+//   pass 2 (over j1): lane l owns butterflies (k0 = l/8 (+4), j0 = l%8)     in: A1               out A2[j0*66 + k0 + 8 k1]
+//   pass 3 (over j0): lane l owns butterflies (k0 + 8 k1) = l and 63-l      in: A2               out D as float2[Q]
+// Q = 64 = 8*8 (4 lanes per FFT, 8 FFTs per warp, FFT f at f*72): j = 8 j1 + j0, k = k0 + 8 k1
+//   pass 1 (over j1): lane u owns butterflies j0 = u and 7-u                in: j0 + 8 j1        out A1[k0*9 + j0]
+//   pass 2 (over j0): lane u owns butterflies k0 = u and 7-u                in: A1               out D as float2[Q] at f*64
+// Every access of a pass is either contiguous over the lanes or hits 16 distinct 8-byte bank pairs per half warp.
+// The passes are size-generic and NOT inlined: all block sizes share ~500 instructions of FFT code, which keeps the hot
+// loop of 16 independently running warps inside the instruction cache.
+__device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ tw) {   // tw: W^j, W^2j, W^3j, W^4j
+	const float4 w12 = *reinterpret_cast<const float4*>(tw), w34 = *reinterpret_cast<const float4*>(tw + 2);
+	const float2 w1 = make_float2(w12.x, w12.y), w2 = make_float2(w12.z, w12.w);
+	const float2 w3 = make_float2(w34.x, w34.y), w4 = make_float2(w34.z, w34.w);
+	a[1] = cmul(a[1], w1);
+	a[2] = cmul(a[2], w2);
+	a[3] = cmul(a[3], w3);
+	a[4] = cmul(a[4], w4);
+	a[5] = cmul(a[5], cmul(w4, w1));
+	a[6] = cmul(a[6], cmul(w4, w2));
+	a[7] = cmul(a[7], cmul(w4, w3));
+}
+
+// Radix-8 DIF pass of two butterflies per lane: inputs in*[m*sin], outputs out*[k*sout] (twiddled by tw*).
+__device__ __noinline__ void r8_pass(const float2* inA, const float2* inB, int sin, const float2* twA, const float2* twB,
+                                     float2* outA, float2* outB, int sout) {
+	float2 a[8], b[8];
+#pragma unroll
+	for(int m = 0; m < 8; ++m) { a[m] = inA[m * sin]; b[m] = inB[m * sin]; }
+	__syncwarp();
+	dft8(a);
+	twiddle8(a, twA);
+	dft8(b);
+	twiddle8(b, twB);
+#pragma unroll
+	for(int k = 0; k < 8; ++k) { outA[k * sout] = a[k]; outB[k * sout] = b[k]; }
+	__syncwarp();
+}
+
+// Last pass + post-rotation of butterflies kkA and kkB = J-1-kkA (rotA = rot + kkA, rotB = rot + kkB):
+//   c[k] = X[k] * w[k];  D2[k] = (D[2k], D[2k+1]) = (Re c[k], -Im c[Q-1-k]);  Q-1-(kkA + J k2) = kkB + J (7-k2)
+__device__ __noinline__ void last_pass(const float2* inA, const float2* inB, int sin, const float2* rotA, const float2* rotB, int J,
+                                       float2* outA, float2* outB) {
+	float2 a[8], b[8];
+#pragma unroll
+	for(int m = 0; m < 8; ++m) { a[m] = inA[m * sin]; b[m] = inB[m * sin]; }
+	__syncwarp();
+	dft8(a);
+	dft8(b);
+#pragma unroll
+	for(int k = 0; k < 8; ++k) {
+		a[k] = cmul(a[k], rotA[J * k]);
+		b[k] = cmul(b[k], rotB[J * k]);
+	}
+#pragma unroll
+	for(int k = 0; k < 8; ++k) {
+		outA[J * k] = make_float2(a[k].x, -b[7 - k].y);
+		outB[J * k] = make_float2(b[k].x, -a[7 - k].y);
+	}
+	__syncwarp();
+}
+
+// Spectral stage of the FFT this lane belongs to: nonzero propagate + inverse coupling + floor multiply + DCT-IV
+// pre-rotation. Lane u handles points u + J*m and their mirrors Q-1-(u + J*m), m = 0..7: the bins (2j, 2j+1) and
+// (M-2-2j, M-1-2j) arrive with two 64-bit loads per channel and feed both points.
+// src*: spectra ([n/2] floats) of the local channels of this lane's packet (src0 = this warp's channel);
+// fmode: 0 evaluate the curve, 1 multiply by 1 (hpp:1247 skipped), 2 multiply by 0.
+template <int NL>
+__device__ __noinline__ void spectral_stage(const float* __restrict__ src0, const float* __restrict__ src1, const float* __restrict__ src2,
+                                            const float* __restrict__ src3, int fmode, const unsigned char* __restrict__ curve, uint32_t rec_cap,
+                                            const float* __restrict__ invdb, const float2* __restrict__ rot, int Q, float2* __restrict__ Tf, int u,
+                                            const FastCouple* __restrict__ cp) {
+	const int J = Q >> 3, M = 2 * Q;
+	const uint2* rec = reinterpret_cast<const uint2*>(curve);
+	const uint8_t* idx = curve + rec_cap * 8u;
+	const int nsteps = (NL > 1) ? (int) cp->nsteps : 0;
+	const float* src[4] = {src0, src1, src2, src3};
+	float2 nva[NL], nvb[NL];
+#pragma unroll
+	for(int i = 0; i < NL; ++i) {
+		nva[i] = __ldg(reinterpret_cast<const float2*>(src[i] + 2 * u));
+		nvb[i] = __ldg(reinterpret_cast<const float2*>(src[i] + M - 2 - 2 * u));
+	}
+#pragma unroll 2
+	for(int m = 0; m < 8; ++m) {
+		const int jp = u + J * m;                  // point jp and its mirror Q-1-jp
+		float2 va[NL], vb[NL];                     // bins (2jp, 2jp+1) and (M-2-2jp, M-1-2jp) of every needed channel
+#pragma unroll
+		for(int i = 0; i < NL; ++i) { va[i] = nva[i]; vb[i] = nvb[i]; }
+		if(m < 7) {
+#pragma unroll
+			for(int i = 0; i < NL; ++i) {
+				nva[i] = __ldg(reinterpret_cast<const float2*>(src[i] + 2 * (jp + J)));
+				nvb[i] = __ldg(reinterpret_cast<const float2*>(src[i] + M - 2 - 2 * (jp + J)));
+			}
+		}
+		if(NL == 2) {
+			for(int st = 0; st + 1 < nsteps; ++st) {
+				if(cp->sm[st] == 0) { uncouple2(va[0], va[NL - 1]); uncouple2(vb[0], vb[NL - 1]); }
+				else                { uncouple2(va[NL - 1], va[0]); uncouple2(vb[NL - 1], vb[0]); }
+			}
+			if(nsteps > 0) {      // last step: only this warp's channel (local index 0) is needed
+				if(cp->sm[nsteps - 1] == 0) {
+					va[0].x = uncouple_mag(va[0].x, va[NL - 1].x); va[0].y = uncouple_mag(va[0].y, va[NL - 1].y);
+					vb[0].x = uncouple_mag(vb[0].x, vb[NL - 1].x); vb[0].y = uncouple_mag(vb[0].y, vb[NL - 1].y);
+				} else {
+					va[0].x = uncouple_ang(va[NL - 1].x, va[0].x); va[0].y = uncouple_ang(va[NL - 1].y, va[0].y);
+					vb[0].x = uncouple_ang(vb[NL - 1].x, vb[0].x); vb[0].y = uncouple_ang(vb[NL - 1].y, vb[0].y);
+				}
+			}
+		} else if(NL > 2) {
+			for(int st = 0; st < nsteps; ++st) {
+				const int mi = cp->sm[st], ai = cp->sa[st];
+				float2 ma = va[0], mb = vb[0], aa = va[0], ab = vb[0];
+#pragma unroll
+				for(int i = 0; i < NL; ++i) {
+					if(i == mi) { ma = va[i]; mb = vb[i]; }
+					if(i == ai) { aa = va[i]; ab = vb[i]; }
+				}
+				uncouple2(ma, aa); uncouple2(mb, ab);
+#pragma unroll
+				for(int i = 0; i < NL; ++i) {
+					if(i == mi) { va[i] = ma; vb[i] = mb; }
+					if(i == ai) { va[i] = aa; vb[i] = ab; }
+				}
+			}
+		}
+		float2 fa, fb;
+		if(fmode == 0) {
+			fa = curve_pair(rec, idx, (uint32_t) (2 * jp), invdb);
+			fb = curve_pair(rec, idx, (uint32_t) (M - 2 - 2 * jp), invdb);
+		} else {
+			const float fill = (fmode == 1) ? 1.f : 0.f;
+			fa = make_float2(fill, fill); fb = fa;
+		}
+		// hpp:1252 residue *= floor (one rounding each)
+		const float a0 = __fmul_rn(va[0].x, fa.x), a1 = __fmul_rn(va[0].y, fa.y);
+		const float b0 = __fmul_rn(vb[0].x, fb.x), b1 = __fmul_rn(vb[0].y, fb.y);
+		// t[j] = (X[2j] + i X[M-1-2j]) * w[j]
+		Tf[jp] = cmul(make_float2(a0, b1), rot[jp]);
+		Tf[Q - 1 - jp] = cmul(make_float2(b0, a1), rot[Q - 1 - jp]);
+	}
+}
+
+// ---- overlap-add ---------------------------------------------------------------------------------------------------
+struct OlaGeom {
+	int Hp, H;          // quarter sizes: Hp = n_prev/4, H = n/4 (= length of the lo / hi halves of D)
+	int shift;          // index in the current frame of the chunk's first sample: n/4 - n_prev/4
+	int lb, lc;         // current frame: left slope begins at lb, has length lc
+	int rbp, pr;        // previous frame, relative to its second half: falling slope begins at rbp, has length pr
+	const float* slL;   // rising slope table of length lc
+	const float* slR;   // rising slope table of length pr (read mirrored)
+};
+
+// One sample of the chunk:  out = prev[n_prev/2 + j] * w_prev + cur[j + shift] * w_cur   (hpp:1008-1017 in gather form)
+// plo = lo half of the previous frame's D, chi = hi half of the current frame's D.
+__device__ __forceinline__ float ola_one(const OlaGeom& G, const float* __restrict__ plo, const float* __restrict__ chi, int j) {
+	float acc = 0.f;
+	if(j < G.rbp + G.pr) {
+		const float y = (j < G.Hp) ? -plo[G.Hp - 1 - j] : -plo[j - G.Hp];
+		const float w = (j >= G.rbp) ? G.slR[G.pr - 1 - (j - G.rbp)] : 1.f;
+		acc = __fadd_rn(acc, __fmul_rn(y, w));
+	}
+	const int ic = j + G.shift;
+	if(ic >= G.lb) {
+		const float y = (ic < G.H) ? chi[ic] : -chi[2 * G.H - 1 - ic];
+		const float w = (ic < G.lb + G.lc) ? G.slL[ic - G.lb] : 1.f;
+		acc = __fadd_rn(acc, __fmul_rn(y, w));
+	}
+	return acc;
+}
+
+// Long block after a long block, both slopes long: every sample has both terms and both windows. Lane produces
+// out[j..j+3] and out[1020-j..1023-j] (j < 512) from the same four vectors (TDAC symmetry of both frames and windows).
+__device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, const float* __restrict__ chi, const float* __restrict__ sl,
+                                              float* __restrict__ dst, int lane) {
+#pragma unroll
+	for(int i = 0; i < 4; ++i) {
+		const int j = 4 * lane + 128 * i;
+		const float4 p = *reinterpret_cast<const float4*>(plo + 508 - j);
+		const float4 c = *reinterpret_cast<const float4*>(chi + j);
+		const float4 wa = *reinterpret_cast<const float4*>(sl + j);
+		const float4 wb = *reinterpret_cast<const float4*>(sl + 1020 - j);
+		float4 o1, o2;
+		o1.x = __fadd_rn(__fmul_rn(-p.w, wb.w), __fmul_rn(c.x, wa.x));
+		o1.y = __fadd_rn(__fmul_rn(-p.z, wb.z), __fmul_rn(c.y, wa.y));
+		o1.z = __fadd_rn(__fmul_rn(-p.y, wb.y), __fmul_rn(c.z, wa.z));
+		o1.w = __fadd_rn(__fmul_rn(-p.x, wb.x), __fmul_rn(c.w, wa.w));
+		o2.x = __fadd_rn(__fmul_rn(-p.x, wa.w), __fmul_rn(-c.w, wb.x));
+		o2.y = __fadd_rn(__fmul_rn(-p.y, wa.z), __fmul_rn(-c.z, wb.y));
+		o2.z = __fadd_rn(__fmul_rn(-p.z, wa.y), __fmul_rn(-c.y, wb.z));
+		o2.w = __fadd_rn(__fmul_rn(-p.w, wa.x), __fmul_rn(-c.x, wb.w));
+		__stcs(reinterpret_cast<float4*>(dst + j), o1);
+		__stcs(reinterpret_cast<float4*>(dst + 1020 - j), o2);
+	}
+}
+
+// Curve mode of channel c of a packet: 0 = decoded curve, 1 = untouched (multiply by 1), 2 = multiply by the
+// reference's zero-initialised floor buffer (channel became "used" through the propagate rule, hpp:1174-1180, 1159, 1247).
+__device__ __forceinline__ int curve_mode(const FastTables* tb, uint32_t mapping, uint32_t used, int c) {
+	if((used >> c) & 1u) return 0;
+	uint32_t prop = used;
+	const int nc = tb->ncoup[mapping];
+	for(int k = 0; k < nc; ++k) {
+		const uint32_t m = tb->cmag[mapping][k], a = tb->cang[mapping][k];
+		if(((prop >> m) | (prop >> a)) & 1u) prop |= (1u << m) | (1u << a);
+	}
+	return ((prop >> c) & 1u) ? 2 : 1;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	const FastTables* tb = reinterpret_cast<const FastTables*>(smem + kOffTabs);
+	const float* s_invdb = reinterpret_cast<const float*>(smem + kOffInvDb);
+	const float* s_slope0 = reinterpret_cast<const float*>(smem + kOffSlope0);
+	const float* s_slope1 = reinterpret_cast<const float*>(smem + kOffSlope1);
+	const float2* s_tw1 = reinterpret_cast<const float2*>(smem + kOffTw1);      // 2048: pass L=512 (256 float2) | pass L=64 (32)
+	const float2* s_tw0 = reinterpret_cast<const float2*>(smem + kOffTw0);      // 256:  pass L=64 (32 float2)
+	const float2* s_rot1 = reinterpret_cast<const float2*>(smem + kOffRot1);
+	const float2* s_rot0 = reinterpret_cast<const float2*>(smem + kOffRot0);
+	uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const DevBatchView& b = P.b;
+
+	// ---- prologue: tables -> shared memory (TMA bulk copies) ----
+	if(threadIdx.x == 0) {
+		mbar_init(s_bar, 1);
+		mbar_fence_init();
+		const uint32_t total = (uint32_t) sizeof(FastTables) + 1024u + 128u * 4u + 1024u * 4u + 288u * 8u + 32u * 8u + 512u * 8u + 64u * 8u;
+		mbar_expect_tx(s_bar, total);
+		tma_bulk_g2s(smem + kOffTabs, P.tabs, (uint32_t) sizeof(FastTables), s_bar);
+		tma_bulk_g2s(smem + kOffInvDb, b.inv_db, 1024u, s_bar);
+		tma_bulk_g2s(smem + kOffSlope0, P.slope[0], 128u * 4u, s_bar);
+		tma_bulk_g2s(smem + kOffSlope1, P.slope[1], 1024u * 4u, s_bar);
+		tma_bulk_g2s(smem + kOffTw1, P.tw8[1], 288u * 8u, s_bar);
+		tma_bulk_g2s(smem + kOffTw0, P.tw8[0], 32u * 8u, s_bar);
+		tma_bulk_g2s(smem + kOffRot1, P.rot[1], 512u * 8u, s_bar);
+		tma_bulk_g2s(smem + kOffRot0, P.rot[0], 64u * 8u, s_bar);
+	}
+	__syncthreads();
+	mbar_wait(s_bar, 0);
+
+	// ---- warp-private areas ----
+	const uint32_t warp_bytes = (uint32_t) kWarpFixedBytes + P.curve_bytes;
+	unsigned char* wbase = smem + kOffWarps + (size_t) warp * warp_bytes;
+	float2* region0 = reinterpret_cast<float2*>(wbase);      // two FFT work regions, used alternately by consecutive steps
+	WPkt* wp = reinterpret_cast<WPkt*>(wbase + 2 * kRegionF2 * 8);
+	unsigned char* curves = wbase + kWarpFixedBytes;
+
+	const int C = (int) P.C;
+	const bool planar = (b.pcm_layout == POV_PCM_PLANAR);
+
+	for(;;) {
+		uint32_t item = 0;
+		if(lane == 0) item = atomicAdd(P.counter, 1u);
+		item = __shfl_sync(FULL, item, 0);
+		if(item >= P.n_items) break;
+		const uint32_t run_idx = item / (uint32_t) C;
+		const int ch = (int) (item - run_idx * (uint32_t) C);
+		const DevRun run = P.runs[run_idx];
+		const int run_n = (int) run.n_packets;        // <= kPktCap
+		__syncwarp();
+		if(lane < run_n) {
+			const pov_packet pk = b.packets[run.first_packet + lane];
+			WPkt w;
+			w.meta = (uint32_t) pk.mode | ((uint32_t) pk.window_flags << 8) | ((uint32_t) pk.floor_used << 16);
+			w.emit = pk.emit_frames; w.ys_off = pk.ys_off; w.pcm_off = pk.pcm_off; w.spec_off = b.spec_off[run.first_packet + lane];
+			wp[lane] = w;
+		}
+		const pov_stream st = b.streams[b.packets[run.first_packet].stream];
+		__syncwarp();
+
+		int prev_valid = 0, prev_n = 0, prev_right = 0;
+		const float* prev_lo = nullptr;
+		int reg = 0;
+		int first = 0;
+		while(first < run_n) {
+			const uint32_t meta0 = wp[first].meta;
+			const uint32_t mode = meta0 & 0xffu;
+			const int flag = tb->mode_flag[mode];
+			const uint32_t mapping = tb->mode_map[mode];
+			const FastCouple* cp = &tb->couple[mapping][ch];
+			const FastFloor* F = &tb->floors[tb->floor_of_ch[mapping][ch]];
+			float2* T = region0 + reg * kRegionF2;
+			int count = 1;
+			if(!flag) while(count < (int) P.group_short && first + count < run_n && (wp[first + count].meta & 0xffu) == mode) ++count;
+
+			// Y offset of this channel's list inside a packet: the posts of the used channels before it (hpp:498-518 order)
+			auto ys_of = [&](const WPkt& w) {
+				uint64_t yo = w.ys_off;
+				const uint32_t used = w.meta >> 16;
+				for(int cc = 0; cc < ch; ++cc)
+					if((used >> cc) & 1u) yo += tb->floors[tb->floor_of_ch[mapping][cc]].n_posts;
+				return yo;
+			};
+
+			if(flag) {
+				// ================= one long packet: the whole warp is one 512-point FFT =================
+				const WPkt& w = wp[first];
+				const int fmode = curve_mode(tb, mapping, w.meta >> 16, ch);
+				if(fmode == 0) {
+					const uint32_t stt = build_curve(F, b.ys + ys_of(w), curves, 32u, 512u, 2048u, lane);
+					if(stt && lane == 0) atomicOr(&b.status[run.first_packet + first], stt);
+				}
+				const float* base = b.spectra + w.spec_off;
+				const float* s0 = base + (size_t) cp->ch[0] * 1024, *s1 = base + (size_t) cp->ch[1] * 1024;
+				const float* s2 = base + (size_t) cp->ch[2] * 1024, *s3 = base + (size_t) cp->ch[3] * 1024;
+				switch(cp->nl) {
+					case 1:  spectral_stage<1>(s0, s0, s0, s0, fmode, curves, 32u, s_invdb, s_rot1, 512, T, lane, cp); break;
+					case 2:  spectral_stage<2>(s0, s1, s0, s0, fmode, curves, 32u, s_invdb, s_rot1, 512, T, lane, cp); break;
+					case 3:  spectral_stage<3>(s0, s1, s2, s0, fmode, curves, 32u, s_invdb, s_rot1, 512, T, lane, cp); break;
+					default: spectral_stage<4>(s0, s1, s2, s3, fmode, curves, 32u, s_invdb, s_rot1, 512, T, lane, cp); break;
+				}
+				__syncwarp();
+				{
+					const int l2 = 63 - lane;
+					r8_pass(T + lane, T + l2, 64, s_tw1 + lane * 4, s_tw1 + l2 * 4, T + lane, T + l2, 72);
+					const int j0 = lane & 7, k0 = lane >> 3;
+					r8_pass(T + k0 * 72 + j0, T + (k0 + 4) * 72 + j0, 8, s_tw1 + 256 + j0 * 4, s_tw1 + 256 + j0 * 4, T + j0 * 66 + k0, T + j0 * 66 + k0 + 4, 8);
+					last_pass(T + lane, T + l2, 66, s_rot1 + lane, s_rot1 + l2, 64, T + lane, T + l2);
+				}
+			} else {
+				// ================= up to 8 short packets: four lanes per 64-point FFT =================
+				const int f = lane >> 2, u = lane & 3;
+				const bool active = f < count;
+				const uint32_t cstride = P.short_curve_stride, rcap = tb->short_posts_cap;
+				int fmode = 1;
+				for(int g = 0; g < count; ++g) {
+					const WPkt& w = wp[first + g];
+					const int md = curve_mode(tb, mapping, w.meta >> 16, ch);
+					if(md == 0) {
+						const uint32_t stt = build_curve(F, b.ys + ys_of(w), curves + (size_t) g * cstride, rcap, 64u, 256u, lane);
+						if(stt && lane == 0) atomicOr(&b.status[run.first_packet + first + g], stt);
+					}
+					if(g == f) fmode = md;
+				}
+				float2* Tf = T + f * 72;
+				if(active) {
+					const float* base = b.spectra + wp[first + f].spec_off;
+					const unsigned char* cv = curves + (size_t) f * cstride;
+					const float* s0 = base + (size_t) cp->ch[0] * 128, *s1 = base + (size_t) cp->ch[1] * 128;
+					const float* s2 = base + (size_t) cp->ch[2] * 128, *s3 = base + (size_t) cp->ch[3] * 128;
+					switch(cp->nl) {
+						case 1:  spectral_stage<1>(s0, s0, s0, s0, fmode, cv, rcap, s_invdb, s_rot0, 64, Tf, u, cp); break;
+						case 2:  spectral_stage<2>(s0, s1, s0, s0, fmode, cv, rcap, s_invdb, s_rot0, 64, Tf, u, cp); break;
+						case 3:  spectral_stage<3>(s0, s1, s2, s0, fmode, cv, rcap, s_invdb, s_rot0, 64, Tf, u, cp); break;
+						default: spectral_stage<4>(s0, s1, s2, s3, fmode, cv, rcap, s_invdb, s_rot0, 64, Tf, u, cp); break;
+					}
+				}
+				__syncwarp();
+				{
+					const int u2 = 7 - u;
+					r8_pass(Tf + u, Tf + u2, 8, s_tw0 + u * 4, s_tw0 + u2 * 4, Tf + u, Tf + u2, 9);
+					last_pass(Tf + u * 9, Tf + u2 * 9, 1, s_rot0 + u, s_rot0 + u2, 8, T + f * 64 + u, T + f * 64 + u2);
+				}
+			}
+
+			// ================= window + overlap-add + emit (hpp:1008-1059 in gather form) =================
+			const int n = flag ? 2048 : 256, Q = n / 4;
+			const float* Dstep = reinterpret_cast<const float*>(T);
+			for(int g = 0; g < count; ++g) {
+				const WPkt& w = wp[first + g];
+				const uint32_t wflags = (w.meta >> 8) & 0xffu, emit = w.emit;
+				// hpp:844-847: short blocks always use blocksize0 slopes; long blocks follow their own prev/next flags
+				const int lc = (flag && (wflags & 1u)) ? 1024 : 128;
+				const int rc = (flag && (wflags & 2u)) ? 1024 : 128;
+				const float* cur_lo = Dstep + (size_t) g * 2 * Q;
+				const float* cur_hi = cur_lo + Q;
+				const bool emits = prev_valid && emit > 0 && (run.first_packet + (uint32_t) (first + g)) != st.first_packet;
+				if(emits) {
+					const uint64_t chan_base = st.pcm_base + (uint64_t) ch * st.pcm_frames + w.pcm_off;
+					if(planar && flag && prev_n == 2048 && lc == 1024 && prev_right == 1024 && emit == 1024u && (chan_base & 3ull) == 0) {
+						ola_long_long(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, lane);
+					} else {
+						OlaGeom G;
+						G.Hp = prev_n / 4; G.H = Q;
+						G.shift = Q - prev_n / 4;
+						G.lc = lc; G.lb = Q - lc / 2;
+						G.pr = prev_right; G.rbp = prev_n / 4 - prev_right / 2;
+						G.slL = (lc == 1024) ? s_slope1 : s_slope0;
+						G.slR = (prev_right == 1024) ? s_slope1 : s_slope0;
+						for(uint32_t j = (uint32_t) lane; j < emit; j += 32u) {
+							const float v = ola_one(G, prev_lo, cur_hi, (int) j);
+							const uint64_t fidx = w.pcm_off + j;
+							const uint64_t o = planar ? st.pcm_base + (uint64_t) ch * st.pcm_frames + fidx : st.pcm_base + fidx * (uint64_t) C + (uint64_t) ch;
+							b.pcm[o] = v;
+						}
+					}
+				}
+				prev_valid = 1; prev_n = n; prev_right = rc; prev_lo = cur_lo;
+			}
+			first += count;
+			reg ^= 1;
+		}
+	}
+}
+
+}  // namespace wk
+
+size_t warp_kernel_smem_bytes(uint32_t short_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out, uint32_t* short_stride_out) {
+	const uint32_t stride = short_posts_cap * 8u + 64u;
+	uint32_t group = 8;
+	uint32_t cb = 32u * 8u + 512u;                        // one long curve: 32 records + 512 cells
+	while(group > 1 && group * stride > 2048u) --group;
+	if(group * stride > cb) cb = group * stride;
+	cb = (cb + 15u) & ~15u;
+	if(group_short_out) *group_short_out = group;
+	if(curve_bytes_out) *curve_bytes_out = cb;
+	if(short_stride_out) *short_stride_out = stride;
+	return (size_t) wk::kOffWarps + (size_t) wk::kWarps * ((size_t) wk::kWarpFixedBytes + cb);
+}
+
+cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
+                        uint32_t short_posts_cap, const float* const slope[2], const float2* const rot[2], const float2* const tw8[2],
+                        uint32_t* d_counter, int sm_count, cudaStream_t st, uint64_t* launches) {
+	if(n_runs == 0) return cudaSuccess;
+	wk::Params P;
+	P.b = b; P.runs = runs; P.n_runs = n_runs; P.C = channels; P.n_items = n_runs * channels;
+	P.counter = d_counter; P.tabs = d_tabs;
+	for(int k = 0; k < 2; ++k) { P.slope[k] = slope[k]; P.rot[k] = rot[k]; P.tw8[k] = tw8[k]; }
+	const size_t smem = warp_kernel_smem_bytes(short_posts_cap, &P.group_short, &P.curve_bytes, &P.short_curve_stride);
+	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+	cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if(e != cudaSuccess) return e;
+	e = cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st);
+	if(e != cudaSuccess) return e;
+	const uint32_t items = P.n_items;
+	uint32_t grid = (uint32_t) sm_count;
+	const uint32_t need = (items + wk::kWarps - 1) / wk::kWarps;
+	if(grid > need) grid = need;
+	wk::k_warp_synth<<<grid, wk::kThreads, smem, st>>>(P);
+	if(launches) ++*launches;
+	return cudaGetLastError();
+}
+
+}  // namespace pov

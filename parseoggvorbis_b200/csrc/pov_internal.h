@@ -76,6 +76,45 @@ struct DevSetup {
 	float2 rotc1[2], rotc6[2];
 };
 
+// ---- compact per-setup tables of the warp-autonomous kernel (kernel_warp.cu), copied into shared memory once per CTA --
+#define POV_FAST_MAX_FLOORS   4
+#define POV_FAST_MAX_MAPPINGS 4
+#define POV_FAST_MAX_STEPS    8     // coupling steps per mapping
+#define POV_FAST_MAX_DEPS     4     // channels one channel's un-coupled value may depend on (itself included)
+#define POV_FAST_MAX_X        1024  // largest floor X (segment lengths index the reciprocal table)
+
+struct FastFloor {
+	uint32_t n_posts, n_levels, range, multiplier;
+	// per lane i (16 bytes, one LDS.128):
+	//   [0] lo | hi << 8 | level << 16 | sorted_idx << 24     (post i; sorted_idx: post index of the i-th smallest X)
+	//   [1] (xs[i] - xs[lo]) | (xs[hi] - xs[lo]) << 16         (prediction numerator / denominator, Utils.hpp:122-137)
+	//   [2] ceil(2^32 / (xs[hi] - xs[lo]))                     (exact division by multiplication, see kernel_warp.cu)
+	//   [3] X of the i-th smallest post
+	uint32_t post[32][4];
+};
+
+// How the warp that owns channel c of a mapping un-couples it (hpp:1213-1241): the channels it has to load
+// (ch[0] == c) and the sub-sequence of coupling steps, in application order, that can reach c; indices are local.
+struct FastCouple {
+	uint8_t nl, nsteps;
+	uint8_t ch[POV_FAST_MAX_DEPS];
+	uint8_t sm[POV_FAST_MAX_STEPS], sa[POV_FAST_MAX_STEPS];
+	uint8_t pad[2];
+};
+
+struct FastTables {
+	FastFloor  floors[POV_FAST_MAX_FLOORS];
+	FastCouple couple[POV_FAST_MAX_MAPPINGS][POV_MAX_CHANNELS];
+	uint8_t floor_of_ch[POV_FAST_MAX_MAPPINGS][POV_MAX_CHANNELS];
+	uint8_t ncoup[POV_FAST_MAX_MAPPINGS];                           // full coupling list, for the nonzero propagate rule (hpp:1174-1180)
+	uint8_t cmag[POV_FAST_MAX_MAPPINGS][POV_FAST_MAX_STEPS], cang[POV_FAST_MAX_MAPPINGS][POV_FAST_MAX_STEPS];
+	uint8_t mode_flag[POV_MAX_MODES], mode_map[POV_MAX_MODES];
+	uint32_t channels;
+	uint32_t short_posts_cap;          // record capacity of a short-block curve (multiple of 4)
+	uint32_t pad[5];
+};
+static_assert(sizeof(FastTables) % 16 == 0, "FastTables is moved with 16-byte bulk copies");
+
 // Work item of the fused kernel: a run of consecutive packets of one stream. The first packet of a run that is
 // not the first packet of its stream is a halo: it is transformed again only to rebuild the overlap half.
 struct DevRun {
