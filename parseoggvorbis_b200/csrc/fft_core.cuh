@@ -17,8 +17,8 @@ namespace pov {
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-	float2 t = __fmul2_rn(make_float2(a.x, a.x), w);                           // ar*wr, ar*wi
-	return __ffma2_rn(make_float2(-a.y, a.y), make_float2(w.y, w.x), t);        // -ai*wi+.., ai*wr+..
+	const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(w.y, w.x));  // ai*wi, ai*wr
+	return __ffma2_rn(make_float2(a.x, a.x), w, make_float2(-t.x, t.y));        // ar*wr - ai*wi, ar*wi + ai*wr
 }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }    // a * (-i)
 #define POV_SQRT1_2 0.70710678118654752440f

@@ -551,6 +551,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				return yo;
 			};
 
+			// pull the next step's spectra towards L2 while this step computes: one 128-byte line per lane and channel
+			if(first + count < run_n) {
+				const WPkt& nw = wp[first + count];
+				const uint32_t nmode = nw.meta & 0xffu;
+				const uint32_t nhalf = tb->mode_flag[nmode] ? 1024u : 128u;
+				const FastCouple* ncp = &tb->couple[tb->mode_map[nmode]][ch];
+				if((uint32_t) lane * 32u < nhalf)
+					for(int i = 0; i < (int) ncp->nl; ++i) prefetch_l2(b.spectra + nw.spec_off + (size_t) ncp->ch[i] * nhalf + (size_t) lane * 32u);
+			}
 			if(flag) {
 				// ================= one long packet: the whole warp is one 512-point FFT =================
 				const WPkt& w = wp[first];
