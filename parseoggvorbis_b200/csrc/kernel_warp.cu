@@ -60,10 +60,12 @@ constexpr int kOffTw1    = kOffSlope1 + 1024 * 4;
 constexpr int kOffTw0    = kOffTw1 + 288 * 8;
 constexpr int kOffRot1   = kOffTw0 + 32 * 8;
 constexpr int kOffRot0   = kOffRot1 + 512 * 8;
-constexpr int kOffBar    = kOffRot0 + 64 * 8;
+constexpr int kOffRecip  = kOffRot0 + 64 * 8;                       // ceil(2^32 / d), d <= POV_FAST_MAX_X
+constexpr int kOffBar    = kOffRecip + (POV_FAST_MAX_X + 4) * 4;
 constexpr int kOffWarps  = kOffBar + 16;
 static_assert(kOffWarps % 16 == 0, "warp areas must stay 16-byte aligned");
-constexpr int kWarpFixedBytes = 2 * kRegionF2 * 8 + kPktCap * (int) sizeof(WPkt);
+constexpr int kFsStride = 36;           // per packet: final Y of every post in ascending-x order (uint8 x 32) + step2 mask (uint32)
+constexpr int kWarpFixedBytes = 2 * kRegionF2 * 8 + kPktCap * (int) sizeof(WPkt) + kPktCap * kFsStride;
 
 // ---- mbarrier / TMA bulk copy (SASS: UBLKCP + SYNCS) ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -123,22 +125,38 @@ __device__ __forceinline__ uint32_t bytes_prefix_max(uint32_t v) {      // littl
 	return v;
 }
 
-// floor1 step 1 (amplitude unwrap, hpp:521-559) + step 2 set-up (hpp:563-585) for one curve by one warp.
-// Returns POV_PKT_* bits (warp uniform).
-__device__ __noinline__ uint32_t build_curve(const FastFloor* __restrict__ F, const uint16_t* __restrict__ ysp, unsigned char* __restrict__ curve,
-                                             uint32_t rec_cap, uint32_t cells, uint32_t n, int lane) {
-	const int posts = (int) F->n_posts;
+// floor1 step 1 (amplitude unwrap, hpp:521-559) for ALL packets of a run at once: lane p owns packet p and walks its
+// posts serially (the neighbour DAG makes the posts of one curve sequential, but the <= 32 curves of a run are
+// independent). The final Y values leave in ascending-x order as bytes, with the step2 flags as a bit mask, 36 bytes per
+// packet; the hpp:536 / hpp:587 checks are evaluated here with full-width values and reported per packet.
+// scratch: [32 posts][32 lanes] uint16, aliasing the (idle) FFT work regions.
+__device__ __noinline__ void unwrap_run(const FastTables* __restrict__ tb, const WPkt* __restrict__ wp, int run_n, int ch,
+                                        const uint16_t* __restrict__ ys, uint16_t* __restrict__ scratch, unsigned char* __restrict__ fs,
+                                        uint32_t* __restrict__ status, int lane) {
+	const bool have = lane < run_n;
+	const uint32_t meta = have ? wp[lane].meta : 0u;
+	const uint32_t mode = meta & 0xffu, used = meta >> 16;
+	const uint32_t mapping = tb->mode_map[mode];
+	const bool act = have && ((used >> ch) & 1u);
+	const FastFloor* F = &tb->floors[tb->floor_of_ch[mapping][ch]];
+	const int posts = act ? (int) F->n_posts : 0;
+	const int maxposts = __reduce_max_sync(FULL, posts);
+	if(maxposts == 0) return;
+	// Y list of this channel inside the packet: after the lists of the used channels before it (hpp:498-518 order)
+	uint64_t yo = have ? wp[lane].ys_off : 0ull;
+	for(int cc = 0; cc < ch; ++cc)
+		if((used >> cc) & 1u) yo += tb->floors[tb->floor_of_ch[mapping][cc]].n_posts;
+	const uint16_t* yp = ys + yo;
 	const uint32_t range = F->range;
-	const bool have = lane < posts;
-	const uint4 t = *reinterpret_cast<const uint4*>(F->post[lane]);
-	uint32_t cur = have ? (uint32_t) __ldg(ysp + lane) : 0u;
-	const uint32_t val = cur;
-	const int lo = (int) (t.x & 0xffu), hi = (int) ((t.x >> 8) & 0xffu), lvl = (int) ((t.x >> 16) & 0xffu), si = (int) (t.x >> 24);
-	uint32_t flags = 0, bad = 0;
-	const int levels = (int) F->n_levels;
-	for(int lv = 1; lv < levels; ++lv) {
-		const uint32_t y0 = __shfl_sync(FULL, cur, lo), y1 = __shfl_sync(FULL, cur, hi);
-		if(lvl == lv) {
+	uint32_t flags = 3u, bad = 0u;
+	uint16_t* col = scratch + lane;
+	if(act) { col[0] = __ldg(yp); col[32] = __ldg(yp + 1); }
+	for(int i = 2; i < maxposts; ++i) {
+		if(i < posts) {
+			const uint4 t = *reinterpret_cast<const uint4*>(F->post[i]);
+			const uint32_t lo = t.x & 0xffu, hi = (t.x >> 8) & 0xffu;
+			const uint32_t y0 = col[lo * 32], y1 = col[hi * 32];
+			const uint32_t val = __ldg(yp + i);
 			const bool up = y1 >= y0;
 			const uint32_t ady = up ? (y1 - y0) : (y0 - y1);
 			// floor(ady * dxn / adx) by multiplication with ceil(2^32/adx): exact while ady * dxn * adx < 2^32 (ady < 2^12)
@@ -150,52 +168,79 @@ __device__ __noinline__ uint32_t build_curve(const FastFloor* __restrict__ F, co
 			const uint32_t room = min(high_room, low_room) * 2;
 			uint32_t fin = predicted;
 			if(val != 0) {
-				flags |= (1u << lo) | (1u << hi) | (1u << lane);
+				flags |= (1u << lo) | (1u << hi) | (1u << i);
 				if(val >= room) fin = (high_room > low_room) ? val - low_room + predicted : predicted - val + high_room - 1;
 				else fin = (val & 1) ? predicted - (val + 1) / 2 : predicted + val / 2;
 			}
-			cur = fin;
+			col[i * 32] = (uint16_t) min(fin, 0xFFFFu);
 		}
 	}
-	flags = __reduce_or_sync(FULL, flags) | 3u;
-	// lane = position in ascending-x order
-	const uint32_t fy = __shfl_sync(FULL, cur, si);
-	const bool f = have && ((flags >> si) & 1u);
-	const uint32_t mask = __ballot_sync(FULL, f);
+	// ascending-x order, step2 mask, and hpp:587 CHECK(floor[i] < 256) over the n bins the reference renders: segments are
+	// monotone, so the maxima are at rendered end points; a segment cut by bin n-1 needs y(n-1)
+	const uint32_t n = tb->mode_flag[mode] ? 2048u : 256u;
+	const uint32_t mult = F->multiplier;
+	uint32_t smask = 0u, xp = 0u, ypv = 0u;
+	bool havep = false;
+	unsigned char* out = fs + lane * kFsStride;
+	for(int sidx = 0; sidx < maxposts; ++sidx) {
+		if(sidx < posts) {
+			const uint32_t si = F->post[sidx][0] >> 24, x = F->post[sidx][3] & 0xffffu;
+			const uint32_t y = col[si * 32];
+			out[sidx] = (unsigned char) min(y, 255u);
+			if((flags >> si) & 1u) {
+				smask |= 1u << sidx;
+				const uint32_t yv = min(y * mult, 0xFFFFu);
+				if(x < n && yv >= 256u) bad |= POV_PKT_FLOOR_RANGE;
+				if(havep && xp < n && x > n - 1) {
+					const bool down = yv < ypv;
+					const uint32_t ady = down ? ypv - yv : yv - ypv, dx = x - xp;
+					const uint32_t q = (uint32_t) (((uint64_t) (n - 1 - xp) * ady) / dx);
+					if((down ? ypv - q : ypv + q) >= 256u) bad |= POV_PKT_FLOOR_RANGE;
+				}
+				xp = x; ypv = yv; havep = true;
+			}
+		}
+	}
+	if(act) {
+		*reinterpret_cast<uint32_t*>(out + 32) = smask;
+		if(bad) atomicOr(status + lane, bad);
+	}
+	__syncwarp();
+}
+
+// floor1 step 2 set-up (hpp:563-585) of one curve by one warp: segment records + cell index from the final Ys.
+__device__ __noinline__ void build_records(const FastFloor* __restrict__ F, const unsigned char* __restrict__ fsp, unsigned char* __restrict__ curve,
+                                           uint32_t rec_cap, uint32_t cells, const uint32_t* __restrict__ recip, int lane) {
+	const int posts = (int) F->n_posts;
+	const bool have = lane < posts;
+	const uint32_t mask = *reinterpret_cast<const uint32_t*>(fsp + 32);
+	const uint32_t yb = fsp[lane];
+	const uint32_t x0 = F->post[lane][3] & 0xffffu;
+	const bool f = have && ((mask >> lane) & 1u);
 	const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-	const uint32_t x0 = t.w & 0xffffu;
-	const uint32_t y0 = min(fy * F->multiplier, 0xFFFFu);
+	const uint32_t y0 = min(yb * F->multiplier, 1023u);
 	const uint32_t above = (lane == 31) ? 0u : (mask & ~((2u << lane) - 1u));
 	const bool last = above == 0u;
 	const int nlane = last ? lane : (__ffs((int) above) - 1);
 	const uint32_t pn = __shfl_sync(FULL, x0 | (y0 << 16), nlane);
 	const uint32_t x1 = pn & 0xffffu, y1 = pn >> 16;
-	// hpp:587 CHECK(floor[i] < 256) over the n bins the reference renders: segments are monotone, so the maxima are at
-	// rendered end points; a segment cut by bin n-1 needs y(n-1)
-	bool over = false;
-	if(f) {
-		if(x0 < n && y0 >= 256u) over = true;
-		if(!last && x0 < n && x1 > n - 1) {
-			const bool down = y1 < y0;
-			const uint32_t ady = down ? y0 - y1 : y1 - y0, dx = x1 - x0;
-			const uint32_t q = (uint32_t) (((uint64_t) (n - 1 - x0) * ady) / dx);
-			if((down ? y0 - q : y0 + q) >= 256u) over = true;
-		}
-	}
-	if(__any_sync(FULL, over)) bad |= POV_PKT_FLOOR_RANGE;
 
 	uint2* rec = reinterpret_cast<uint2*>(curve);
 	uint8_t* idx = curve + rec_cap * 8u;
 	if((uint32_t) lane < cells / 16u) reinterpret_cast<uint4*>(idx)[lane] = make_uint4(0, 0, 0, 0);
 	__syncwarp();
 	if(f) {
-		const uint32_t yc0 = min(y0, 1023u), yc1 = min(y1, 1023u);
 		uint2 r;
-		if(last) r = make_uint2(x0 | (2047u << 11) | (yc0 << 22), 0u);
+		if(last) r = make_uint2(x0 | (2047u << 11) | (y0 << 22), 0u);
 		else {
-			const bool down = yc1 < yc0;
-			const uint32_t ady = down ? yc0 - yc1 : yc1 - yc0, adx = x1 - x0;
-			r = make_uint2(x0 | (x1 << 11) | (yc0 << 22), (((ady << 20) + adx - 1u) / adx) | (down ? 0x80000000u : 0u));
+			const bool down = y1 < y0;
+			const uint32_t ady = down ? y0 - y1 : y1 - y0, adx = x1 - x0;
+			// slope = ceil(2^20 |dy| / dx) = floor(N / dx), N = (|dy| << 20) + dx - 1 < 2^31: the table quotient is exact or one too big
+			const uint32_t N = (ady << 20) + adx - 1u;
+			uint32_t q = __umulhi(N, recip[adx]);
+			if(q * adx > N) --q;
+			if(adx == 1u) q = N;
+			r = make_uint2(x0 | (x1 << 11) | (y0 << 22), q | (down ? 0x80000000u : 0u));
 		}
 		rec[rank] = r;
 		// first 2-bin cell whose first bin is >= x0; only the last claimant of a cell writes
@@ -225,7 +270,6 @@ __device__ __noinline__ uint32_t build_curve(const FastFloor* __restrict__ F, co
 		if(mine) reinterpret_cast<uint4*>(idx)[lane] = make_uint4(__vmaxu4(w.x, bc), __vmaxu4(w.y, bc), __vmaxu4(w.z, bc), __vmaxu4(w.w, bc));
 	}
 	__syncwarp();
-	return __reduce_or_sync(FULL, bad);
 }
 
 // Two consecutive bins x, x+1 (x even) of a curve as inverse-dB table values (hpp:586-589).
@@ -474,6 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	const float2* s_tw0 = reinterpret_cast<const float2*>(smem + kOffTw0);      // 256:  pass L=64 (32 float2)
 	const float2* s_rot1 = reinterpret_cast<const float2*>(smem + kOffRot1);
 	const float2* s_rot0 = reinterpret_cast<const float2*>(smem + kOffRot0);
+	uint32_t* s_recip = reinterpret_cast<uint32_t*>(smem + kOffRecip);
 	uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -494,6 +539,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 		tma_bulk_g2s(smem + kOffRot1, P.rot[1], 512u * 8u, s_bar);
 		tma_bulk_g2s(smem + kOffRot0, P.rot[0], 64u * 8u, s_bar);
 	}
+	for(uint32_t d = threadIdx.x; d <= POV_FAST_MAX_X; d += kThreads)
+		s_recip[d] = (d < 2) ? 0xFFFFFFFFu : (uint32_t) ((0x100000000ull + d - 1) / d);
 	__syncthreads();
 	mbar_wait(s_bar, 0);
 
@@ -502,6 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	unsigned char* wbase = smem + kOffWarps + (size_t) warp * warp_bytes;
 	float2* region0 = reinterpret_cast<float2*>(wbase);      // two FFT work regions, used alternately by consecutive steps
 	WPkt* wp = reinterpret_cast<WPkt*>(wbase + 2 * kRegionF2 * 8);
+	unsigned char* fs = wbase + 2 * kRegionF2 * 8 + kPktCap * (int) sizeof(WPkt);
 	unsigned char* curves = wbase + kWarpFixedBytes;
 
 	const int C = (int) P.C;
@@ -526,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 		}
 		const pov_stream st = b.streams[b.packets[run.first_packet].stream];
 		__syncwarp();
+		unwrap_run(tb, wp, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(region0), fs, b.status + run.first_packet, lane);
 
 		int prev_valid = 0, prev_n = 0, prev_right = 0;
 		const float* prev_lo = nullptr;
@@ -542,15 +591,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			int count = 1;
 			if(!flag) while(count < (int) P.group_short && first + count < run_n && (wp[first + count].meta & 0xffu) == mode) ++count;
 
-			// Y offset of this channel's list inside a packet: the posts of the used channels before it (hpp:498-518 order)
-			auto ys_of = [&](const WPkt& w) {
-				uint64_t yo = w.ys_off;
-				const uint32_t used = w.meta >> 16;
-				for(int cc = 0; cc < ch; ++cc)
-					if((used >> cc) & 1u) yo += tb->floors[tb->floor_of_ch[mapping][cc]].n_posts;
-				return yo;
-			};
-
 			// pull the next step's spectra towards L2 while this step computes: one 128-byte line per lane and channel
 			if(first + count < run_n) {
 				const WPkt& nw = wp[first + count];
@@ -564,10 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				// ================= one long packet: the whole warp is one 512-point FFT =================
 				const WPkt& w = wp[first];
 				const int fmode = curve_mode(tb, mapping, w.meta >> 16, ch);
-				if(fmode == 0) {
-					const uint32_t stt = build_curve(F, b.ys + ys_of(w), curves, 32u, 512u, 2048u, lane);
-					if(stt && lane == 0) atomicOr(&b.status[run.first_packet + first], stt);
-				}
+				if(fmode == 0) build_records(F, fs + first * kFsStride, curves, 32u, 512u, s_recip, lane);
 				const float* base = b.spectra + w.spec_off;
 				const float* s0 = base + (size_t) cp->ch[0] * 1024, *s1 = base + (size_t) cp->ch[1] * 1024;
 				const float* s2 = base + (size_t) cp->ch[2] * 1024, *s3 = base + (size_t) cp->ch[3] * 1024;
@@ -594,10 +631,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				for(int g = 0; g < count; ++g) {
 					const WPkt& w = wp[first + g];
 					const int md = curve_mode(tb, mapping, w.meta >> 16, ch);
-					if(md == 0) {
-						const uint32_t stt = build_curve(F, b.ys + ys_of(w), curves + (size_t) g * cstride, rcap, 64u, 256u, lane);
-						if(stt && lane == 0) atomicOr(&b.status[run.first_packet + first + g], stt);
-					}
+					if(md == 0) build_records(F, fs + (first + g) * kFsStride, curves + (size_t) g * cstride, rcap, 64u, s_recip, lane);
 					if(g == f) fmode = md;
 				}
 				float2* Tf = T + f * 72;
