@@ -118,13 +118,7 @@ __device__ __forceinline__ float uncouple_ang(float m, float a) {
 // fractional part of k*|dy|/dx (<= 1 - 1/dx) over the next integer. |dy| <= 1023 keeps the slope below 2^30. Curves that
 // violate these bounds also violate hpp:587 and are reported through the packet status word (samples unspecified, as in
 // the reference, which aborts the stream there).
-// Block layout: uint2 rec[cap] | uint8 idx[cells], cells = n/4: idx[c] = record that contains bin 2c.
-__device__ __forceinline__ uint32_t bytes_prefix_max(uint32_t v) {      // little-endian: byte i = max(byte 0..i)
-	v = __vmaxu4(v, v << 8);
-	v = __vmaxu4(v, v << 16);
-	return v;
-}
-
+// Block layout: uint2 rec[cap] | uint2 tab[n/64] (rank table, see build_records).
 // floor1 step 1 (amplitude unwrap, hpp:521-559) for ALL packets of a run at once: lane p owns packet p and walks its
 // posts serially (the neighbour DAG makes the posts of one curve sequential, but the <= 32 curves of a run are
 // independent). The final Y values leave in ascending-x order as bytes, with the step2 flags as a bit mask, 36 bytes per
@@ -208,9 +202,12 @@ __device__ __noinline__ void unwrap_run(const FastTables* __restrict__ tb, const
 	__syncwarp();
 }
 
-// floor1 step 2 set-up (hpp:563-585) of one curve by one warp: segment records + cell index from the final Ys.
+// floor1 step 2 set-up (hpp:563-585) of one curve by one warp: segment records + rank table from the final Ys.
+// Rank table: for every 32-bin word w of the curve, tab[w] = (bitmap of the flagged posts inside the word,
+// number of flagged posts before the word - 1); the record that contains bin x is
+//   tab[x >> 5].y + popc(tab[x >> 5].x & (0xFFFFFFFF >> (31 - (x & 31)))).
 __device__ __noinline__ void build_records(const FastFloor* __restrict__ F, const unsigned char* __restrict__ fsp, unsigned char* __restrict__ curve,
-                                           uint32_t rec_cap, uint32_t cells, const uint32_t* __restrict__ recip, int lane) {
+                                           uint32_t rec_cap, uint32_t nwords, const uint32_t* __restrict__ recip, int lane) {
 	const int posts = (int) F->n_posts;
 	const bool have = lane < posts;
 	const uint32_t mask = *reinterpret_cast<const uint32_t*>(fsp + 32);
@@ -226,8 +223,9 @@ __device__ __noinline__ void build_records(const FastFloor* __restrict__ F, cons
 	const uint32_t x1 = pn & 0xffffu, y1 = pn >> 16;
 
 	uint2* rec = reinterpret_cast<uint2*>(curve);
-	uint8_t* idx = curve + rec_cap * 8u;
-	if((uint32_t) lane < cells / 16u) reinterpret_cast<uint4*>(idx)[lane] = make_uint4(0, 0, 0, 0);
+	uint2* tab = rec + rec_cap;
+	uint32_t* bits = reinterpret_cast<uint32_t*>(tab);          // word w at bits[2w] while the bitmap is collected
+	if((uint32_t) lane < nwords) bits[2 * lane] = 0u;
 	__syncwarp();
 	if(f) {
 		uint2 r;
@@ -243,39 +241,27 @@ __device__ __noinline__ void build_records(const FastFloor* __restrict__ F, cons
 			r = make_uint2(x0 | (x1 << 11) | (y0 << 22), q | (down ? 0x80000000u : 0u));
 		}
 		rec[rank] = r;
-		// first 2-bin cell whose first bin is >= x0; only the last claimant of a cell writes
-		const uint32_t cell = (x0 + 1) >> 1;
-		const uint32_t ncell = last ? 0xFFFFFFFFu : ((x1 + 1) >> 1);
-		if(cell < cells && ncell != cell) idx[cell] = (uint8_t) rank;
+		if((x0 >> 5) < nwords) atomicOr(&bits[2 * (x0 >> 5)], 1u << (x0 & 31u));
 	}
 	__syncwarp();
-	// inclusive max-scan over the cell bytes: four words per lane
 	{
-		const uint32_t words = cells / 4;
-		const bool mine = (uint32_t) (4 * lane) < words;
-		uint4 w = mine ? reinterpret_cast<const uint4*>(idx)[lane] : make_uint4(0, 0, 0, 0);
-		w.x = bytes_prefix_max(w.x);
-		w.y = __vmaxu4(bytes_prefix_max(w.y), (w.x >> 24) * 0x01010101u);
-		w.z = __vmaxu4(bytes_prefix_max(w.z), (w.y >> 24) * 0x01010101u);
-		w.w = __vmaxu4(bytes_prefix_max(w.w), (w.z >> 24) * 0x01010101u);
-		uint32_t incl = w.w >> 24;
+		const uint32_t w = ((uint32_t) lane < nwords) ? bits[2 * lane] : 0u;
+		uint32_t incl = __popc(w);
 #pragma unroll
 		for(int o = 1; o < 32; o <<= 1) {
 			const uint32_t v = __shfl_up_sync(FULL, incl, o);
-			if(lane >= o) incl = max(incl, v);
+			if(lane >= o) incl += v;
 		}
-		uint32_t before = __shfl_up_sync(FULL, incl, 1);
-		if(lane == 0) before = 0;
-		const uint32_t bc = before * 0x01010101u;
-		if(mine) reinterpret_cast<uint4*>(idx)[lane] = make_uint4(__vmaxu4(w.x, bc), __vmaxu4(w.y, bc), __vmaxu4(w.z, bc), __vmaxu4(w.w, bc));
+		if((uint32_t) lane < nwords) bits[2 * lane + 1] = incl - __popc(w) - 1u;
 	}
 	__syncwarp();
 }
 
 // Two consecutive bins x, x+1 (x even) of a curve as inverse-dB table values (hpp:586-589).
-__device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, const uint8_t* __restrict__ idx, uint32_t x,
+__device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, const uint2* __restrict__ tab, uint32_t x,
                                              const float* __restrict__ invdb) {
-	const uint32_t s = idx[x >> 1];
+	const uint2 t = tab[x >> 5];
+	const uint32_t s = t.y + __popc(t.x & (0xFFFFFFFFu >> (31u - (x & 31u))));
 	uint2 r = rec[s];
 	float2 out;
 	{
@@ -372,7 +358,7 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ src0, cons
                                             const FastCouple* __restrict__ cp) {
 	const int J = Q >> 3, M = 2 * Q;
 	const uint2* rec = reinterpret_cast<const uint2*>(curve);
-	const uint8_t* idx = curve + rec_cap * 8u;
+	const uint2* idx = rec + rec_cap;
 	const int nsteps = (NL > 1) ? (int) cp->nsteps : 0;
 	const float* src[4] = {src0, src1, src2, src3};
 	float2 nva[NL], nvb[NL];
@@ -381,7 +367,7 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ src0, cons
 		nva[i] = __ldg(reinterpret_cast<const float2*>(src[i] + 2 * u));
 		nvb[i] = __ldg(reinterpret_cast<const float2*>(src[i] + M - 2 - 2 * u));
 	}
-#pragma unroll 2
+#pragma unroll 1
 	for(int m = 0; m < 8; ++m) {
 		const int jp = u + J * m;                  // point jp and its mirror Q-1-jp
 		float2 va[NL], vb[NL];                     // bins (2jp, 2jp+1) and (M-2-2jp, M-1-2jp) of every needed channel
@@ -604,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				// ================= one long packet: the whole warp is one 512-point FFT =================
 				const WPkt& w = wp[first];
 				const int fmode = curve_mode(tb, mapping, w.meta >> 16, ch);
-				if(fmode == 0) build_records(F, fs + first * kFsStride, curves, 32u, 512u, s_recip, lane);
+				if(fmode == 0) build_records(F, fs + first * kFsStride, curves, 32u, 32u, s_recip, lane);
 				const float* base = b.spectra + w.spec_off;
 				const float* s0 = base + (size_t) cp->ch[0] * 1024, *s1 = base + (size_t) cp->ch[1] * 1024;
 				const float* s2 = base + (size_t) cp->ch[2] * 1024, *s3 = base + (size_t) cp->ch[3] * 1024;
@@ -631,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				for(int g = 0; g < count; ++g) {
 					const WPkt& w = wp[first + g];
 					const int md = curve_mode(tb, mapping, w.meta >> 16, ch);
-					if(md == 0) build_records(F, fs + (first + g) * kFsStride, curves + (size_t) g * cstride, rcap, 64u, s_recip, lane);
+					if(md == 0) build_records(F, fs + (first + g) * kFsStride, curves + (size_t) g * cstride, rcap, 4u, s_recip, lane);
 					if(g == f) fmode = md;
 				}
 				float2* Tf = T + f * 72;
@@ -698,9 +684,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 }  // namespace wk
 
 size_t warp_kernel_smem_bytes(uint32_t short_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out, uint32_t* short_stride_out) {
-	const uint32_t stride = short_posts_cap * 8u + 64u;
+	const uint32_t stride = short_posts_cap * 8u + 32u;        // records + 4 rank-table words
 	uint32_t group = 8;
-	uint32_t cb = 32u * 8u + 512u;                        // one long curve: 32 records + 512 cells
+	uint32_t cb = 32u * 8u + 32u * 8u;                    // one long curve: 32 records + 32 rank-table words
 	while(group > 1 && group * stride > 2048u) --group;
 	if(group * stride > cb) cb = group * stride;
 	cb = (cb + 15u) & ~15u;
