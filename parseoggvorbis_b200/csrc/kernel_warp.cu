@@ -67,6 +67,8 @@ static_assert(kOffWarps % 16 == 0, "warp areas must stay 16-byte aligned");
 constexpr int kFsStride = 36;           // per packet: final Y of every post in ascending-x order (uint8 x 32) + step2 mask (uint32)
 constexpr int kWarpFixedBytes = 2 * kRegionF2 * 8 + kPktCap * (int) sizeof(WPkt) + kPktCap * kFsStride;
 
+extern __shared__ __align__(128) unsigned char g_smem[];     // the kernel's dynamic shared memory (map above)
+
 // ---- mbarrier / TMA bulk copy (SASS: UBLKCP + SYNCS) ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -89,6 +91,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Shared-memory arguments of the out-of-line routines travel as 32-bit shared-window addresses: inside the callee the
+// pointer is rebuilt with a shared->generic conversion that the compiler folds, so every access is a plain LDS/STS
+// (a generic pointer argument would cost a window-base subtraction per access).
+template <class T> __device__ __forceinline__ T* sptr(uint32_t a) { return reinterpret_cast<T*>(__cvta_shared_to_generic((size_t) a)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void uncouple_f(float& m, float& a) {   // hpp:1220-1239, branch-free
@@ -308,16 +314,18 @@ __device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ t
 }
 
 // Radix-8 DIF pass of two butterflies per lane: inputs in*[m*sin], outputs out*[k*sout] (twiddled by tw*).
-__device__ __noinline__ void r8_pass(const float2* inA, const float2* inB, int sin, const float2* twA, const float2* twB,
-                                     float2* outA, float2* outB, int sout) {
+// All addresses are shared-window byte addresses, strides are in float2 units.
+__device__ __noinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t twA_, uint32_t twB_, uint32_t outA_, uint32_t outB_, int sout) {
+	const float2* inA = sptr<const float2>(inA_); const float2* inB = sptr<const float2>(inB_);
+	float2* outA = sptr<float2>(outA_); float2* outB = sptr<float2>(outB_);
 	float2 a[8], b[8];
 #pragma unroll
 	for(int m = 0; m < 8; ++m) { a[m] = inA[m * sin]; b[m] = inB[m * sin]; }
 	__syncwarp();
 	dft8(a);
-	twiddle8(a, twA);
+	twiddle8(a, sptr<const float2>(twA_));
 	dft8(b);
-	twiddle8(b, twB);
+	twiddle8(b, sptr<const float2>(twB_));
 #pragma unroll
 	for(int k = 0; k < 8; ++k) { outA[k * sout] = a[k]; outB[k * sout] = b[k]; }
 	__syncwarp();
@@ -325,8 +333,10 @@ __device__ __noinline__ void r8_pass(const float2* inA, const float2* inB, int s
 
 // Last pass + post-rotation of butterflies kkA and kkB = J-1-kkA (rotA = rot + kkA, rotB = rot + kkB):
 //   c[k] = X[k] * w[k];  D2[k] = (D[2k], D[2k+1]) = (Re c[k], -Im c[Q-1-k]);  Q-1-(kkA + J k2) = kkB + J (7-k2)
-__device__ __noinline__ void last_pass(const float2* inA, const float2* inB, int sin, const float2* rotA, const float2* rotB, int J,
-                                       float2* outA, float2* outB) {
+__device__ __noinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t rotA_, uint32_t rotB_, int J, uint32_t outA_, uint32_t outB_) {
+	const float2* inA = sptr<const float2>(inA_); const float2* inB = sptr<const float2>(inB_);
+	const float2* rotA = sptr<const float2>(rotA_); const float2* rotB = sptr<const float2>(rotB_);
+	float2* outA = sptr<float2>(outA_); float2* outB = sptr<float2>(outB_);
 	float2 a[8], b[8];
 #pragma unroll
 	for(int m = 0; m < 8; ++m) { a[m] = inA[m * sin]; b[m] = inB[m * sin]; }
@@ -352,20 +362,24 @@ __device__ __noinline__ void last_pass(const float2* inA, const float2* inB, int
 // src*: spectra ([n/2] floats) of the local channels of this lane's packet (src0 = this warp's channel);
 // fmode: 0 evaluate the curve, 1 multiply by 1 (hpp:1247 skipped), 2 multiply by 0.
 template <int NL>
-__device__ __noinline__ void spectral_stage(const float* __restrict__ src0, const float* __restrict__ src1, const float* __restrict__ src2,
-                                            const float* __restrict__ src3, int fmode, const unsigned char* __restrict__ curve, uint32_t rec_cap,
-                                            const float* __restrict__ invdb, const float2* __restrict__ rot, int Q, float2* __restrict__ Tf, int u,
-                                            const FastCouple* __restrict__ cp) {
+__device__ __noinline__ void spectral_stage(const float* __restrict__ base, int o0, int o1, int o2, int o3, int fmode, uint32_t curve_, uint32_t rec_cap,
+                                            uint32_t rot_, int Q, uint32_t Tf_, int u, uint32_t cp_) {
 	const int J = Q >> 3, M = 2 * Q;
-	const uint2* rec = reinterpret_cast<const uint2*>(curve);
-	const uint2* idx = rec + rec_cap;
+	const uint2* rec = sptr<const uint2>(curve_);
+	const uint2* tab = rec + rec_cap;
+	const float* invdb = reinterpret_cast<const float*>(g_smem + kOffInvDb);
+	const float2* rot = sptr<const float2>(rot_);
+	float2* Tf = sptr<float2>(Tf_);
+	const FastCouple* cp = sptr<const FastCouple>(cp_);
+	// coupling program in registers (the loop below stores to shared memory, so nothing would be hoisted otherwise)
 	const int nsteps = (NL > 1) ? (int) cp->nsteps : 0;
-	const float* src[4] = {src0, src1, src2, src3};
+	const bool last_mag = (NL > 1 && nsteps > 0) ? (cp->sm[nsteps - 1] == 0) : false;
+	const int off[4] = {o0, o1, o2, o3};
 	float2 nva[NL], nvb[NL];
 #pragma unroll
 	for(int i = 0; i < NL; ++i) {
-		nva[i] = __ldg(reinterpret_cast<const float2*>(src[i] + 2 * u));
-		nvb[i] = __ldg(reinterpret_cast<const float2*>(src[i] + M - 2 - 2 * u));
+		nva[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + 2 * u)));
+		nvb[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + M - 2 - 2 * u)));
 	}
 #pragma unroll 1
 	for(int m = 0; m < 8; ++m) {
@@ -376,8 +390,8 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ src0, cons
 		if(m < 7) {
 #pragma unroll
 			for(int i = 0; i < NL; ++i) {
-				nva[i] = __ldg(reinterpret_cast<const float2*>(src[i] + 2 * (jp + J)));
-				nvb[i] = __ldg(reinterpret_cast<const float2*>(src[i] + M - 2 - 2 * (jp + J)));
+				nva[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + 2 * (jp + J))));
+				nvb[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + M - 2 - 2 * (jp + J))));
 			}
 		}
 		if(NL == 2) {
@@ -386,7 +400,7 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ src0, cons
 				else                { uncouple2(va[NL - 1], va[0]); uncouple2(vb[NL - 1], vb[0]); }
 			}
 			if(nsteps > 0) {      // last step: only this warp's channel (local index 0) is needed
-				if(cp->sm[nsteps - 1] == 0) {
+				if(last_mag) {
 					va[0].x = uncouple_mag(va[0].x, va[NL - 1].x); va[0].y = uncouple_mag(va[0].y, va[NL - 1].y);
 					vb[0].x = uncouple_mag(vb[0].x, vb[NL - 1].x); vb[0].y = uncouple_mag(vb[0].y, vb[NL - 1].y);
 				} else {
@@ -413,8 +427,8 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ src0, cons
 		}
 		float2 fa, fb;
 		if(fmode == 0) {
-			fa = curve_pair(rec, idx, (uint32_t) (2 * jp), invdb);
-			fb = curve_pair(rec, idx, (uint32_t) (M - 2 - 2 * jp), invdb);
+			fa = curve_pair(rec, tab, (uint32_t) (2 * jp), invdb);
+			fb = curve_pair(rec, tab, (uint32_t) (M - 2 - 2 * jp), invdb);
 		} else {
 			const float fill = (fmode == 1) ? 1.f : 0.f;
 			fa = make_float2(fill, fill); fb = fa;
@@ -495,9 +509,8 @@ __device__ __forceinline__ int curve_mode(const FastTables* tb, uint32_t mapping
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
-	extern __shared__ __align__(128) unsigned char smem[];
+	unsigned char* const smem = g_smem;
 	const FastTables* tb = reinterpret_cast<const FastTables*>(smem + kOffTabs);
-	const float* s_invdb = reinterpret_cast<const float*>(smem + kOffInvDb);
 	const float* s_slope0 = reinterpret_cast<const float*>(smem + kOffSlope0);
 	const float* s_slope1 = reinterpret_cast<const float*>(smem + kOffSlope1);
 	const float2* s_tw1 = reinterpret_cast<const float2*>(smem + kOffTw1);      // 2048: pass L=512 (256 float2) | pass L=64 (32)
@@ -592,21 +605,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				const int fmode = curve_mode(tb, mapping, w.meta >> 16, ch);
 				if(fmode == 0) build_records(F, fs + first * kFsStride, curves, 32u, 32u, s_recip, lane);
 				const float* base = b.spectra + w.spec_off;
-				const float* s0 = base + (size_t) cp->ch[0] * 1024, *s1 = base + (size_t) cp->ch[1] * 1024;
-				const float* s2 = base + (size_t) cp->ch[2] * 1024, *s3 = base + (size_t) cp->ch[3] * 1024;
+				const int o0 = (int) cp->ch[0] * 1024, o1 = (int) cp->ch[1] * 1024, o2 = (int) cp->ch[2] * 1024, o3 = (int) cp->ch[3] * 1024;
+				const uint32_t Ts = smem_u32(T), cvs = smem_u32(curves), cps = smem_u32(cp);
+				const uint32_t rot1s = smem_u32(s_rot1), tw1s = smem_u32(s_tw1);
 				switch(cp->nl) {
-					case 1:  spectral_stage<1>(s0, s0, s0, s0, fmode, curves, 32u, s_invdb, s_rot1, 512, T, lane, cp); break;
-					case 2:  spectral_stage<2>(s0, s1, s0, s0, fmode, curves, 32u, s_invdb, s_rot1, 512, T, lane, cp); break;
-					case 3:  spectral_stage<3>(s0, s1, s2, s0, fmode, curves, 32u, s_invdb, s_rot1, 512, T, lane, cp); break;
-					default: spectral_stage<4>(s0, s1, s2, s3, fmode, curves, 32u, s_invdb, s_rot1, 512, T, lane, cp); break;
+					case 1:  spectral_stage<1>(base, o0, o0, o0, o0, fmode, cvs, 32u, rot1s, 512, Ts, lane, cps); break;
+					case 2:  spectral_stage<2>(base, o0, o1, o0, o0, fmode, cvs, 32u, rot1s, 512, Ts, lane, cps); break;
+					case 3:  spectral_stage<3>(base, o0, o1, o2, o0, fmode, cvs, 32u, rot1s, 512, Ts, lane, cps); break;
+					default: spectral_stage<4>(base, o0, o1, o2, o3, fmode, cvs, 32u, rot1s, 512, Ts, lane, cps); break;
 				}
 				__syncwarp();
 				{
-					const int l2 = 63 - lane;
-					r8_pass(T + lane, T + l2, 64, s_tw1 + lane * 4, s_tw1 + l2 * 4, T + lane, T + l2, 72);
-					const int j0 = lane & 7, k0 = lane >> 3;
-					r8_pass(T + k0 * 72 + j0, T + (k0 + 4) * 72 + j0, 8, s_tw1 + 256 + j0 * 4, s_tw1 + 256 + j0 * 4, T + j0 * 66 + k0, T + j0 * 66 + k0 + 4, 8);
-					last_pass(T + lane, T + l2, 66, s_rot1 + lane, s_rot1 + l2, 64, T + lane, T + l2);
+					const uint32_t l2 = 63u - (uint32_t) lane, l1 = (uint32_t) lane;
+					r8_pass(Ts + l1 * 8, Ts + l2 * 8, 64, tw1s + l1 * 32, tw1s + l2 * 32, Ts + l1 * 8, Ts + l2 * 8, 72);
+					const uint32_t j0 = l1 & 7u, k0 = l1 >> 3;
+					r8_pass(Ts + (k0 * 72 + j0) * 8, Ts + ((k0 + 4) * 72 + j0) * 8, 8, tw1s + (256 + j0 * 4) * 8, tw1s + (256 + j0 * 4) * 8,
+					        Ts + (j0 * 66 + k0) * 8, Ts + (j0 * 66 + k0 + 4) * 8, 8);
+					last_pass(Ts + l1 * 8, Ts + l2 * 8, 66, rot1s + l1 * 8, rot1s + l2 * 8, 64, Ts + l1 * 8, Ts + l2 * 8);
 				}
 			} else {
 				// ================= up to 8 short packets: four lanes per 64-point FFT =================
@@ -623,21 +638,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				float2* Tf = T + f * 72;
 				if(active) {
 					const float* base = b.spectra + wp[first + f].spec_off;
-					const unsigned char* cv = curves + (size_t) f * cstride;
-					const float* s0 = base + (size_t) cp->ch[0] * 128, *s1 = base + (size_t) cp->ch[1] * 128;
-					const float* s2 = base + (size_t) cp->ch[2] * 128, *s3 = base + (size_t) cp->ch[3] * 128;
+					const uint32_t cvs = smem_u32(curves + (size_t) f * cstride), cps = smem_u32(cp), rot0s = smem_u32(s_rot0);
+					const int o0 = (int) cp->ch[0] * 128, o1 = (int) cp->ch[1] * 128, o2 = (int) cp->ch[2] * 128, o3 = (int) cp->ch[3] * 128;
 					switch(cp->nl) {
-						case 1:  spectral_stage<1>(s0, s0, s0, s0, fmode, cv, rcap, s_invdb, s_rot0, 64, Tf, u, cp); break;
-						case 2:  spectral_stage<2>(s0, s1, s0, s0, fmode, cv, rcap, s_invdb, s_rot0, 64, Tf, u, cp); break;
-						case 3:  spectral_stage<3>(s0, s1, s2, s0, fmode, cv, rcap, s_invdb, s_rot0, 64, Tf, u, cp); break;
-						default: spectral_stage<4>(s0, s1, s2, s3, fmode, cv, rcap, s_invdb, s_rot0, 64, Tf, u, cp); break;
+						case 1:  spectral_stage<1>(base, o0, o0, o0, o0, fmode, cvs, rcap, rot0s, 64, smem_u32(Tf), u, cps); break;
+						case 2:  spectral_stage<2>(base, o0, o1, o0, o0, fmode, cvs, rcap, rot0s, 64, smem_u32(Tf), u, cps); break;
+						case 3:  spectral_stage<3>(base, o0, o1, o2, o0, fmode, cvs, rcap, rot0s, 64, smem_u32(Tf), u, cps); break;
+						default: spectral_stage<4>(base, o0, o1, o2, o3, fmode, cvs, rcap, rot0s, 64, smem_u32(Tf), u, cps); break;
 					}
 				}
 				__syncwarp();
 				{
-					const int u2 = 7 - u;
-					r8_pass(Tf + u, Tf + u2, 8, s_tw0 + u * 4, s_tw0 + u2 * 4, Tf + u, Tf + u2, 9);
-					last_pass(Tf + u * 9, Tf + u2 * 9, 1, s_rot0 + u, s_rot0 + u2, 8, T + f * 64 + u, T + f * 64 + u2);
+					const uint32_t uu = (uint32_t) u, u2 = 7u - uu, Tfs = smem_u32(Tf), tw0s = smem_u32(s_tw0), rot0s = smem_u32(s_rot0);
+					r8_pass(Tfs + uu * 8, Tfs + u2 * 8, 8, tw0s + uu * 32, tw0s + u2 * 32, Tfs + uu * 8, Tfs + u2 * 8, 9);
+					last_pass(Tfs + uu * 72, Tfs + u2 * 72, 1, rot0s + uu * 8, rot0s + u2 * 8, 8, smem_u32(T) + ((uint32_t) f * 64 + uu) * 8, smem_u32(T) + ((uint32_t) f * 64 + u2) * 8);
 				}
 			}
 
