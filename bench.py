@@ -247,6 +247,7 @@ def main():
     # ---- device-resident leg ----
     bh = ctx.upload(batch)
     ctx.sync(bh)
+    kernel_name = ctx.kernel_name(bh)
     for _ in range(args.warmup):
         ctx.run(bh)
     ctx.sync(bh)
@@ -329,7 +330,7 @@ def main():
                        "l2_policy": "inputs+outputs per step (%.2f GB) far exceed the 126 MB L2; no flush needed" %
                                     (samples_per_step * BYTES_PER_SAMPLE / 1e9),
                        "parallelism": "independent streams sharded across ranks, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "k_fused_synth", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": samples_per_step * BYTES_PER_SAMPLE,
                          "kernel_ms": kernel_ms},

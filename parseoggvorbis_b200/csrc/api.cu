@@ -683,6 +683,12 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
 	return POV_OK;
 }
 
+extern "C" const char* pov_batch_kernel_name(const pov_ctx* ctx, const pov_batch_handle* h) {
+	if(!ctx || !h) return "none";
+	if(h->warp_ok) return "k_warp_synth";
+	return h->fused_ok ? "k_fused_synth" : "staged";
+}
+
 extern "C" int pov_batch_sync(pov_ctx* ctx, pov_batch_handle* h) {
 	if(!ctx || !h) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);

@@ -21,7 +21,7 @@ _LIB: Optional[C.CDLL] = None
 SYMBOLS = [
     "pov_abi_version", "pov_inverse_db_table", "pov_ctx_create", "pov_ctx_destroy", "pov_last_error", "pov_ctx_stream",
     "pov_ctx_launch_count", "pov_setup_register", "pov_setup_entry_bits", "pov_setup_get_window",
-    "pov_batch_upload", "pov_batch_run", "pov_batch_run_staged", "pov_batch_fetch_pcm", "pov_batch_pcm_dev",
+    "pov_batch_upload", "pov_batch_run", "pov_batch_kernel_name", "pov_batch_run_staged", "pov_batch_fetch_pcm", "pov_batch_pcm_dev",
     "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_mdct_backward_batch",
     "pov_ogg_vorbis_decode_memory", "pov_decoded_free", "pov_decode_corpus", "pov_ogg_vorbis_full_read_from_memory",
     "pov_ogg_parse_memory", "pov_parsed_stream_count", "pov_parsed_get", "pov_parsed_free",
@@ -64,6 +64,8 @@ def load() -> C.CDLL:
     L.pov_batch_upload.argtypes = [vp, C.POINTER(abi.pov_batch), C.POINTER(vp)]
     L.pov_batch_run.argtypes = [vp, vp]
     L.pov_batch_run_staged.argtypes = [vp, vp]
+    L.pov_batch_kernel_name.argtypes = [vp, vp]
+    L.pov_batch_kernel_name.restype = C.c_char_p
     L.pov_batch_fetch_pcm.argtypes = [vp, vp, C.POINTER(C.c_float), u64, i32]
     L.pov_batch_pcm_dev.argtypes = [vp]
     L.pov_batch_pcm_dev.restype = vp
@@ -200,6 +202,10 @@ class SynthContext:
 
     def run(self, bh: BatchHandle):
         self._check(self.L.pov_batch_run(self.ctx, bh.h))
+
+    def kernel_name(self, bh: BatchHandle) -> str:
+        """Kernel that run() launches for this batch (k_warp_synth / k_fused_synth / staged)."""
+        return self.L.pov_batch_kernel_name(self.ctx, bh.h).decode()
 
     def run_staged(self, bh: BatchHandle):
         self._check(self.L.pov_batch_run_staged(self.ctx, bh.h))
