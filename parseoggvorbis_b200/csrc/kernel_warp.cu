@@ -54,7 +54,7 @@ struct Params {
 // ---- shared memory map (bytes) -----------------------------------------------------------------------------------
 constexpr int kOffTabs   = 0;
 constexpr int kOffInvDb  = kOffTabs + (int) sizeof(FastTables);
-constexpr int kOffSlope0 = kOffInvDb + 1024;
+constexpr int kOffSlope0 = kOffInvDb + 1024 + 16;                   // invdb[256] = 0.0f (curve of a channel multiplied by zero)
 constexpr int kOffSlope1 = kOffSlope0 + 128 * 4;
 constexpr int kOffTw1    = kOffSlope1 + 1024 * 4;
 constexpr int kOffTw0    = kOffTw1 + 288 * 8;
@@ -263,6 +263,16 @@ __device__ __noinline__ void build_records(const FastFloor* __restrict__ F, cons
 	__syncwarp();
 }
 
+// Curve block of a channel without a decoded floor: one flat segment at table index y (255 -> 1.0f: the reference
+// skips the multiplication, hpp:1247; 256 -> 0.0f: multiplied by its zero-initialised floor buffer, hpp:1159).
+__device__ __forceinline__ void flat_curve(unsigned char* __restrict__ curve, uint32_t rec_cap, uint32_t nwords, uint32_t y, int lane) {
+	uint2* rec = reinterpret_cast<uint2*>(curve);
+	uint2* tab = rec + rec_cap;
+	if(lane == 0) rec[0] = make_uint2(0u | (2047u << 11) | (y << 22), 0u);
+	if((uint32_t) lane < nwords) tab[lane] = make_uint2(lane == 0 ? 1u : 0u, lane == 0 ? 0xFFFFFFFFu : 0u);
+	__syncwarp();
+}
+
 // Two consecutive bins x, x+1 (x even) of a curve as inverse-dB table values (hpp:586-589).
 __device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, const uint2* __restrict__ tab, uint32_t x,
                                              const float* __restrict__ invdb) {
@@ -275,7 +285,7 @@ __device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, cons
 		const uint32_t q = __umulhi(k << 12, r.y & 0x7fffffffu);
 		const uint32_t y0 = r.x >> 22;
 		const uint32_t y = ((int) r.y < 0) ? y0 - q : y0 + q;
-		out.x = invdb[y & 255u];
+		out.x = invdb[y];
 	}
 	if(x + 1 >= ((r.x >> 11) & 0x7ffu)) r = rec[s + 1];
 	{
@@ -283,7 +293,7 @@ __device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, cons
 		const uint32_t q = __umulhi(k << 12, r.y & 0x7fffffffu);
 		const uint32_t y0 = r.x >> 22;
 		const uint32_t y = ((int) r.y < 0) ? y0 - q : y0 + q;
-		out.y = invdb[y & 255u];
+		out.y = invdb[y];
 	}
 	return out;
 }
@@ -361,8 +371,8 @@ __device__ __noinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, ui
 // (M-2-2j, M-1-2j) arrive with two 64-bit loads per channel and feed both points.
 // src*: spectra ([n/2] floats) of the local channels of this lane's packet (src0 = this warp's channel);
 // fmode: 0 evaluate the curve, 1 multiply by 1 (hpp:1247 skipped), 2 multiply by 0.
-template <int NL>
-__device__ __noinline__ void spectral_stage(const float* __restrict__ base, int o0, int o1, int o2, int o3, int fmode, uint32_t curve_, uint32_t rec_cap,
+template <int NL, bool GEN>
+__device__ __noinline__ void spectral_stage(const float* __restrict__ base, int o0, int o1, int o2, int o3, uint32_t curve_, uint32_t rec_cap,
                                             uint32_t rot_, int Q, uint32_t Tf_, int u, uint32_t cp_) {
 	const int J = Q >> 3, M = 2 * Q;
 	const uint2* rec = sptr<const uint2>(curve_);
@@ -394,21 +404,16 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ base, int 
 				nvb[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + M - 2 - 2 * (jp + J))));
 			}
 		}
-		if(NL == 2) {
-			for(int st = 0; st + 1 < nsteps; ++st) {
-				if(cp->sm[st] == 0) { uncouple2(va[0], va[NL - 1]); uncouple2(vb[0], vb[NL - 1]); }
-				else                { uncouple2(va[NL - 1], va[0]); uncouple2(vb[NL - 1], vb[0]); }
+		if(NL > 1 && !GEN) {
+			// single coupling step between two channels: only this warp's channel (local index 0) is needed
+			if(last_mag) {
+				va[0].x = uncouple_mag(va[0].x, va[NL - 1].x); va[0].y = uncouple_mag(va[0].y, va[NL - 1].y);
+				vb[0].x = uncouple_mag(vb[0].x, vb[NL - 1].x); vb[0].y = uncouple_mag(vb[0].y, vb[NL - 1].y);
+			} else {
+				va[0].x = uncouple_ang(va[NL - 1].x, va[0].x); va[0].y = uncouple_ang(va[NL - 1].y, va[0].y);
+				vb[0].x = uncouple_ang(vb[NL - 1].x, vb[0].x); vb[0].y = uncouple_ang(vb[NL - 1].y, vb[0].y);
 			}
-			if(nsteps > 0) {      // last step: only this warp's channel (local index 0) is needed
-				if(last_mag) {
-					va[0].x = uncouple_mag(va[0].x, va[NL - 1].x); va[0].y = uncouple_mag(va[0].y, va[NL - 1].y);
-					vb[0].x = uncouple_mag(vb[0].x, vb[NL - 1].x); vb[0].y = uncouple_mag(vb[0].y, vb[NL - 1].y);
-				} else {
-					va[0].x = uncouple_ang(va[NL - 1].x, va[0].x); va[0].y = uncouple_ang(va[NL - 1].y, va[0].y);
-					vb[0].x = uncouple_ang(vb[NL - 1].x, vb[0].x); vb[0].y = uncouple_ang(vb[NL - 1].y, vb[0].y);
-				}
-			}
-		} else if(NL > 2) {
+		} else if(NL > 1) {
 			for(int st = 0; st < nsteps; ++st) {
 				const int mi = cp->sm[st], ai = cp->sa[st];
 				float2 ma = va[0], mb = vb[0], aa = va[0], ab = vb[0];
@@ -425,14 +430,8 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ base, int 
 				}
 			}
 		}
-		float2 fa, fb;
-		if(fmode == 0) {
-			fa = curve_pair(rec, tab, (uint32_t) (2 * jp), invdb);
-			fb = curve_pair(rec, tab, (uint32_t) (M - 2 - 2 * jp), invdb);
-		} else {
-			const float fill = (fmode == 1) ? 1.f : 0.f;
-			fa = make_float2(fill, fill); fb = fa;
-		}
+		const float2 fa = curve_pair(rec, tab, (uint32_t) (2 * jp), invdb);
+		const float2 fb = curve_pair(rec, tab, (uint32_t) (M - 2 - 2 * jp), invdb);
 		// hpp:1252 residue *= floor (one rounding each)
 		const float a0 = __fmul_rn(va[0].x, fa.x), a1 = __fmul_rn(va[0].y, fa.y);
 		const float b0 = __fmul_rn(vb[0].x, fb.x), b1 = __fmul_rn(vb[0].y, fb.y);
@@ -440,6 +439,19 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ base, int 
 		Tf[jp] = cmul(make_float2(a0, b1), rot[jp]);
 		Tf[Q - 1 - jp] = cmul(make_float2(b0, a1), rot[Q - 1 - jp]);
 	}
+}
+
+// picks the instantiation: <1> no coupling, <2,false> the stereo case (one step), generic otherwise
+__device__ __forceinline__ void spectral_dispatch(const FastCouple* cp, const float* base, int half, uint32_t curve_, uint32_t rec_cap,
+                                                  uint32_t rot_, int Q, uint32_t Tf_, int u) {
+	const int o0 = (int) cp->ch[0] * half, o1 = (int) cp->ch[1] * half, o2 = (int) cp->ch[2] * half, o3 = (int) cp->ch[3] * half;
+	const uint32_t cps = smem_u32(cp);
+	const int nl = cp->nl;
+	if(nl == 1) spectral_stage<1, false>(base, o0, o0, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	else if(nl == 2 && cp->nsteps == 1) spectral_stage<2, false>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	else if(nl == 2) spectral_stage<2, true>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	else if(nl == 3) spectral_stage<3, true>(base, o0, o1, o2, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	else spectral_stage<4, true>(base, o0, o1, o2, o3, curve_, rec_cap, rot_, Q, Tf_, u, cps);
 }
 
 // ---- overlap-add ---------------------------------------------------------------------------------------------------
@@ -538,6 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 		tma_bulk_g2s(smem + kOffRot1, P.rot[1], 512u * 8u, s_bar);
 		tma_bulk_g2s(smem + kOffRot0, P.rot[0], 64u * 8u, s_bar);
 	}
+	if(threadIdx.x < 4) reinterpret_cast<float*>(smem + kOffInvDb + 1024)[threadIdx.x] = 0.f;
 	for(uint32_t d = threadIdx.x; d <= POV_FAST_MAX_X; d += kThreads)
 		s_recip[d] = (d < 2) ? 0xFFFFFFFFu : (uint32_t) ((0x100000000ull + d - 1) / d);
 	__syncthreads();
@@ -599,60 +612,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				if((uint32_t) lane * 32u < nhalf)
 					for(int i = 0; i < (int) ncp->nl; ++i) prefetch_l2(b.spectra + nw.spec_off + (size_t) ncp->ch[i] * nhalf + (size_t) lane * 32u);
 			}
-			if(flag) {
-				// ================= one long packet: the whole warp is one 512-point FFT =================
-				const WPkt& w = wp[first];
-				const int fmode = curve_mode(tb, mapping, w.meta >> 16, ch);
-				if(fmode == 0) build_records(F, fs + first * kFsStride, curves, 32u, 32u, s_recip, lane);
-				const float* base = b.spectra + w.spec_off;
-				const int o0 = (int) cp->ch[0] * 1024, o1 = (int) cp->ch[1] * 1024, o2 = (int) cp->ch[2] * 1024, o3 = (int) cp->ch[3] * 1024;
-				const uint32_t Ts = smem_u32(T), cvs = smem_u32(curves), cps = smem_u32(cp);
-				const uint32_t rot1s = smem_u32(s_rot1), tw1s = smem_u32(s_tw1);
-				switch(cp->nl) {
-					case 1:  spectral_stage<1>(base, o0, o0, o0, o0, fmode, cvs, 32u, rot1s, 512, Ts, lane, cps); break;
-					case 2:  spectral_stage<2>(base, o0, o1, o0, o0, fmode, cvs, 32u, rot1s, 512, Ts, lane, cps); break;
-					case 3:  spectral_stage<3>(base, o0, o1, o2, o0, fmode, cvs, 32u, rot1s, 512, Ts, lane, cps); break;
-					default: spectral_stage<4>(base, o0, o1, o2, o3, fmode, cvs, 32u, rot1s, 512, Ts, lane, cps); break;
-				}
-				__syncwarp();
-				{
-					const uint32_t l2 = 63u - (uint32_t) lane, l1 = (uint32_t) lane;
-					r8_pass(Ts + l1 * 8, Ts + l2 * 8, 64, tw1s + l1 * 32, tw1s + l2 * 32, Ts + l1 * 8, Ts + l2 * 8, 72);
-					const uint32_t j0 = l1 & 7u, k0 = l1 >> 3;
-					r8_pass(Ts + (k0 * 72 + j0) * 8, Ts + ((k0 + 4) * 72 + j0) * 8, 8, tw1s + (256 + j0 * 4) * 8, tw1s + (256 + j0 * 4) * 8,
+			// ================= one long packet (the whole warp is one 512-point FFT) or up to 8 short packets (four lanes
+			//                   per 64-point FFT): same code, geometry in registers =================
+			const int Qs = flag ? 512 : 64, Js = Qs >> 3;
+			const int lshift = flag ? 5 : 2;                      // log2(lanes per FFT) = log2(Q / 16)
+			const int f = lane >> lshift, u = lane & ((1 << lshift) - 1);
+			const uint32_t cstride = flag ? 0u : P.short_curve_stride, rcap = flag ? 32u : tb->short_posts_cap, nwords = flag ? 32u : 4u;
+			for(int g = 0; g < count; ++g) {
+				const int md = curve_mode(tb, mapping, wp[first + g].meta >> 16, ch);
+				unsigned char* cv = curves + (size_t) g * cstride;
+				if(md == 0) build_records(F, fs + (first + g) * kFsStride, cv, rcap, nwords, s_recip, lane);
+				else flat_curve(cv, rcap, nwords, md == 1 ? 255u : 256u, lane);
+			}
+			const uint32_t Ts = smem_u32(T), Tfs = Ts + (uint32_t) f * (72u * 8u);
+			const uint32_t rots = smem_u32(flag ? s_rot1 : s_rot0), tws = smem_u32(flag ? s_tw1 : s_tw0);
+			if(f < count)
+				spectral_dispatch(cp, b.spectra + wp[first + f].spec_off, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u);
+			__syncwarp();
+			{
+				const uint32_t uu = (uint32_t) u, u2 = (uint32_t) Js - 1u - uu;
+				// pass 1: natural order -> A1 (stride 72 for Q = 512, 9 for Q = 64)
+				r8_pass(Tfs + uu * 8, Tfs + u2 * 8, Js, tws + uu * 32, tws + u2 * 32, Tfs + uu * 8, Tfs + u2 * 8, flag ? 72 : 9);
+				if(flag) {
+					const uint32_t j0 = uu & 7u, k0 = uu >> 3;    // pass 2 of the 512-point FFT: A1 -> A2
+					r8_pass(Ts + (k0 * 72 + j0) * 8, Ts + ((k0 + 4) * 72 + j0) * 8, 8, tws + (256 + j0 * 4) * 8, tws + (256 + j0 * 4) * 8,
 					        Ts + (j0 * 66 + k0) * 8, Ts + (j0 * 66 + k0 + 4) * 8, 8);
-					last_pass(Ts + l1 * 8, Ts + l2 * 8, 66, rot1s + l1 * 8, rot1s + l2 * 8, 64, Ts + l1 * 8, Ts + l2 * 8);
 				}
-			} else {
-				// ================= up to 8 short packets: four lanes per 64-point FFT =================
-				const int f = lane >> 2, u = lane & 3;
-				const bool active = f < count;
-				const uint32_t cstride = P.short_curve_stride, rcap = tb->short_posts_cap;
-				int fmode = 1;
-				for(int g = 0; g < count; ++g) {
-					const WPkt& w = wp[first + g];
-					const int md = curve_mode(tb, mapping, w.meta >> 16, ch);
-					if(md == 0) build_records(F, fs + (first + g) * kFsStride, curves + (size_t) g * cstride, rcap, 4u, s_recip, lane);
-					if(g == f) fmode = md;
-				}
-				float2* Tf = T + f * 72;
-				if(active) {
-					const float* base = b.spectra + wp[first + f].spec_off;
-					const uint32_t cvs = smem_u32(curves + (size_t) f * cstride), cps = smem_u32(cp), rot0s = smem_u32(s_rot0);
-					const int o0 = (int) cp->ch[0] * 128, o1 = (int) cp->ch[1] * 128, o2 = (int) cp->ch[2] * 128, o3 = (int) cp->ch[3] * 128;
-					switch(cp->nl) {
-						case 1:  spectral_stage<1>(base, o0, o0, o0, o0, fmode, cvs, rcap, rot0s, 64, smem_u32(Tf), u, cps); break;
-						case 2:  spectral_stage<2>(base, o0, o1, o0, o0, fmode, cvs, rcap, rot0s, 64, smem_u32(Tf), u, cps); break;
-						case 3:  spectral_stage<3>(base, o0, o1, o2, o0, fmode, cvs, rcap, rot0s, 64, smem_u32(Tf), u, cps); break;
-						default: spectral_stage<4>(base, o0, o1, o2, o3, fmode, cvs, rcap, rot0s, 64, smem_u32(Tf), u, cps); break;
-					}
-				}
-				__syncwarp();
-				{
-					const uint32_t uu = (uint32_t) u, u2 = 7u - uu, Tfs = smem_u32(Tf), tw0s = smem_u32(s_tw0), rot0s = smem_u32(s_rot0);
-					r8_pass(Tfs + uu * 8, Tfs + u2 * 8, 8, tw0s + uu * 32, tw0s + u2 * 32, Tfs + uu * 8, Tfs + u2 * 8, 9);
-					last_pass(Tfs + uu * 72, Tfs + u2 * 72, 1, rot0s + uu * 8, rot0s + u2 * 8, 8, smem_u32(T) + ((uint32_t) f * 64 + uu) * 8, smem_u32(T) + ((uint32_t) f * 64 + u2) * 8);
-				}
+				// last pass + post-rotation -> D (float2[Q] per FFT, packed back to back)
+				const uint32_t ia = flag ? uu * 8u : uu * 72u, ib = flag ? u2 * 8u : u2 * 72u;
+				const uint32_t od = Ts + (uint32_t) f * (64u * 8u);
+				last_pass(Tfs + ia, Tfs + ib, flag ? 66 : 1, rots + uu * 8, rots + u2 * 8, Js, od + uu * 8, od + u2 * 8);
 			}
 
 			// ================= window + overlap-add + emit (hpp:1008-1059 in gather form) =================

@@ -14,7 +14,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpov_synth.so")
+LIB_PATH = os.environ.get("POV_LIB_PATH") or os.path.join(_HERE, "libpov_synth.so")   # override: A/B builds while tuning
 _LIB: Optional[C.CDLL] = None
 
 # every symbol include/pov_synth.h declares (tests/test_abi.py checks the header against this list and the .so)
