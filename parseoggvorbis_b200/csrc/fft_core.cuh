@@ -315,8 +315,9 @@ __device__ __forceinline__ void pass_radix8_s(float2* __restrict__ T, int t, con
 #pragma unroll
 	for(int m = 0; m < 8; ++m) a[m] = p[m * ps];
 	constexpr int kOff = Tw8Tables<Q>::offset(L);
-	const float4* tw = reinterpret_cast<const float4*>(tw8 + kOff + j * 4);
-	const float4 w12 = tw[0], w34 = tw[1];
+	// table of a pass: [s x (W^j, W^2j)] then [s x (W^3j, W^4j)] (host: make_fft_r8_tables)
+	const float4 w12 = *reinterpret_cast<const float4*>(tw8 + kOff + j * 2);
+	const float4 w34 = *reinterpret_cast<const float4*>(tw8 + kOff + 2 * s + j * 2);
 	dft8(a);
 	const float2 w1 = make_float2(w12.x, w12.y), w2 = make_float2(w12.z, w12.w);
 	const float2 w3 = make_float2(w34.x, w34.y), w4 = make_float2(w34.z, w34.w);

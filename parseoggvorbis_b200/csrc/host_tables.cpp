@@ -96,20 +96,23 @@ void make_fft_pass_tables(uint32_t n, std::vector<float>& out) {
 }
 
 // Layout must match Tw8Tables<Q> in fft_core.cuh: radix-8 passes in execution order (L = L1, L1/8, ... >= 64), per
-// butterfly j the four factors W_L^(j*1..4).
+// pass the factors W_L^(j*1..4) of butterfly j, split in two halves (see below).
 void make_fft_r8_tables(uint32_t n, std::vector<float>& out) {
 	const uint32_t Q = n / 4;
 	uint32_t log2q = 0;
 	while((1u << log2q) < Q) ++log2q;
 	const uint32_t r0 = (log2q % 3 == 0) ? 8 : (log2q % 3 == 1) ? 2 : 4;
 	out.clear();
+	// per pass: [L/8 x (W^j, W^2j)] then [L/8 x (W^3j, W^4j)] — a warp whose lanes take consecutive butterflies reads each
+	// half with consecutive 16-byte loads (no shared-memory bank conflicts)
 	for(uint32_t L = (r0 == 8) ? Q : Q / r0; L >= 64; L /= 8)
-		for(uint32_t j = 0; j < L / 8; ++j)
-			for(uint32_t k = 1; k <= 4; ++k) {
-				const double a = -2.0 * M_PI * (double) (j * k) / (double) L;
-				out.push_back((float) cos(a));
-				out.push_back((float) sin(a));
-			}
+		for(uint32_t half = 0; half < 2; ++half)
+			for(uint32_t j = 0; j < L / 8; ++j)
+				for(uint32_t k = 1 + 2 * half; k <= 2 + 2 * half; ++k) {
+					const double a = -2.0 * M_PI * (double) (j * k) / (double) L;
+					out.push_back((float) cos(a));
+					out.push_back((float) sin(a));
+				}
 	if(out.empty()) { out.assign(8, 0.f); }
 }
 

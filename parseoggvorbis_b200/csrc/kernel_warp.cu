@@ -310,8 +310,8 @@ __device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, cons
 // Every access of a pass is either contiguous over the lanes or hits 16 distinct 8-byte bank pairs per half warp.
 // The passes are size-generic and NOT inlined: all block sizes share ~500 instructions of FFT code, which keeps the hot
 // loop of 16 independently running warps inside the instruction cache.
-__device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ tw) {   // tw: W^j, W^2j, W^3j, W^4j
-	const float4 w12 = *reinterpret_cast<const float4*>(tw), w34 = *reinterpret_cast<const float4*>(tw + 2);
+__device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ tw, int half) {   // tw: (W^j, W^2j); tw + half: (W^3j, W^4j)
+	const float4 w12 = *reinterpret_cast<const float4*>(tw), w34 = *reinterpret_cast<const float4*>(tw + half);
 	const float2 w1 = make_float2(w12.x, w12.y), w2 = make_float2(w12.z, w12.w);
 	const float2 w3 = make_float2(w34.x, w34.y), w4 = make_float2(w34.z, w34.w);
 	a[1] = cmul(a[1], w1);
@@ -324,8 +324,9 @@ __device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ t
 }
 
 // Radix-8 DIF pass of two butterflies per lane: inputs in*[m*sin], outputs out*[k*sout] (twiddled by tw*).
-// All addresses are shared-window byte addresses, strides are in float2 units.
-__device__ __noinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t twA_, uint32_t twB_, uint32_t outA_, uint32_t outB_, int sout) {
+// All addresses are shared-window byte addresses, strides are in float2 units. Twiddles of butterfly j: (W^j, W^2j) at
+// tw, (W^3j, W^4j) at tw + twhalf (the table keeps the two halves apart so that lanes read consecutive 16-byte words).
+__device__ __noinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t twA_, uint32_t twB_, int twhalf, uint32_t outA_, uint32_t outB_, int sout) {
 	const float2* inA = sptr<const float2>(inA_); const float2* inB = sptr<const float2>(inB_);
 	float2* outA = sptr<float2>(outA_); float2* outB = sptr<float2>(outB_);
 	float2 a[8], b[8];
@@ -333,9 +334,9 @@ __device__ __noinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint
 	for(int m = 0; m < 8; ++m) { a[m] = inA[m * sin]; b[m] = inB[m * sin]; }
 	__syncwarp();
 	dft8(a);
-	twiddle8(a, sptr<const float2>(twA_));
+	twiddle8(a, sptr<const float2>(twA_), twhalf);
 	dft8(b);
-	twiddle8(b, sptr<const float2>(twB_));
+	twiddle8(b, sptr<const float2>(twB_), twhalf);
 #pragma unroll
 	for(int k = 0; k < 8; ++k) { outA[k * sout] = a[k]; outB[k * sout] = b[k]; }
 	__syncwarp();
@@ -632,10 +633,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			{
 				const uint32_t uu = (uint32_t) u, u2 = (uint32_t) Js - 1u - uu;
 				// pass 1: natural order -> A1 (stride 72 for Q = 512, 9 for Q = 64)
-				r8_pass(Tfs + uu * 8, Tfs + u2 * 8, Js, tws + uu * 32, tws + u2 * 32, Tfs + uu * 8, Tfs + u2 * 8, flag ? 72 : 9);
+				r8_pass(Tfs + uu * 8, Tfs + u2 * 8, Js, tws + uu * 16, tws + u2 * 16, 2 * Js, Tfs + uu * 8, Tfs + u2 * 8, flag ? 72 : 9);
 				if(flag) {
 					const uint32_t j0 = uu & 7u, k0 = uu >> 3;    // pass 2 of the 512-point FFT: A1 -> A2
-					r8_pass(Ts + (k0 * 72 + j0) * 8, Ts + ((k0 + 4) * 72 + j0) * 8, 8, tws + (256 + j0 * 4) * 8, tws + (256 + j0 * 4) * 8,
+					r8_pass(Ts + (k0 * 72 + j0) * 8, Ts + ((k0 + 4) * 72 + j0) * 8, 8, tws + (256 + j0 * 2) * 8, tws + (256 + j0 * 2) * 8, 16,
 					        Ts + (j0 * 66 + k0) * 8, Ts + (j0 * 66 + k0 + 4) * 8, 8);
 				}
 				// last pass + post-rotation -> D (float2[Q] per FFT, packed back to back)
