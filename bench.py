@@ -203,7 +203,7 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="independent config-2 streams per GPU per step")
     ap.add_argument("--packets", type=int, default=4096, help="packets per stream")
     ap.add_argument("--distinct", type=int, default=4, help="independently generated streams (rest are replicas)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-streams", type=int, default=0, help="streams of the CPU-baseline sample (0 = one per core)")
     ap.add_argument("--ref-decodes", type=int, default=40, help="reference arm: decodes per thread per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,12 +264,21 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * samples_per_step * args.steps / (ms_max * 1e-3)
+    clocks = None
+    if sampler:
+        # the timed region lasts tens of milliseconds, nvidia-smi samples every 50 ms: keep the same kernel running
+        # back to back (untimed) for about a second so that the clock / throttle record is taken under this load
+        t_end = time.perf_counter() + 1.0
+        while time.perf_counter() < t_end:
+            for _ in range(8):
+                ctx.run(bh)
+            ctx.sync(bh)
+        clocks = sampler.stop()
+        clocks["note"] = "sampled from warm-up through the timed region and 1 s of the same launches repeated untimed"
+    launches_timed = launches
+    from parseoggvorbis_b200 import sharding
+    total_units, ms_max = sharding.aggregate_throughput(samples_per_step * args.steps, ms, dist, device="cuda")
+    value = total_units / (ms_max * 1e-3)          # whole job: units of all ranks / slowest rank's device time
     kernel_ms = ms / args.steps          # this rank's fused-kernel launch duration (one launch per step)
 
     # correctness spot check of what was just timed (first stream vs the oracle) — outside the timed region
@@ -287,34 +296,60 @@ def main():
                  "packets_with_status": status_bad}
 
     # ---- end-to-end leg: host buffers in, host PCM out, every step ----
+    # Every step validates the descriptors, copies all input arenas from pinned host memory to the device, runs the
+    # kernel and copies the whole PCM arena back into pinned host memory. Steps are issued as a 2-deep pipeline on two
+    # contexts (= two CUDA streams), so that the H2D copy of step k+1 overlaps the D2H copy of step k on the two copy
+    # engines — the way a corpus decode streams batches through the device. Timed with the host clock around the whole
+    # pipeline (barrier + synchronize on both sides), which includes every copy and every launch.
     e2e = None
     if not args.no_e2e:
+        depth = 2
         pb, keep = pin_batch(batch)
-        out_t = torch.empty(int(batch.pcm_floats), dtype=torch.float32, pin_memory=True)
-        out_np = out_t.numpy()
+        ctxs = [ctx, SynthContext(local)]
+        pb2 = pb
+        handles, outs = [bh], []
+        sid2 = ctxs[1].register_setup(setup)
+        assert sid2 == int(batch.streams["setup_id"][0])
+        handles.append(ctxs[1].upload(pb2))
+        for _ in range(depth):
+            t_out = torch.empty(int(batch.pcm_floats), dtype=torch.float32, pin_memory=True)
+            keep.append(t_out)
+            outs.append(t_out.numpy())
         h2d = int(pb.streams.nbytes + pb.packets.nbytes + pb.ys.nbytes + pb.payload.nbytes + 8 * len(pb.packets))
-        d2h = int(out_np.nbytes)
-        def e2e_step():
-            ctx.upload(pb, reuse=bh)
-            ctx.run(bh)
-            ctx.fetch_pcm(bh, out=out_np, sync=True)
-        e2e_step()
+        d2h = int(outs[0].nbytes)
+
+        def e2e_issue(k):
+            c, h = ctxs[k % depth], handles[k % depth]
+            c.sync(h)                               # the previous step on this context has delivered its PCM
+            c.upload(pb, reuse=h)
+            c.run(h)
+            c.fetch_pcm(h, out=outs[k % depth], sync=False)
+
+        def e2e_drain():
+            for c, h in zip(ctxs, handles):
+                c.sync(h)
+
+        for k in range(depth):
+            e2e_issue(k)
+        e2e_drain()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        e1.record(stream)
+        for k in range(args.e2e_steps):
+            e2e_issue(k)
+        e2e_drain()
         barrier()
         wall = time.perf_counter() - t0
-        dev_ms = e0.elapsed_time(e1)
-        tt = torch.tensor([max(wall * 1e3, dev_ms)], dtype=torch.float64, device="cuda")
+        e2e_ok = bool(np.array_equal(outs[0][:1 << 20], outs[1][:1 << 20])) if args.e2e_steps >= 2 else True
+        tt = torch.tensor([wall * 1e3], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * samples_per_step * args.e2e_steps / (float(tt.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-               "ms_per_step": float(tt.item()) / args.e2e_steps}
+               "ms_per_step": float(tt.item()) / args.e2e_steps, "pipeline_depth": depth,
+               "timing": "host clock around the pipelined steps (upload+run+fetch each), max over ranks",
+               "outputs_identical_across_contexts": e2e_ok}
+        handles[1].free()
+        ctxs[1].close()
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -334,7 +369,7 @@ def main():
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": samples_per_step * BYTES_PER_SAMPLE,
                          "kernel_ms": kernel_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "check": check,
+            "gpu_launches": int(launches_timed), "clocks": clocks, "check": check,
         }
         if e2e:
             line["e2e"] = e2e
