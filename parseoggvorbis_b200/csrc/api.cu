@@ -553,6 +553,18 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 		}
 	}
 	if(expect_first != P) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: %u packets not covered by the stream table", (uint32_t) (P - expect_first));
+	if(h->warp_ok) {
+		// the warp kernel keeps per-packet offsets relative to the run's first packet in 32 bits
+		for(const DevRun& r : h->runs) {
+			const uint64_t s0 = h->spec_off[r.first_packet], p0 = b->packets[r.first_packet].pcm_off;
+			for(uint32_t k = 0; k < r.n_packets && h->warp_ok; ++k) {
+				const int64_t ds = (int64_t) (h->spec_off[r.first_packet + k] - s0);
+				const uint64_t pk = b->packets[r.first_packet + k].pcm_off;
+				if(ds < INT32_MIN / 2 || ds > INT32_MAX / 2 || pk < p0 || pk - p0 > 0x7fffffffull) h->warp_ok = false;
+			}
+			if(!h->warp_ok) break;
+		}
+	}
 	if(b->input_kind == POV_INPUT_ENTRIES) {
 		// walk the payload headers on the host so that a malformed offset cannot send the kernel out of bounds
 		for(uint32_t p = 0; p < P; ++p) {

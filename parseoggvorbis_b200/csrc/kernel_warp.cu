@@ -32,10 +32,13 @@ namespace wk {
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRegionF2 = 576;          // float2 slots of one FFT work region (long: 8*72, short: 8 FFTs * 72)
+constexpr int kSlotF2 = kRegionF2 / 2;  // the work area of a warp is three half regions A | B | C: even steps transform in
+                                        // A+B and leave their overlap half (D lo) in A, odd steps use B+C and leave it in C;
+                                        // the other half (D hi, consumed by the same step's overlap-add) always lands in B
 constexpr int kPktCap = 32;             // packets per run, halo included
 constexpr uint32_t FULL = 0xffffffffu;
 
-struct __align__(16) WPkt { uint32_t meta, emit; uint64_t ys_off, pcm_off, spec_off; };   // 32 bytes
+struct __align__(16) WPkt { uint32_t meta, emit, pcm_rel; int32_t spec_rel; };   // 16 bytes; offsets relative to the run's first packet
 
 struct Params {
 	DevBatchView b;
@@ -65,7 +68,8 @@ constexpr int kOffBar    = kOffRecip + (POV_FAST_MAX_X + 4) * 4;
 constexpr int kOffWarps  = kOffBar + 16;
 static_assert(kOffWarps % 16 == 0, "warp areas must stay 16-byte aligned");
 constexpr int kFsStride = 36;           // per packet: final Y of every post in ascending-x order (uint8 x 32) + step2 mask (uint32)
-constexpr int kWarpFixedBytes = 2 * kRegionF2 * 8 + kPktCap * (int) sizeof(WPkt) + kPktCap * kFsStride;
+constexpr int kWorkBytes = 3 * kSlotF2 * 8;
+constexpr int kWarpFixedBytes = kWorkBytes + kPktCap * (int) sizeof(WPkt) + kPktCap * kFsStride;
 
 extern __shared__ __align__(128) unsigned char g_smem[];     // the kernel's dynamic shared memory (map above)
 
@@ -130,7 +134,7 @@ __device__ __forceinline__ float uncouple_ang(float m, float a) {
 // independent). The final Y values leave in ascending-x order as bytes, with the step2 flags as a bit mask, 36 bytes per
 // packet; the hpp:536 / hpp:587 checks are evaluated here with full-width values and reported per packet.
 // scratch: [32 posts][32 lanes] uint16, aliasing the (idle) FFT work regions.
-__device__ __noinline__ void unwrap_run(const FastTables* __restrict__ tb, const WPkt* __restrict__ wp, int run_n, int ch,
+__device__ __noinline__ void unwrap_run(const FastTables* __restrict__ tb, const WPkt* __restrict__ wp, const pov_packet* __restrict__ pk0, int run_n, int ch,
                                         const uint16_t* __restrict__ ys, uint16_t* __restrict__ scratch, unsigned char* __restrict__ fs,
                                         uint32_t* __restrict__ status, int lane) {
 	const bool have = lane < run_n;
@@ -143,7 +147,7 @@ __device__ __noinline__ void unwrap_run(const FastTables* __restrict__ tb, const
 	const int maxposts = __reduce_max_sync(FULL, posts);
 	if(maxposts == 0) return;
 	// Y list of this channel inside the packet: after the lists of the used channels before it (hpp:498-518 order)
-	uint64_t yo = have ? wp[lane].ys_off : 0ull;
+	uint64_t yo = have ? pk0[lane].ys_off : 0ull;
 	for(int cc = 0; cc < ch; ++cc)
 		if((used >> cc) & 1u) yo += tb->floors[tb->floor_of_ch[mapping][cc]].n_posts;
 	const uint16_t* yp = ys + yo;
@@ -344,10 +348,12 @@ __device__ __noinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint
 
 // Last pass + post-rotation of butterflies kkA and kkB = J-1-kkA (rotA = rot + kkA, rotB = rot + kkB):
 //   c[k] = X[k] * w[k];  D2[k] = (D[2k], D[2k+1]) = (Re c[k], -Im c[Q-1-k]);  Q-1-(kkA + J k2) = kkB + J (7-k2)
-__device__ __noinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t rotA_, uint32_t rotB_, int J, uint32_t outA_, uint32_t outB_) {
+__device__ __noinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t rotA_, uint32_t rotB_, int J,
+                                       uint32_t loA_, uint32_t loB_, uint32_t hiA_, uint32_t hiB_) {
 	const float2* inA = sptr<const float2>(inA_); const float2* inB = sptr<const float2>(inB_);
 	const float2* rotA = sptr<const float2>(rotA_); const float2* rotB = sptr<const float2>(rotB_);
-	float2* outA = sptr<float2>(outA_); float2* outB = sptr<float2>(outB_);
+	float2* loA = sptr<float2>(loA_); float2* loB = sptr<float2>(loB_);      // D2[kk + J k2], k2 < 4  (D lo half: next packet's overlap)
+	float2* hiA = sptr<float2>(hiA_); float2* hiB = sptr<float2>(hiB_);      // D2[kk + J k2], k2 >= 4 (D hi half), indexed by k2 - 4
 	float2 a[8], b[8];
 #pragma unroll
 	for(int m = 0; m < 8; ++m) { a[m] = inA[m * sin]; b[m] = inB[m * sin]; }
@@ -360,9 +366,11 @@ __device__ __noinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, ui
 		b[k] = cmul(b[k], rotB[J * k]);
 	}
 #pragma unroll
-	for(int k = 0; k < 8; ++k) {
-		outA[J * k] = make_float2(a[k].x, -b[7 - k].y);
-		outB[J * k] = make_float2(b[k].x, -a[7 - k].y);
+	for(int k = 0; k < 4; ++k) {
+		loA[J * k] = make_float2(a[k].x, -b[7 - k].y);
+		loB[J * k] = make_float2(b[k].x, -a[7 - k].y);
+		hiA[J * k] = make_float2(a[k + 4].x, -b[3 - k].y);
+		hiB[J * k] = make_float2(b[k + 4].x, -a[3 - k].y);
 	}
 	__syncwarp();
 }
@@ -560,9 +568,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	// ---- warp-private areas ----
 	const uint32_t warp_bytes = (uint32_t) kWarpFixedBytes + P.curve_bytes;
 	unsigned char* wbase = smem + kOffWarps + (size_t) warp * warp_bytes;
-	float2* region0 = reinterpret_cast<float2*>(wbase);      // two FFT work regions, used alternately by consecutive steps
-	WPkt* wp = reinterpret_cast<WPkt*>(wbase + 2 * kRegionF2 * 8);
-	unsigned char* fs = wbase + 2 * kRegionF2 * 8 + kPktCap * (int) sizeof(WPkt);
+	float2* slotA = reinterpret_cast<float2*>(wbase);        // work area: three half regions A | B | C (see kSlotF2)
+	WPkt* wp = reinterpret_cast<WPkt*>(wbase + kWorkBytes);
+	unsigned char* fs = wbase + kWorkBytes + kPktCap * (int) sizeof(WPkt);
 	unsigned char* curves = wbase + kWarpFixedBytes;
 
 	const int C = (int) P.C;
@@ -578,20 +586,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 		const DevRun run = P.runs[run_idx];
 		const int run_n = (int) run.n_packets;        // <= kPktCap
 		__syncwarp();
+		const pov_packet* pk0 = b.packets + run.first_packet;
+		const uint64_t spec0 = b.spec_off[run.first_packet], pcm0 = pk0->pcm_off;
 		if(lane < run_n) {
-			const pov_packet pk = b.packets[run.first_packet + lane];
+			const pov_packet pk = pk0[lane];
 			WPkt w;
 			w.meta = (uint32_t) pk.mode | ((uint32_t) pk.window_flags << 8) | ((uint32_t) pk.floor_used << 16);
-			w.emit = pk.emit_frames; w.ys_off = pk.ys_off; w.pcm_off = pk.pcm_off; w.spec_off = b.spec_off[run.first_packet + lane];
+			w.emit = pk.emit_frames;
+			w.pcm_rel = (uint32_t) (pk.pcm_off - pcm0);                                       // host guarantees 32-bit deltas
+			w.spec_rel = (int32_t) (int64_t) (b.spec_off[run.first_packet + lane] - spec0);
 			wp[lane] = w;
 		}
-		const pov_stream st = b.streams[b.packets[run.first_packet].stream];
+		const pov_stream st = b.streams[pk0->stream];
+		const float* spec_base = b.spectra + spec0;
+		const uint64_t frame0 = pcm0;           // stream frame index of the run's first packet chunk
 		__syncwarp();
-		unwrap_run(tb, wp, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(region0), fs, b.status + run.first_packet, lane);
+		unwrap_run(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, lane);
 
 		int prev_valid = 0, prev_n = 0, prev_right = 0;
 		const float* prev_lo = nullptr;
-		int reg = 0;
+		int par = 0;                             // step parity: which half regions this step uses
 		int first = 0;
 		while(first < run_n) {
 			const uint32_t meta0 = wp[first].meta;
@@ -600,7 +614,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			const uint32_t mapping = tb->mode_map[mode];
 			const FastCouple* cp = &tb->couple[mapping][ch];
 			const FastFloor* F = &tb->floors[tb->floor_of_ch[mapping][ch]];
-			float2* T = region0 + reg * kRegionF2;
+			float2* T = slotA + par * kSlotF2;                       // A+B or B+C
+			float2* surv = slotA + par * (2 * kSlotF2);              // A or C: where this step's last D lo half stays
+			float2* slotB = slotA + kSlotF2;
 			int count = 1;
 			if(!flag) while(count < (int) P.group_short && first + count < run_n && (wp[first + count].meta & 0xffu) == mode) ++count;
 
@@ -611,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				const uint32_t nhalf = tb->mode_flag[nmode] ? 1024u : 128u;
 				const FastCouple* ncp = &tb->couple[tb->mode_map[nmode]][ch];
 				if((uint32_t) lane * 32u < nhalf)
-					for(int i = 0; i < (int) ncp->nl; ++i) prefetch_l2(b.spectra + nw.spec_off + (size_t) ncp->ch[i] * nhalf + (size_t) lane * 32u);
+					for(int i = 0; i < (int) ncp->nl; ++i) prefetch_l2(spec_base + nw.spec_rel + (int) (ncp->ch[i] * nhalf) + lane * 32);
 			}
 			// ================= one long packet (the whole warp is one 512-point FFT) or up to 8 short packets (four lanes
 			//                   per 64-point FFT): same code, geometry in registers =================
@@ -628,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			const uint32_t Ts = smem_u32(T), Tfs = Ts + (uint32_t) f * (72u * 8u);
 			const uint32_t rots = smem_u32(flag ? s_rot1 : s_rot0), tws = smem_u32(flag ? s_tw1 : s_tw0);
 			if(f < count)
-				spectral_dispatch(cp, b.spectra + wp[first + f].spec_off, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u);
+				spectral_dispatch(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u);
 			__syncwarp();
 			{
 				const uint32_t uu = (uint32_t) u, u2 = (uint32_t) Js - 1u - uu;
@@ -640,25 +656,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 					        Ts + (j0 * 66 + k0) * 8, Ts + (j0 * 66 + k0 + 4) * 8, 8);
 				}
 				// last pass + post-rotation -> D (float2[Q] per FFT, packed back to back)
+				// long: lo half -> survivor slot, hi half -> slot B; short: D of FFT f packed at T + 64 f (lo | hi)
 				const uint32_t ia = flag ? uu * 8u : uu * 72u, ib = flag ? u2 * 8u : u2 * 72u;
-				const uint32_t od = Ts + (uint32_t) f * (64u * 8u);
-				last_pass(Tfs + ia, Tfs + ib, flag ? 66 : 1, rots + uu * 8, rots + u2 * 8, Js, od + uu * 8, od + u2 * 8);
+				const uint32_t lo = flag ? smem_u32(surv) : Ts + (uint32_t) f * (64u * 8u);
+				const uint32_t hi = flag ? smem_u32(slotB) : lo + 32u * 8u;
+				last_pass(Tfs + ia, Tfs + ib, flag ? 66 : 1, rots + uu * 8, rots + u2 * 8, Js, lo + uu * 8, lo + u2 * 8, hi + uu * 8, hi + u2 * 8);
 			}
 
 			// ================= window + overlap-add + emit (hpp:1008-1059 in gather form) =================
 			const int n = flag ? 2048 : 256, Q = n / 4;
 			const float* Dstep = reinterpret_cast<const float*>(T);
+			const uint64_t chan0 = st.pcm_base + (uint64_t) ch * st.pcm_frames + frame0;
 			for(int g = 0; g < count; ++g) {
 				const WPkt& w = wp[first + g];
 				const uint32_t wflags = (w.meta >> 8) & 0xffu, emit = w.emit;
 				// hpp:844-847: short blocks always use blocksize0 slopes; long blocks follow their own prev/next flags
 				const int lc = (flag && (wflags & 1u)) ? 1024 : 128;
 				const int rc = (flag && (wflags & 2u)) ? 1024 : 128;
-				const float* cur_lo = Dstep + (size_t) g * 2 * Q;
-				const float* cur_hi = cur_lo + Q;
+				const float* cur_lo = flag ? reinterpret_cast<const float*>(surv) : Dstep + (size_t) g * 2 * Q;
+				const float* cur_hi = flag ? reinterpret_cast<const float*>(slotB) : cur_lo + Q;
 				const bool emits = prev_valid && emit > 0 && (run.first_packet + (uint32_t) (first + g)) != st.first_packet;
 				if(emits) {
-					const uint64_t chan_base = st.pcm_base + (uint64_t) ch * st.pcm_frames + w.pcm_off;
+					const uint64_t chan_base = chan0 + w.pcm_rel;
 					if(planar && flag && prev_n == 2048 && lc == 1024 && prev_right == 1024 && emit == 1024u && (chan_base & 3ull) == 0) {
 						ola_long_long(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, lane);
 					} else {
@@ -671,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 						G.slR = (prev_right == 1024) ? s_slope1 : s_slope0;
 						for(uint32_t j = (uint32_t) lane; j < emit; j += 32u) {
 							const float v = ola_one(G, prev_lo, cur_hi, (int) j);
-							const uint64_t fidx = w.pcm_off + j;
+							const uint64_t fidx = frame0 + w.pcm_rel + j;
 							const uint64_t o = planar ? st.pcm_base + (uint64_t) ch * st.pcm_frames + fidx : st.pcm_base + fidx * (uint64_t) C + (uint64_t) ch;
 							b.pcm[o] = v;
 						}
@@ -679,8 +698,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				}
 				prev_valid = 1; prev_n = n; prev_right = rc; prev_lo = cur_lo;
 			}
+			if(!flag && prev_lo != reinterpret_cast<const float*>(surv)) {
+				// short step: move the last packet's D lo half (32 float2) into the survivor slot
+				__syncwarp();
+				const float2 v = reinterpret_cast<const float2*>(prev_lo)[lane];
+				__syncwarp();
+				surv[lane] = v;
+				__syncwarp();
+				prev_lo = reinterpret_cast<const float*>(surv);
+			}
 			first += count;
-			reg ^= 1;
+			par ^= 1;
 		}
 	}
 }
