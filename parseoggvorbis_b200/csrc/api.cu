@@ -482,6 +482,8 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	}
 	h->warp_ok = warp_ok;
 	h->warp_setup = warp_ok ? b->streams[0].setup_id : 0;
+	// enough work for several items per warp: worth ordering the items so that the short ones come last
+	const bool balance_tail = warp_ok && (uint64_t) P * ctx->setups[h->warp_setup].channels >= (uint64_t) ctx->sm_count * 16 * 31 * 4;
 	uint32_t run_len = ctx->run_len;
 	if(warp_ok) {
 		// work items = runs x channels, taken dynamically by sm_count*16 warps: aim for >= 8 items per warp, keep the
@@ -542,17 +544,30 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 			h->pk_n[p] = n; h->pk_setup[p] = st.setup_id;
 			n_prev = n;
 		}
-		// runs of <= run_len packets, each later run re-transforming one halo packet
-		for(uint32_t k = 0; k < st.n_packets; k += run_len) {
-			DevRun r;
-			r.halo = k ? 1u : 0u;
-			r.first_packet = st.first_packet + k - r.halo;
-			r.n_packets = std::min(run_len, st.n_packets - k) + r.halo;
-			r.pad = 0;
-			h->runs.push_back(r);
+		// runs of <= run_len packets, each later run re-transforming one halo packet. For the persistent warp kernel the
+		// last ~7 % / ~3.5 % of every stream are cut into half / quarter length runs (tiers 1, 2) that are handed out last:
+		// the final wave of work items is then a quarter as long, which trims the idle tail of the launch.
+		{
+			const uint32_t t1 = (warp_ok && balance_tail && run_len >= 16) ? st.n_packets - st.n_packets * 7 / 100 : st.n_packets;
+			const uint32_t t2 = (warp_ok && balance_tail && run_len >= 16) ? st.n_packets - st.n_packets * 35 / 1000 : st.n_packets;
+			for(uint32_t k = 0; k < st.n_packets;) {
+				const uint32_t tier = k >= t2 ? 2u : k >= t1 ? 1u : 0u;
+				uint32_t len = tier == 2 ? run_len / 4 : tier == 1 ? run_len / 2 : run_len;
+				if(tier == 0 && k + len > t1 && t1 > k) len = t1 - k;          // do not straddle a tier boundary
+				if(tier == 1 && k + len > t2 && t2 > k) len = t2 - k;
+				DevRun r;
+				r.halo = k ? 1u : 0u;
+				r.first_packet = st.first_packet + k - r.halo;
+				r.n_packets = std::min(len, st.n_packets - k) + r.halo;
+				r.pad = tier;
+				h->runs.push_back(r);
+				k += r.n_packets - r.halo;
+			}
 		}
 	}
 	if(expect_first != P) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: %u packets not covered by the stream table", (uint32_t) (P - expect_first));
+	if(warp_ok && balance_tail)
+		std::stable_sort(h->runs.begin(), h->runs.end(), [](const DevRun& a, const DevRun& b) { return a.pad < b.pad; });
 	if(h->warp_ok) {
 		// the warp kernel keeps per-packet offsets relative to the run's first packet in 32 bits
 		for(const DevRun& r : h->runs) {
