@@ -354,6 +354,15 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = samples_per_step * BYTES_PER_SAMPLE / (kernel_ms * 1e-3) / 1e9
+        # DRAM traffic of one launch from the committed ncu --set full capture of this very workload (per launch, GB)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            if tj["kernel"] == kernel_name and int(tj["samples_per_launch"]) == samples_per_step:
+                traffic = tj["traffic_bytes_per_launch"] / 1e9
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -366,7 +375,8 @@ def main():
                                     (samples_per_step * BYTES_PER_SAMPLE / 1e9),
                        "parallelism": "independent streams sharded across ranks, no collective"},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": samples_per_step * BYTES_PER_SAMPLE,
                          "kernel_ms": kernel_ms},
             "gpu_launches": int(launches_timed), "clocks": clocks, "check": check,
