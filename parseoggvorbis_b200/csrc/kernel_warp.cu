@@ -400,7 +400,7 @@ __device__ __noinline__ void spectral_stage(const float* __restrict__ base, int 
 		nva[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + 2 * u)));
 		nvb[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + M - 2 - 2 * u)));
 	}
-#pragma unroll 1
+#pragma unroll 2        // two iterations in flight: more independent work per warp; 4 would overflow the instruction cache
 	for(int m = 0; m < 8; ++m) {
 		const int jp = u + J * m;                  // point jp and its mirror Q-1-jp
 		float2 va[NL], vb[NL];                     // bins (2jp, 2jp+1) and (M-2-2jp, M-1-2jp) of every needed channel
