@@ -134,7 +134,7 @@ __device__ __forceinline__ float uncouple_ang(float m, float a) {
 // independent). The final Y values leave in ascending-x order as bytes, with the step2 flags as a bit mask, 36 bytes per
 // packet; the hpp:536 / hpp:587 checks are evaluated here with full-width values and reported per packet.
 // scratch: [32 posts][32 lanes] uint16, aliasing the (idle) FFT work regions.
-__device__ __noinline__ void unwrap_run(const FastTables* __restrict__ tb, const WPkt* __restrict__ wp, const pov_packet* __restrict__ pk0, int run_n, int ch,
+__device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, const WPkt* __restrict__ wp, const pov_packet* __restrict__ pk0, int run_n, int ch,
                                         const uint16_t* __restrict__ ys, uint16_t* __restrict__ scratch, unsigned char* __restrict__ fs,
                                         uint32_t* __restrict__ status, int lane) {
 	const bool have = lane < run_n;
@@ -216,7 +216,7 @@ __device__ __noinline__ void unwrap_run(const FastTables* __restrict__ tb, const
 // Rank table: for every 32-bin word w of the curve, tab[w] = (bitmap of the flagged posts inside the word,
 // number of flagged posts before the word - 1); the record that contains bin x is
 //   tab[x >> 5].y + popc(tab[x >> 5].x & (0xFFFFFFFF >> (31 - (x & 31)))).
-__device__ __noinline__ void build_records(const FastFloor* __restrict__ F, const unsigned char* __restrict__ fsp, unsigned char* __restrict__ curve,
+__device__ __forceinline__ void build_records(const FastFloor* __restrict__ F, const unsigned char* __restrict__ fsp, unsigned char* __restrict__ curve,
                                            uint32_t rec_cap, uint32_t nwords, const uint32_t* __restrict__ recip, int lane) {
 	const int posts = (int) F->n_posts;
 	const bool have = lane < posts;
@@ -330,7 +330,7 @@ __device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ t
 // Radix-8 DIF pass of two butterflies per lane: inputs in*[m*sin], outputs out*[k*sout] (twiddled by tw*).
 // All addresses are shared-window byte addresses, strides are in float2 units. Twiddles of butterfly j: (W^j, W^2j) at
 // tw, (W^3j, W^4j) at tw + twhalf (the table keeps the two halves apart so that lanes read consecutive 16-byte words).
-__device__ __noinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t twA_, uint32_t twB_, int twhalf, uint32_t outA_, uint32_t outB_, int sout) {
+__device__ __forceinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t twA_, uint32_t twB_, int twhalf, uint32_t outA_, uint32_t outB_, int sout) {
 	const float2* inA = sptr<const float2>(inA_); const float2* inB = sptr<const float2>(inB_);
 	float2* outA = sptr<float2>(outA_); float2* outB = sptr<float2>(outB_);
 	float2 a[8], b[8];
@@ -348,7 +348,7 @@ __device__ __noinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint
 
 // Last pass + post-rotation of butterflies kkA and kkB = J-1-kkA (rotA = rot + kkA, rotB = rot + kkB):
 //   c[k] = X[k] * w[k];  D2[k] = (D[2k], D[2k+1]) = (Re c[k], -Im c[Q-1-k]);  Q-1-(kkA + J k2) = kkB + J (7-k2)
-__device__ __noinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t rotA_, uint32_t rotB_, int J,
+__device__ __forceinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t rotA_, uint32_t rotB_, int J,
                                        uint32_t loA_, uint32_t loB_, uint32_t hiA_, uint32_t hiB_) {
 	const float2* inA = sptr<const float2>(inA_); const float2* inB = sptr<const float2>(inB_);
 	const float2* rotA = sptr<const float2>(rotA_); const float2* rotB = sptr<const float2>(rotB_);
@@ -381,7 +381,7 @@ __device__ __noinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, ui
 // src*: spectra ([n/2] floats) of the local channels of this lane's packet (src0 = this warp's channel);
 // fmode: 0 evaluate the curve, 1 multiply by 1 (hpp:1247 skipped), 2 multiply by 0.
 template <int NL, bool GEN>
-__device__ __noinline__ void spectral_stage(const float* __restrict__ base, int o0, int o1, int o2, int o3, uint32_t curve_, uint32_t rec_cap,
+__device__ __forceinline__ void spectral_stage(const float* __restrict__ base, int o0, int o1, int o2, int o3, uint32_t curve_, uint32_t rec_cap,
                                             uint32_t rot_, int Q, uint32_t Tf_, int u, uint32_t cp_) {
 	const int J = Q >> 3, M = 2 * Q;
 	const uint2* rec = sptr<const uint2>(curve_);
