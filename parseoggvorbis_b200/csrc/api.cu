@@ -483,15 +483,16 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	h->warp_ok = warp_ok;
 	h->warp_setup = warp_ok ? b->streams[0].setup_id : 0;
 	// enough work for several items per warp: worth ordering the items so that the short ones come last
-	const bool balance_tail = warp_ok && (uint64_t) P * ctx->setups[h->warp_setup].channels >= (uint64_t) ctx->sm_count * 16 * 31 * 4;
+	const bool balance_tail = warp_ok && (uint64_t) P * ctx->setups[h->warp_setup].channels >= (uint64_t) ctx->sm_count * warp_kernel_warps() * warp_kernel_max_run() * 4;
 	uint32_t run_len = ctx->run_len;
 	if(warp_ok) {
 		// work items = runs x channels, taken dynamically by sm_count*16 warps: aim for >= 8 items per warp, keep the
 		// halo overhead (one re-transformed packet per run) small; a run holds <= 32 packet descriptors, halo included
 		const uint64_t C = ctx->setups[h->warp_setup].channels;
-		const uint64_t want_items = (uint64_t) ctx->sm_count * 16 * 8;
-		const uint64_t auto_len = std::min<uint64_t>(31, std::max<uint64_t>(8, (uint64_t) P * C / want_items));
-		run_len = run_len ? std::min<uint32_t>(run_len, 31) : (uint32_t) auto_len;
+		const uint64_t want_items = (uint64_t) ctx->sm_count * warp_kernel_warps() * 8;
+		const uint64_t max_run = warp_kernel_max_run();
+		const uint64_t auto_len = std::min<uint64_t>(max_run, std::max<uint64_t>(8, (uint64_t) P * C / want_items));
+		run_len = run_len ? std::min<uint32_t>(run_len, (uint32_t) max_run) : (uint32_t) auto_len;
 	} else if(run_len == 0) {
 		// aim for >= ~8 CTAs per SM when the batch is big enough, keep the halo overhead <= 1/run_len
 		const uint64_t want_runs = (uint64_t) ctx->sm_count * 8;

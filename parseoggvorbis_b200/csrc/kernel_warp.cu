@@ -29,13 +29,23 @@
 namespace pov {
 namespace wk {
 
-constexpr int kWarps = 16;
+#ifndef POV_WARP_WARPS
+#define POV_WARP_WARPS 20
+#endif
+constexpr int kWarps = POV_WARP_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRegionF2 = 576;          // float2 slots of one FFT work region (long: 8*72, short: 8 FFTs * 72)
 constexpr int kSlotF2 = kRegionF2 / 2;  // the work area of a warp is three half regions A | B | C: even steps transform in
                                         // A+B and leave their overlap half (D lo) in A, odd steps use B+C and leave it in C;
                                         // the other half (D hi, consumed by the same step's overlap-add) always lands in B
-constexpr int kPktCap = 32;             // packets per run, halo included
+#ifndef POV_WARP_PKT_CAP
+#define POV_WARP_PKT_CAP 32
+#endif
+#ifndef POV_WARP_CURVE_MAX
+#define POV_WARP_CURVE_MAX 2048
+#endif
+constexpr int kPktCap = POV_WARP_PKT_CAP;   // packets per run, halo included (<= 32: one lane per packet in unwrap_run)
+constexpr uint32_t kCurveMax = POV_WARP_CURVE_MAX;   // bytes of curve blocks a warp may hold (bounds the short-packet group)
 constexpr uint32_t FULL = 0xffffffffu;
 
 struct __align__(16) WPkt { uint32_t meta, emit, pcm_rel; int32_t spec_rel; };   // 16 bytes; offsets relative to the run's first packet
@@ -719,7 +729,7 @@ size_t warp_kernel_smem_bytes(uint32_t short_posts_cap, uint32_t* group_short_ou
 	const uint32_t stride = short_posts_cap * 8u + 32u;        // records + 4 rank-table words
 	uint32_t group = 8;
 	uint32_t cb = 32u * 8u + 32u * 8u;                    // one long curve: 32 records + 32 rank-table words
-	while(group > 1 && group * stride > 2048u) --group;
+	while(group > 1 && group * stride > wk::kCurveMax) --group;
 	if(group * stride > cb) cb = group * stride;
 	cb = (cb + 15u) & ~15u;
 	if(group_short_out) *group_short_out = group;
@@ -727,6 +737,9 @@ size_t warp_kernel_smem_bytes(uint32_t short_posts_cap, uint32_t* group_short_ou
 	if(short_stride_out) *short_stride_out = stride;
 	return (size_t) wk::kOffWarps + (size_t) wk::kWarps * ((size_t) wk::kWarpFixedBytes + cb);
 }
+
+uint32_t warp_kernel_max_run(void) { return (uint32_t) wk::kPktCap - 1u; }
+uint32_t warp_kernel_warps(void) { return (uint32_t) wk::kWarps; }
 
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
                         uint32_t short_posts_cap, const float* const slope[2], const float2* const rot[2], const float2* const tw8[2],
