@@ -267,3 +267,83 @@ def golden_setup_and_batch(g: Dict[str, np.ndarray]) -> Tuple[abi.Setup, abi.Bat
     batch = abi.Batch(streams, packets, np.concatenate(ys_list), g["after_residue"].astype(np.float32),
                       int(emit.sum()) * C)
     return setup, batch
+
+
+# ---- randomised setups (parity stress: many floors, submaps, modes, coupling graphs) ------------------------------
+def random_setup(rng: np.random.Generator, channels: int, blocksizes=(256, 2048), max_posts: int = 32,
+                 max_couplings: int = 5, max_component: int = 4) -> abi.Setup:
+    """A random but well-formed setup: 1-2 floors per blocksize class with random distinct X lists and multipliers,
+    1-3 submaps with their own floors, up to `max_couplings` coupling steps whose connected components stay within
+    `max_component` channels, and 2-4 modes over 2-4 mappings. Floor class of a mapping follows its modes."""
+    bs0, bs1 = blocksizes
+    floors, cls_floors = [], {0: [], 1: []}
+    for cls, half in ((0, bs0 // 2), (1, bs1 // 2)):
+        for _ in range(int(rng.integers(1, 3))):
+            posts = int(rng.integers(2, min(max_posts, half) + 1))
+            inner = rng.choice(np.arange(1, half), size=posts - 2, replace=False) if posts > 2 else np.zeros(0, int)
+            xs = [0, half] + [int(v) for v in inner]
+            cls_floors[cls].append(len(floors))
+            floors.append(abi.Floor1(xs, int(rng.integers(1, 5))))
+    # coupling steps with bounded connected components
+    comp = list(range(channels))
+    size = {c: 1 for c in range(channels)}
+
+    def find(c):
+        while comp[c] != c:
+            c = comp[c]
+        return c
+    coupl = []
+    for _ in range(int(rng.integers(0, max_couplings + 1)) if channels > 1 else 0):
+        m, a = (int(v) for v in rng.choice(channels, size=2, replace=False))
+        rm, ra = find(m), find(a)
+        if rm != ra:
+            if size[rm] + size[ra] > max_component:
+                continue
+            comp[ra] = rm
+            size[rm] += size[ra]
+        coupl.append((m, a))
+    n_submaps = int(rng.integers(1, min(3, channels) + 1))
+    mux = [int(v) for v in rng.integers(0, n_submaps, size=channels)]
+    mappings, modes = [], []
+    n_modes = int(rng.integers(2, 5))
+    flags = [0, 1] + [int(v) for v in rng.integers(0, 2, size=n_modes - 2)]
+    for f in flags:
+        mappings.append(abi.Mapping(mux=mux, submap_floor=[int(rng.choice(cls_floors[f])) for _ in range(n_submaps)],
+                                    submap_residue=[0] * n_submaps, couplings=list(coupl)))
+        modes.append(abi.Mode(f, len(mappings) - 1))
+    return abi.Setup(channels=channels, sample_rate=44100, blocksize=(bs0, bs1), floors=floors, mappings=mappings, modes=modes)
+
+
+def random_batch(setup: abi.Setup, rng: np.random.Generator, streams: int = 3, packets_per_stream: int = 70,
+                 p_unused: float = 0.15, p_short: float = 0.2) -> abi.Batch:
+    """Dense batch for an arbitrary setup (per-channel floors through the submaps, any mode of the right block class)."""
+    C = setup.channels
+    modes_of = {0: [i for i, m in enumerate(setup.modes) if not m.blockflag], 1: [i for i, m in enumerate(setup.modes) if m.blockflag]}
+    pk_rows, st_rows, ys_all, spec_all = [], [], [], []
+    ys_off = spec_off = pcm_base = first = 0
+    for s in range(streams):
+        bf = block_sequence(packets_per_stream, rng, p_short=p_short)
+        plan = plan_stream(bf, setup.blocksize, trim_last=int(rng.integers(0, 40)))
+        for k in range(packets_per_stream):
+            mode = int(rng.choice(modes_of[int(bf[k])]))
+            mp = setup.mappings[setup.modes[mode].mapping]
+            half = int(plan.n[k]) // 2
+            used = 0
+            this_ys_off = ys_off
+            for c in range(C):
+                if rng.random() >= p_unused:
+                    used |= 1 << c
+                    fl = setup.floors[mp.submap_floor[mp.mux[c]]]
+                    ys_all.append(gen_ys(rng, 1, len(fl.xs), FLOOR_RANGE[fl.multiplier])[0])
+                    ys_off += len(fl.xs)
+            spec_all.append(gen_spectra(rng, C, half).ravel())
+            pk_rows.append((s, mode, int(plan.window_flags[k]), used, int(plan.emit[k]), 0, int(plan.pcm_off[k]), this_ys_off, spec_off))
+            spec_off += C * half
+        st_rows.append((0, first, packets_per_stream, 0, plan.frames, pcm_base))
+        pcm_base += plan.frames * C
+        first += packets_per_stream
+    packets = np.array(pk_rows, dtype=abi.PACKET_DTYPE)
+    st = np.array(st_rows, dtype=abi.STREAM_DTYPE)
+    ys = np.concatenate(ys_all).astype(np.uint16) if ys_all else np.zeros(0, np.uint16)
+    return abi.Batch(streams=st, packets=packets, ys=ys, payload=np.concatenate(spec_all).astype(np.float32),
+                     pcm_floats=pcm_base, input_kind=abi.POV_INPUT_DENSE, pcm_layout=abi.POV_PCM_PLANAR)

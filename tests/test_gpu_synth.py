@@ -116,7 +116,8 @@ def _check_against_oracle(ctx, setup, batch, stages=False):
         staged = ctx.fetch_pcm(bh)
         _assert_float_parity(fused, staged, "fused vs staged")
         C = setup.channels
-        n_of = np.asarray(setup.blocksize)[batch.packets["mode"].astype(int)]   # mode 0 short / 1 long in workloads
+        flag_of_mode = np.asarray([m.blockflag for m in setup.modes])
+        n_of = np.asarray(setup.blocksize)[flag_of_mode[batch.packets["mode"].astype(int)]]
         for p in range(0, len(batch.packets), max(1, len(batch.packets) // 40)):
             n = int(n_of[p])
             for c in range(C):
@@ -241,3 +242,60 @@ def test_descriptor_validation_errors(ctx):
     s2.floors[0] = abi.Floor1([0, 128, 14, 14], 4)       # duplicate X
     with pytest.raises(PovError):
         ctx.register_setup(s2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_random_setups_against_oracle(ctx, seed):
+    """Random floors (2..32 posts, multipliers 1..4, random X lists), submaps with their own floors, several modes and
+    mappings, coupling graphs with shared channels, unused channels: the persistent warp kernel (and, for seeds whose
+    setup it does not take, the generic kernel) against the CPU oracle, status words included."""
+    rng = np.random.default_rng(1000 + seed)
+    C = int(rng.integers(1, 9))
+    setup = workloads.random_setup(rng, C)
+    batch = workloads.random_batch(setup, rng, streams=3, packets_per_stream=70)
+    _check_against_oracle(ctx, setup, batch, stages=(seed % 4 == 0))
+
+
+@pytest.mark.gpu
+def test_random_setups_take_the_warp_kernel(ctx):
+    taken = 0
+    for seed in range(12):
+        rng = np.random.default_rng(1000 + seed)
+        C = int(rng.integers(1, 9))
+        setup = workloads.random_setup(rng, C)
+        batch = workloads.random_batch(setup, rng, streams=1, packets_per_stream=8)
+        batch.streams["setup_id"] = ctx.register_setup(setup)
+        bh = ctx.upload(batch)
+        taken += ctx.kernel_name(bh) == "k_warp_synth"
+        bh.free()
+    assert taken >= 9, taken      # the generator keeps coupling components within what the warp kernel supports
+
+
+@pytest.mark.gpu
+def test_full_size_properties_config2(ctx, monkeypatch):
+    """BASELINE.json configs[1] at its full per-stream size (4096 packets, mixed blocks): properties that do not need
+    the oracle at full size — replicated streams decode to bit-identical PCM wherever they sit in the arenas, the result
+    does not depend on how streams are cut into runs, no packet reports a status — plus the oracle on one whole stream."""
+    setup, batch = workloads.config2(P=4096, streams=8, distinct=4, seed=5)
+    batch.streams["setup_id"] = ctx.register_setup(setup)
+    bh = ctx.upload(batch)
+    assert ctx.kernel_name(bh) == "k_warp_synth"
+    ctx.run(bh)
+    pcm = ctx.fetch_pcm(bh)
+    assert not ctx.status(bh).any()
+    per = int(batch.pcm_floats) // 2
+    assert np.array_equal(pcm[:per], pcm[per:])                    # second replica of the 4 distinct streams
+    st = batch.streams[:1].copy(); st["setup_id"] = 0
+    sub = abi.Batch(st, batch.packets[:int(st["n_packets"][0])].copy(), batch.ys, batch.payload,
+                    int(st["pcm_frames"][0]) * setup.channels)
+    ref, _ = ob.synth_batch([setup], sub, imdct="fast")
+    _assert_float_parity(pcm[:sub.pcm_floats], ref, "stream 0 vs oracle")
+    from parseoggvorbis_b200.lib import SynthContext
+    monkeypatch.setenv("POV_RUN_LEN", "13")
+    c2 = SynthContext(0)
+    batch.streams["setup_id"] = c2.register_setup(setup)
+    bh2 = c2.upload(batch)
+    c2.run(bh2)
+    assert np.array_equal(c2.fetch_pcm(bh2), pcm)
+    bh2.free(); c2.close(); bh.free()
