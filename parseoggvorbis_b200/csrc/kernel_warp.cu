@@ -312,6 +312,28 @@ __device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, cons
 	return out;
 }
 
+// Four consecutive bins x..x+3 (x a multiple of 4) of a curve as inverse-dB table values (hpp:586-589): one rank-table
+// and one record read for the quad; the bitmap tells which of the bins x+1..x+3 start a new segment.
+__device__ __forceinline__ float4 curve_quad(const uint2* __restrict__ rec, const uint2* __restrict__ tab, uint32_t x,
+                                             const float* __restrict__ invdb) {
+	const uint2 t = tab[x >> 5];
+	const uint32_t sh = x & 31u;                                         // <= 28
+	uint32_t s = t.y + __popc(t.x & (0xFFFFFFFFu >> (31u - sh)));
+	const uint32_t cross = t.x >> (sh + 1u);                             // bit b-1: bin x+b starts a segment (b = 1..3)
+	uint2 r = rec[s];
+	float out[4];
+#pragma unroll
+	for(int b = 0; b < 4; ++b) {
+		if(b > 0 && ((cross >> (b - 1)) & 1u)) r = rec[++s];
+		const uint32_t k = x + (uint32_t) b - (r.x & 0x7ffu);
+		const uint32_t q = __umulhi(k << 12, r.y & 0x7fffffffu);
+		const uint32_t y0 = r.x >> 22;
+		const uint32_t y = ((int) r.y < 0) ? y0 - q : y0 + q;
+		out[b] = invdb[y];
+	}
+	return make_float4(out[0], out[1], out[2], out[3]);
+}
+
 // ---- FFT geometry ----------------------------------------------------------------------------------------------------
 // The spectral stage leaves the pre-rotated points in natural order (point j at slot j of the FFT's buffer). Then
 // Q = 512 = 8*8*8: j = 64 j2 + 8 j1 + j0, k = k0 + 8 k1 + 64 k2
@@ -392,71 +414,83 @@ __device__ __forceinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin,
 // fmode: 0 evaluate the curve, 1 multiply by 1 (hpp:1247 skipped), 2 multiply by 0.
 template <int NL, bool GEN>
 __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, int o0, int o1, int o2, int o3, uint32_t curve_, uint32_t rec_cap,
-                                            uint32_t rot_, int Q, uint32_t Tf_, int u, uint32_t cp_) {
-	const int J = Q >> 3, M = 2 * Q;
+                                               uint32_t rot_, int Q, uint32_t Tf_, int u, uint32_t cp_) {
+	// Lane u handles the quads q = u + (Q/16) m, m = 0..3: bins 4q..4q+3 and M-4-4q..M-1-4q arrive with two 128-bit loads
+	// per channel and yield the points 2q, 2q+1 and their mirrors Q-2-2q, Q-1-2q (two 128-bit stores, natural order).
+	const int LPF = Q >> 4, M = 2 * Q;
 	const uint2* rec = sptr<const uint2>(curve_);
 	const uint2* tab = rec + rec_cap;
 	const float* invdb = reinterpret_cast<const float*>(g_smem + kOffInvDb);
-	const float2* rot = sptr<const float2>(rot_);
-	float2* Tf = sptr<float2>(Tf_);
+	const float4* rot4 = sptr<const float4>(rot_);        // rot4[j/2] = (w[j], w[j+1]), j even
+	float4* T4 = sptr<float4>(Tf_);
 	const FastCouple* cp = sptr<const FastCouple>(cp_);
 	// coupling program in registers (the loop below stores to shared memory, so nothing would be hoisted otherwise)
 	const int nsteps = (NL > 1) ? (int) cp->nsteps : 0;
 	const bool last_mag = (NL > 1 && nsteps > 0) ? (cp->sm[nsteps - 1] == 0) : false;
 	const int off[4] = {o0, o1, o2, o3};
-	float2 nva[NL], nvb[NL];
+	float4 nlo[NL], nhi[NL];
 #pragma unroll
 	for(int i = 0; i < NL; ++i) {
-		nva[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + 2 * u)));
-		nvb[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + M - 2 - 2 * u)));
+		nlo[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + 4 * u)));
+		nhi[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + M - 4 - 4 * u)));
 	}
-#pragma unroll 2        // two iterations in flight: more independent work per warp; 4 would overflow the instruction cache
-	for(int m = 0; m < 8; ++m) {
-		const int jp = u + J * m;                  // point jp and its mirror Q-1-jp
-		float2 va[NL], vb[NL];                     // bins (2jp, 2jp+1) and (M-2-2jp, M-1-2jp) of every needed channel
+#pragma unroll 1
+	for(int m = 0; m < 4; ++m) {
+		const int q = u + LPF * m;
+		float4 lo[NL], hi[NL];
 #pragma unroll
-		for(int i = 0; i < NL; ++i) { va[i] = nva[i]; vb[i] = nvb[i]; }
-		if(m < 7) {
+		for(int i = 0; i < NL; ++i) { lo[i] = nlo[i]; hi[i] = nhi[i]; }
+		if(m < 3) {
 #pragma unroll
 			for(int i = 0; i < NL; ++i) {
-				nva[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + 2 * (jp + J))));
-				nvb[i] = __ldg(reinterpret_cast<const float2*>(base + (off[i] + M - 2 - 2 * (jp + J))));
+				nlo[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + 4 * (q + LPF))));
+				nhi[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + M - 4 - 4 * (q + LPF))));
 			}
 		}
 		if(NL > 1 && !GEN) {
 			// single coupling step between two channels: only this warp's channel (local index 0) is needed
 			if(last_mag) {
-				va[0].x = uncouple_mag(va[0].x, va[NL - 1].x); va[0].y = uncouple_mag(va[0].y, va[NL - 1].y);
-				vb[0].x = uncouple_mag(vb[0].x, vb[NL - 1].x); vb[0].y = uncouple_mag(vb[0].y, vb[NL - 1].y);
+				lo[0].x = uncouple_mag(lo[0].x, lo[NL - 1].x); lo[0].y = uncouple_mag(lo[0].y, lo[NL - 1].y);
+				lo[0].z = uncouple_mag(lo[0].z, lo[NL - 1].z); lo[0].w = uncouple_mag(lo[0].w, lo[NL - 1].w);
+				hi[0].x = uncouple_mag(hi[0].x, hi[NL - 1].x); hi[0].y = uncouple_mag(hi[0].y, hi[NL - 1].y);
+				hi[0].z = uncouple_mag(hi[0].z, hi[NL - 1].z); hi[0].w = uncouple_mag(hi[0].w, hi[NL - 1].w);
 			} else {
-				va[0].x = uncouple_ang(va[NL - 1].x, va[0].x); va[0].y = uncouple_ang(va[NL - 1].y, va[0].y);
-				vb[0].x = uncouple_ang(vb[NL - 1].x, vb[0].x); vb[0].y = uncouple_ang(vb[NL - 1].y, vb[0].y);
+				lo[0].x = uncouple_ang(lo[NL - 1].x, lo[0].x); lo[0].y = uncouple_ang(lo[NL - 1].y, lo[0].y);
+				lo[0].z = uncouple_ang(lo[NL - 1].z, lo[0].z); lo[0].w = uncouple_ang(lo[NL - 1].w, lo[0].w);
+				hi[0].x = uncouple_ang(hi[NL - 1].x, hi[0].x); hi[0].y = uncouple_ang(hi[NL - 1].y, hi[0].y);
+				hi[0].z = uncouple_ang(hi[NL - 1].z, hi[0].z); hi[0].w = uncouple_ang(hi[NL - 1].w, hi[0].w);
 			}
 		} else if(NL > 1) {
 			for(int st = 0; st < nsteps; ++st) {
 				const int mi = cp->sm[st], ai = cp->sa[st];
-				float2 ma = va[0], mb = vb[0], aa = va[0], ab = vb[0];
+				float4 ml = lo[0], mh = hi[0], al = lo[0], ah = hi[0];
 #pragma unroll
 				for(int i = 0; i < NL; ++i) {
-					if(i == mi) { ma = va[i]; mb = vb[i]; }
-					if(i == ai) { aa = va[i]; ab = vb[i]; }
+					if(i == mi) { ml = lo[i]; mh = hi[i]; }
+					if(i == ai) { al = lo[i]; ah = hi[i]; }
 				}
-				uncouple2(ma, aa); uncouple2(mb, ab);
+				uncouple_f(ml.x, al.x); uncouple_f(ml.y, al.y); uncouple_f(ml.z, al.z); uncouple_f(ml.w, al.w);
+				uncouple_f(mh.x, ah.x); uncouple_f(mh.y, ah.y); uncouple_f(mh.z, ah.z); uncouple_f(mh.w, ah.w);
 #pragma unroll
 				for(int i = 0; i < NL; ++i) {
-					if(i == mi) { va[i] = ma; vb[i] = mb; }
-					if(i == ai) { va[i] = aa; vb[i] = ab; }
+					if(i == mi) { lo[i] = ml; hi[i] = mh; }
+					if(i == ai) { lo[i] = al; hi[i] = ah; }
 				}
 			}
 		}
-		const float2 fa = curve_pair(rec, tab, (uint32_t) (2 * jp), invdb);
-		const float2 fb = curve_pair(rec, tab, (uint32_t) (M - 2 - 2 * jp), invdb);
+		const float4 fl = curve_quad(rec, tab, (uint32_t) (4 * q), invdb);
+		const float4 fh = curve_quad(rec, tab, (uint32_t) (M - 4 - 4 * q), invdb);
 		// hpp:1252 residue *= floor (one rounding each)
-		const float a0 = __fmul_rn(va[0].x, fa.x), a1 = __fmul_rn(va[0].y, fa.y);
-		const float b0 = __fmul_rn(vb[0].x, fb.x), b1 = __fmul_rn(vb[0].y, fb.y);
-		// t[j] = (X[2j] + i X[M-1-2j]) * w[j]
-		Tf[jp] = cmul(make_float2(a0, b1), rot[jp]);
-		Tf[Q - 1 - jp] = cmul(make_float2(b0, a1), rot[Q - 1 - jp]);
+		const float l0 = __fmul_rn(lo[0].x, fl.x), l1 = __fmul_rn(lo[0].y, fl.y), l2 = __fmul_rn(lo[0].z, fl.z), l3 = __fmul_rn(lo[0].w, fl.w);
+		const float h0 = __fmul_rn(hi[0].x, fh.x), h1 = __fmul_rn(hi[0].y, fh.y), h2 = __fmul_rn(hi[0].z, fh.z), h3 = __fmul_rn(hi[0].w, fh.w);
+		// t[j] = (X[2j] + i X[M-1-2j]) * w[j] for j = 2q, 2q+1 and Q-2-2q, Q-1-2q
+		const float4 wl = rot4[q], wh = rot4[(Q >> 1) - 1 - q];
+		const float2 t0 = cmul(make_float2(l0, h3), make_float2(wl.x, wl.y));
+		const float2 t1 = cmul(make_float2(l2, h1), make_float2(wl.z, wl.w));
+		const float2 t2 = cmul(make_float2(h0, l3), make_float2(wh.x, wh.y));
+		const float2 t3 = cmul(make_float2(h2, l1), make_float2(wh.z, wh.w));
+		T4[q] = make_float4(t0.x, t0.y, t1.x, t1.y);
+		T4[(Q >> 1) - 1 - q] = make_float4(t2.x, t2.y, t3.x, t3.y);
 	}
 }
 
