@@ -428,24 +428,16 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 	const int nsteps = (NL > 1) ? (int) cp->nsteps : 0;
 	const bool last_mag = (NL > 1 && nsteps > 0) ? (cp->sm[nsteps - 1] == 0) : false;
 	const int off[4] = {o0, o1, o2, o3};
-	float4 nlo[NL], nhi[NL];
-#pragma unroll
-	for(int i = 0; i < NL; ++i) {
-		nlo[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + 4 * u)));
-		nhi[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + M - 4 - 4 * u)));
-	}
+	// (no hand-written register prefetch: with 20 warps per SM the loads of a whole iteration issued together hide
+	// their latency behind the other warps, and the 16 registers it would cost are what keeps the kernel spill free)
 #pragma unroll 1
 	for(int m = 0; m < 4; ++m) {
 		const int q = u + LPF * m;
 		float4 lo[NL], hi[NL];
 #pragma unroll
-		for(int i = 0; i < NL; ++i) { lo[i] = nlo[i]; hi[i] = nhi[i]; }
-		if(m < 3) {
-#pragma unroll
-			for(int i = 0; i < NL; ++i) {
-				nlo[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + 4 * (q + LPF))));
-				nhi[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + M - 4 - 4 * (q + LPF))));
-			}
+		for(int i = 0; i < NL; ++i) {
+			lo[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + 4 * q)));
+			hi[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + M - 4 - 4 * q)));
 		}
 		if(NL > 1 && !GEN) {
 			// single coupling step between two channels: only this warp's channel (local index 0) is needed
