@@ -439,6 +439,9 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 			lo[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + 4 * q)));
 			hi[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + M - 4 - 4 * q)));
 		}
+		// the floor evaluation needs none of the loaded values: it runs while the loads are in flight
+		const float4 fl = curve_quad(rec, tab, (uint32_t) (4 * q), invdb);
+		const float4 fh = curve_quad(rec, tab, (uint32_t) (M - 4 - 4 * q), invdb);
 		if(NL > 1 && !GEN) {
 			// single coupling step between two channels: only this warp's channel (local index 0) is needed
 			if(last_mag) {
@@ -470,8 +473,6 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 				}
 			}
 		}
-		const float4 fl = curve_quad(rec, tab, (uint32_t) (4 * q), invdb);
-		const float4 fh = curve_quad(rec, tab, (uint32_t) (M - 4 - 4 * q), invdb);
 		// hpp:1252 residue *= floor (one rounding each)
 		const float l0 = __fmul_rn(lo[0].x, fl.x), l1 = __fmul_rn(lo[0].y, fl.y), l2 = __fmul_rn(lo[0].z, fl.z), l3 = __fmul_rn(lo[0].w, fl.w);
 		const float h0 = __fmul_rn(hi[0].x, fh.x), h1 = __fmul_rn(hi[0].y, fh.y), h2 = __fmul_rn(hi[0].z, fh.z), h3 = __fmul_rn(hi[0].w, fh.w);
