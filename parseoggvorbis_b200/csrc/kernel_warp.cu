@@ -110,6 +110,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 // (a generic pointer argument would cost a window-base subtraction per access).
 template <class T> __device__ __forceinline__ T* sptr(uint32_t a) { return reinterpret_cast<T*>(__cvta_shared_to_generic((size_t) a)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {   // TMA bulk prefetch (size multiple of 16)
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ void uncouple_f(float& m, float& a) {   // hpp:1220-1239, branch-free
 	const float mv = m, av = a;
@@ -663,8 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				const uint32_t nmode = nw.meta & 0xffu;
 				const uint32_t nhalf = tb->mode_flag[nmode] ? 1024u : 128u;
 				const FastCouple* ncp = &tb->couple[tb->mode_map[nmode]][ch];
-				if((uint32_t) lane * 32u < nhalf)
-					for(int i = 0; i < (int) ncp->nl; ++i) prefetch_l2(spec_base + nw.spec_rel + (int) (ncp->ch[i] * nhalf) + lane * 32);
+				if(lane < (int) ncp->nl) prefetch_l2_bulk(spec_base + nw.spec_rel + (int) (ncp->ch[lane] * nhalf), nhalf * 4u);
 			}
 			// ================= one long packet (the whole warp is one 512-point FFT) or up to 8 short packets (four lanes
 			//                   per 64-point FFT): same code, geometry in registers =================
