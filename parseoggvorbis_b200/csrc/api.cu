@@ -478,7 +478,7 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	bool warp_ok = b->n_streams > 0 && ctx->kernel_choice != 1;
 	for(uint32_t si = 0; si < b->n_streams && warp_ok; ++si) {
 		const uint32_t id = b->streams[si].setup_id;
-		if(id >= ctx->setups.size() || id != b->streams[0].setup_id || !ctx->setups[id].fast_ok) warp_ok = false;
+		if(id >= ctx->setups.size() || !ctx->setups[id].fast_ok) warp_ok = false;     // several setups: one launch per setup
 	}
 	h->warp_ok = warp_ok;
 	h->warp_setup = warp_ok ? b->streams[0].setup_id : 0;
@@ -560,15 +560,24 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 				r.halo = k ? 1u : 0u;
 				r.first_packet = st.first_packet + k - r.halo;
 				r.n_packets = std::min(len, st.n_packets - k) + r.halo;
-				r.pad = tier;
+				r.pad = tier | (st.setup_id << 8);       // sort key below: work items grouped by setup, short tiers last
 				h->runs.push_back(r);
 				k += r.n_packets - r.halo;
 			}
 		}
 	}
 	if(expect_first != P) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: %u packets not covered by the stream table", (uint32_t) (P - expect_first));
-	if(warp_ok && balance_tail)
+	h->warp_groups.clear();
+	if(warp_ok) {
 		std::stable_sort(h->runs.begin(), h->runs.end(), [](const DevRun& a, const DevRun& b) { return a.pad < b.pad; });
+		for(uint32_t i = 0; i < h->runs.size();) {
+			const uint32_t sid = h->runs[i].pad >> 8;
+			uint32_t j = i;
+			while(j < h->runs.size() && (h->runs[j].pad >> 8) == sid) ++j;
+			h->warp_groups.push_back({sid, i, j - i});
+			i = j;
+		}
+	}
 	if(h->warp_ok) {
 		// the warp kernel keeps per-packet offsets relative to the run's first packet in 32 bits
 		for(const DevRun& r : h->runs) {
@@ -701,9 +710,11 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
 	int rc = run_residue_if_needed(ctx, h, v);
 	if(rc) return rc;
 	if(h->warp_ok) {
-		const SetupRec& su = ctx->setups[h->warp_setup];
-		CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), su.channels, su.d_fast, su.fast_short_cap,
-		                          su.dev.slope, su.dev.rot, su.dev.fft8, ctx->d_counter, ctx->sm_count, ctx->stream, &ctx->launches));
+		for(const WarpGroup& g : h->warp_groups) {      // one persistent launch per setup (its tables live in shared memory)
+			const SetupRec& su = ctx->setups[g.setup];
+			CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr + g.first_run, g.n_runs, su.channels, su.d_fast, su.fast_short_cap,
+			                          su.dev.slope, su.dev.rot, su.dev.fft8, ctx->d_counter, ctx->sm_count, ctx->stream, &ctx->launches));
+		}
 		return POV_OK;
 	}
 	CUDA_TRY(ctx, launch_fused(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), h->max_channels, h->max_blocksize,

@@ -70,6 +70,8 @@ struct pov_ctx {
 	char err[512] = {0};
 };
 
+struct WarpGroup { uint32_t setup, first_run, n_runs; };   // runs of one setup: one launch of the persistent warp kernel
+
 struct pov_batch_handle {
 	uint32_t n_streams = 0, n_packets = 0, input_kind = 0, pcm_layout = 0;
 	uint64_t pcm_floats = 0, stage_floats = 0, dense_floats = 0;
@@ -79,6 +81,7 @@ struct pov_batch_handle {
 	bool fused_ok = true, staged_ready = false, only_256_2048 = false;
 	bool warp_ok = false;         // every stream uses one setup that kernel_warp.cu supports
 	uint32_t warp_setup = 0;
+	std::vector<WarpGroup> warp_groups;
 	std::vector<uint64_t> spec_off, stage_off;
 	std::vector<uint32_t> pk_n, pk_setup;
 	std::vector<DevRun> runs;

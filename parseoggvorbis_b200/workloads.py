@@ -347,3 +347,20 @@ def random_batch(setup: abi.Setup, rng: np.random.Generator, streams: int = 3, p
     ys = np.concatenate(ys_all).astype(np.uint16) if ys_all else np.zeros(0, np.uint16)
     return abi.Batch(streams=st, packets=packets, ys=ys, payload=np.concatenate(spec_all).astype(np.float32),
                      pcm_floats=pcm_base, input_kind=abi.POV_INPUT_DENSE, pcm_layout=abi.POV_PCM_PLANAR)
+
+
+def concat_batches(a: abi.Batch, b: abi.Batch, setup_id_b: int) -> abi.Batch:
+    """Streams of `b` appended to `a` (dense batches): arenas concatenated, offsets rebased, b's streams get setup_id_b."""
+    assert a.input_kind == b.input_kind == abi.POV_INPUT_DENSE and a.pcm_layout == b.pcm_layout
+    sb, pb = b.streams.copy(), b.packets.copy()
+    sb["setup_id"] = setup_id_b
+    sb["first_packet"] += len(a.packets)
+    sb["pcm_base"] += np.uint64(a.pcm_floats)
+    pb["stream"] += len(a.streams)
+    pb["ys_off"] += np.uint64(len(a.ys))
+    pad = (-len(a.payload)) % 4                       # keep 16-byte alignment of every spectrum
+    pb["spec_off"] += np.uint64(len(a.payload) + pad)
+    payload = np.concatenate([a.payload, np.zeros(pad, np.float32), b.payload])
+    return abi.Batch(streams=np.concatenate([a.streams, sb]), packets=np.concatenate([a.packets, pb]),
+                     ys=np.concatenate([a.ys, b.ys]), payload=payload, pcm_floats=a.pcm_floats + b.pcm_floats,
+                     input_kind=a.input_kind, pcm_layout=a.pcm_layout)

@@ -299,3 +299,44 @@ def test_full_size_properties_config2(ctx, monkeypatch):
     c2.run(bh2)
     assert np.array_equal(c2.fetch_pcm(bh2), pcm)
     bh2.free(); c2.close(); bh.free()
+
+
+@pytest.mark.gpu
+def test_mixed_setups_in_one_batch(ctx):
+    """Streams of different setups (stereo, 5.1, mono) in one batch: the warp kernel is launched once per setup;
+    PCM and status against the oracle, and the edge cases of tiny streams (1 and 2 packets) ride along."""
+    s2, b2 = workloads.config2(P=150, streams=2, distinct=2, seed=21)
+    s3, b3 = workloads.config3(P=90, streams=1, distinct=1, seed=22)
+    s4, b4 = workloads.config4(clips=5, packets_per_clip=33, seed=23)
+    s5, b5 = workloads.config4(clips=2, packets_per_clip=1, seed=24)       # single-packet streams emit nothing (hpp:1021)
+    s6, b6 = workloads.config2(P=2, streams=1, distinct=1, seed=25)
+    ids = [ctx.register_setup(s) for s in (s2, s3, s4)]
+    merged = b2
+    merged.streams["setup_id"] = 0
+    merged = workloads.concat_batches(merged, b3, 1)
+    merged = workloads.concat_batches(merged, b4, 2)
+    merged = workloads.concat_batches(merged, b5, 2)
+    merged = workloads.concat_batches(merged, b6, 0)
+    ref, rstatus = ob.synth_batch([s2, s3, s4], merged, imdct="fast")
+    dev = merged
+    dev.streams["setup_id"] = np.asarray(ids, np.uint32)[merged.streams["setup_id"]]
+    bh = ctx.upload(dev)
+    assert ctx.kernel_name(bh) == "k_warp_synth"
+    n0 = ctx.launch_count
+    ctx.run(bh)
+    assert ctx.launch_count - n0 == 3                  # one persistent launch per setup
+    pcm = ctx.fetch_pcm(bh)
+    assert np.array_equal(ctx.status(bh), rstatus)
+    _assert_float_parity(pcm, ref, "mixed setups vs oracle")
+    bh.free()
+
+
+@pytest.mark.gpu
+def test_empty_batch_is_a_no_op(ctx):
+    setup, batch = workloads.config2(P=4, seed=1)
+    batch.streams["setup_id"] = ctx.register_setup(setup)
+    empty = abi.Batch(batch.streams[:0].copy(), batch.packets[:0].copy(), batch.ys[:0], batch.payload[:0], 0)
+    bh = ctx.upload(empty)
+    ctx.run(bh)
+    assert ctx.fetch_pcm(bh).size == 0
+    bh.free()
