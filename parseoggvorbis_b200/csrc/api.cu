@@ -188,7 +188,7 @@ static void serialize_setup(const pov_setup* s, std::string& out) {
 static bool build_fast_tables(const pov_setup* s, const std::vector<DevFloor>& floors, const std::vector<DevMapping>& maps,
                               const uint32_t posts_cls[2], FastTables& ft, uint32_t& short_cap) {
 	memset(&ft, 0, sizeof ft);
-	if(s->blocksize[0] != 256 || s->blocksize[1] != 2048) return false;
+	if(!warp_kernel_supports(s->blocksize[0], s->blocksize[1])) return false;
 	if(s->channels > POV_MAX_CHANNELS || s->n_floors > POV_FAST_MAX_FLOORS || s->n_mappings > POV_FAST_MAX_MAPPINGS) return false;
 	if(posts_cls[0] > 32 || posts_cls[1] > 32) return false;
 	short_cap = (posts_cls[0] + 3u) & ~3u;
@@ -248,7 +248,7 @@ static bool build_fast_tables(const pov_setup* s, const std::vector<DevFloor>& f
 		}
 	}
 	for(uint32_t i = 0; i < s->n_modes; ++i) { ft.mode_flag[i] = s->modes[i].blockflag ? 1 : 0; ft.mode_map[i] = s->modes[i].mapping; }
-	return warp_kernel_smem_bytes(short_cap, nullptr, nullptr, nullptr) <= 227 * 1024;
+	return warp_kernel_smem_bytes(s->blocksize[0], s->blocksize[1], short_cap, nullptr, nullptr, nullptr) <= 227 * 1024;
 }
 
 extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id_out) {
@@ -712,8 +712,9 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
 	if(h->warp_ok) {
 		for(const WarpGroup& g : h->warp_groups) {      // one persistent launch per setup (its tables live in shared memory)
 			const SetupRec& su = ctx->setups[g.setup];
-			CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr + g.first_run, g.n_runs, su.channels, su.d_fast, su.fast_short_cap,
-			                          su.dev.slope, su.dev.rot, su.dev.fft8, ctx->d_counter, ctx->sm_count, ctx->stream, &ctx->launches));
+			CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr + g.first_run, g.n_runs, su.channels, su.d_fast, su.blocksize[0], su.blocksize[1],
+			                          su.fast_short_cap, su.dev.slope, su.dev.rot, su.dev.fft8, su.dev.fftp, ctx->d_counter, ctx->sm_count, ctx->stream,
+			                          &ctx->launches));
 		}
 		return POV_OK;
 	}

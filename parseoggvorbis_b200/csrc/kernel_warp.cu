@@ -59,24 +59,32 @@ struct Params {
 	const float* slope[2];
 	const float2* rot[2];
 	const float2* tw8[2];
+	const float2* fp[2];         // twiddles of the first radix-2 / radix-4 pass (block sizes 512 and 1024)
 	uint32_t group_short;        // short packets per step (<= 8)
 	uint32_t curve_bytes;        // per-warp curve area
 	uint32_t short_curve_stride; // bytes of one short-block curve block
 };
 
-// ---- shared memory map (bytes) -----------------------------------------------------------------------------------
-constexpr int kOffTabs   = 0;
-constexpr int kOffInvDb  = kOffTabs + (int) sizeof(FastTables);
-constexpr int kOffSlope0 = kOffInvDb + 1024 + 16;                   // invdb[256] = 0.0f (curve of a channel multiplied by zero)
-constexpr int kOffSlope1 = kOffSlope0 + 128 * 4;
-constexpr int kOffTw1    = kOffSlope1 + 1024 * 4;
-constexpr int kOffTw0    = kOffTw1 + 288 * 8;
-constexpr int kOffRot1   = kOffTw0 + 32 * 8;
-constexpr int kOffRot0   = kOffRot1 + 512 * 8;
-constexpr int kOffRecip  = kOffRot0 + 64 * 8;                       // ceil(2^32 / d), d <= POV_FAST_MAX_X
-constexpr int kOffBar    = kOffRecip + (POV_FAST_MAX_X + 4) * 4;
-constexpr int kOffWarps  = kOffBar + 16;
-static_assert(kOffWarps % 16 == 0, "warp areas must stay 16-byte aligned");
+// ---- shared memory map (bytes), per pair of FFT sizes Q0 = blocksize0/4, Q1 = blocksize1/4 in {64, 128, 256, 512} ------
+__host__ __device__ constexpr int tw8_count(int Q) { return Q == 512 ? 288 : 32; }      // float2 of make_fft_r8_tables: Q = 512 has the L = 512 and L = 64 passes
+__host__ __device__ constexpr int fp_count(int Q) { return (Q == 128 || Q == 256) ? Q : 0; }   // first radix-2 / radix-4 pass (make_fft_pass_tables)
+template <int Q0, int Q1> struct Map {
+	static constexpr int kOffTabs   = 0;
+	static constexpr int kOffInvDb  = kOffTabs + (int) sizeof(FastTables);
+	static constexpr int kOffSlope0 = kOffInvDb + 1024 + 16;               // invdb[256] = 0.0f (curve of a channel multiplied by zero)
+	static constexpr int kOffSlope1 = kOffSlope0 + 2 * Q0 * 4;
+	static constexpr int kOffTw1    = kOffSlope1 + 2 * Q1 * 4;
+	static constexpr int kOffTw0    = kOffTw1 + tw8_count(Q1) * 8;
+	static constexpr int kOffRot1   = kOffTw0 + tw8_count(Q0) * 8;
+	static constexpr int kOffRot0   = kOffRot1 + Q1 * 8;
+	static constexpr int kOffFp1    = kOffRot0 + Q0 * 8;
+	static constexpr int kOffFp0    = kOffFp1 + fp_count(Q1) * 8;
+	static constexpr int kOffRecip  = kOffFp0 + fp_count(Q0) * 8;           // ceil(2^32 / d), d <= POV_FAST_MAX_X
+	static constexpr int kOffBar    = kOffRecip + (POV_FAST_MAX_X + 4) * 4;
+	static constexpr int kOffWarps  = kOffBar + 16;
+	static_assert(kOffWarps % 16 == 0, "warp areas must stay 16-byte aligned");
+};
+constexpr int kOffInvDb = (int) sizeof(FastTables);    // the same for every geometry
 constexpr int kFsStride = 36;           // per packet: final Y of every post in ascending-x order (uint8 x 32) + step2 mask (uint32)
 constexpr int kWorkBytes = 3 * kSlotF2 * 8;
 constexpr int kWarpFixedBytes = kWorkBytes + kPktCap * (int) sizeof(WPkt) + kPktCap * kFsStride;
@@ -149,7 +157,7 @@ __device__ __forceinline__ float uncouple_ang(float m, float a) {
 // scratch: [32 posts][32 lanes] uint16, aliasing the (idle) FFT work regions.
 __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, const WPkt* __restrict__ wp, const pov_packet* __restrict__ pk0, int run_n, int ch,
                                         const uint16_t* __restrict__ ys, uint16_t* __restrict__ scratch, unsigned char* __restrict__ fs,
-                                        uint32_t* __restrict__ status, int lane) {
+                                        uint32_t* __restrict__ status, uint32_t n0, uint32_t n1, int lane) {
 	const bool have = lane < run_n;
 	const uint32_t meta = have ? wp[lane].meta : 0u;
 	const uint32_t mode = meta & 0xffu, used = meta >> 16;
@@ -194,7 +202,7 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 	}
 	// ascending-x order, step2 mask, and hpp:587 CHECK(floor[i] < 256) over the n bins the reference renders: segments are
 	// monotone, so the maxima are at rendered end points; a segment cut by bin n-1 needs y(n-1)
-	const uint32_t n = tb->mode_flag[mode] ? 2048u : 256u;
+	const uint32_t n = tb->mode_flag[mode] ? n1 : n0;
 	const uint32_t mult = F->multiplier;
 	uint32_t smask = 0u, xp = 0u, ypv = 0u;
 	bool havep = false;
@@ -410,6 +418,65 @@ __device__ __forceinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin,
 	__syncwarp();
 }
 
+// First pass of a Q = R*64 point FFT with R = 2 or 4 (block sizes 512 and 1024): radix-R DIF over the stride-64 index,
+// x[j + 64 r] -> sub-FFT r' at T + 72 r' + j, twiddled by W_Q^(j r') (table: R factors per j, make_fft_pass_tables).
+// Lane u of the Q/16 lanes of the FFT handles j = u + (Q/16) i, i < 1024/Q... i.e. 16/R butterflies of R points.
+template <int R>
+__device__ __forceinline__ void first_pass_small(uint32_t Tf_, uint32_t fp_, int u) {
+	constexpr int LPF = 4 * R, NB = 16 / R;
+	float2* T = sptr<float2>(Tf_);
+	const float2* fp = sptr<const float2>(fp_);
+	float2 x[NB][R];
+#pragma unroll
+	for(int i = 0; i < NB; ++i)
+#pragma unroll
+		for(int r = 0; r < R; ++r) x[i][r] = T[u + LPF * i + 64 * r];
+	__syncwarp();
+#pragma unroll
+	for(int i = 0; i < NB; ++i) {
+		const int j = u + LPF * i;
+		if(R == 2) {
+			dft2(x[i][0], x[i][1]);
+			x[i][1] = cmul(x[i][1], fp[2 * j + 1]);
+		} else {
+			dft4(x[i][0], x[i][1], x[i][2], x[i][3]);
+			const float4 w01 = *reinterpret_cast<const float4*>(fp + 4 * j), w23 = *reinterpret_cast<const float4*>(fp + 4 * j + 2);
+			x[i][1] = cmul(x[i][1], make_float2(w01.z, w01.w));
+			x[i][2] = cmul(x[i][2], make_float2(w23.x, w23.y));
+			x[i][3] = cmul(x[i][3], make_float2(w23.z, w23.w));
+		}
+#pragma unroll
+		for(int r = 0; r < R; ++r) T[72 * r + j] = x[i][r];
+	}
+	__syncwarp();
+}
+
+// All FFT passes of one step for block class Q (compile time): natural-order points at Tf -> D halves at lo / hi.
+//   Q = 64:            r8 over j1                    -> A1[k0*9 + j0]              -> last pass (J = 8)
+//   Q = 128, 256:      radix-R first pass (R = Q/64) -> R sub-FFTs at T + 72 r'
+//                      r8 over j1 inside each        -> A2[j0*(J+2) + r' + R k1]   -> last pass (J = 8R)
+//   Q = 512:           r8 over j2 (R = 8)            -> A1[k0*72 + j], then as above
+// f = FFT index inside the warp (0 for Q = 512), u = lane inside the FFT, tw / fp / rot = shared-window table addresses.
+template <int Q>
+__device__ __forceinline__ void fft_passes(uint32_t Tfs, int u, uint32_t tws, uint32_t fps, uint32_t rots, uint32_t lo, uint32_t hi) {
+	constexpr int R = Q / 64, J = Q / 8;
+	const uint32_t uu = (uint32_t) u, u2 = (uint32_t) J - 1u - uu;
+	if constexpr(R == 1) {
+		r8_pass(Tfs + uu * 8, Tfs + u2 * 8, 8, tws + uu * 16, tws + u2 * 16, 16, Tfs + uu * 8, Tfs + u2 * 8, 9);
+		last_pass(Tfs + uu * 72, Tfs + u2 * 72, 1, rots + uu * 8, rots + u2 * 8, J, lo + uu * 8, lo + u2 * 8, hi + uu * 8, hi + u2 * 8);
+	} else {
+		constexpr int S2 = J + 2;
+		if constexpr(R == 8) r8_pass(Tfs + uu * 8, Tfs + u2 * 8, 64, tws + uu * 16, tws + u2 * 16, 128, Tfs + uu * 8, Tfs + u2 * 8, 72);
+		else first_pass_small<R>(Tfs, fps, u);
+		// pass over j1 inside the sub-FFTs: lane owns (r' = u/8, j0 = u%8) and (r' + R/2, j0); its twiddles are the L = 64 pass
+		constexpr uint32_t kTw64 = (R == 8) ? 256u : 0u;
+		const uint32_t j0 = uu & 7u, rp = uu >> 3;
+		r8_pass(Tfs + (rp * 72 + j0) * 8, Tfs + ((rp + R / 2) * 72 + j0) * 8, 8, tws + (kTw64 + j0 * 2) * 8, tws + (kTw64 + j0 * 2) * 8, 16,
+		        Tfs + (j0 * S2 + rp) * 8, Tfs + (j0 * S2 + rp + R / 2) * 8, R);
+		last_pass(Tfs + uu * 8, Tfs + u2 * 8, S2, rots + uu * 8, rots + u2 * 8, J, lo + uu * 8, lo + u2 * 8, hi + uu * 8, hi + u2 * 8);
+	}
+}
+
 // Spectral stage of the FFT this lane belongs to: nonzero propagate + inverse coupling + floor multiply + DCT-IV
 // pre-rotation. Lane u handles points u + J*m and their mirrors Q-1-(u + J*m), m = 0..7: the bins (2j, 2j+1) and
 // (M-2-2j, M-1-2j) arrive with two 64-bit loads per channel and feed both points.
@@ -533,15 +600,17 @@ __device__ __forceinline__ float ola_one(const OlaGeom& G, const float* __restri
 
 // Long block after a long block, both slopes long: every sample has both terms and both windows. Lane produces
 // out[j..j+3] and out[1020-j..1023-j] (j < 512) from the same four vectors (TDAC symmetry of both frames and windows).
+template <int Q>
 __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, const float* __restrict__ chi, const float* __restrict__ sl,
                                               float* __restrict__ dst, int lane) {
+	// n = 4Q: the chunk has 2Q samples, half of them (Q) below the centre; 8 samples per lane and iteration
 #pragma unroll
-	for(int i = 0; i < 4; ++i) {
+	for(int i = 0; i < Q / 128; ++i) {
 		const int j = 4 * lane + 128 * i;
-		const float4 p = *reinterpret_cast<const float4*>(plo + 508 - j);
+		const float4 p = *reinterpret_cast<const float4*>(plo + (Q - 4) - j);
 		const float4 c = *reinterpret_cast<const float4*>(chi + j);
 		const float4 wa = *reinterpret_cast<const float4*>(sl + j);
-		const float4 wb = *reinterpret_cast<const float4*>(sl + 1020 - j);
+		const float4 wb = *reinterpret_cast<const float4*>(sl + (2 * Q - 4) - j);
 		float4 o1, o2;
 		o1.x = __fadd_rn(__fmul_rn(-p.w, wb.w), __fmul_rn(c.x, wa.x));
 		o1.y = __fadd_rn(__fmul_rn(-p.z, wb.z), __fmul_rn(c.y, wa.y));
@@ -552,7 +621,7 @@ __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, con
 		o2.z = __fadd_rn(__fmul_rn(-p.z, wa.y), __fmul_rn(-c.y, wb.z));
 		o2.w = __fadd_rn(__fmul_rn(-p.w, wa.x), __fmul_rn(-c.x, wb.w));
 		__stcs(reinterpret_cast<float4*>(dst + j), o1);
-		__stcs(reinterpret_cast<float4*>(dst + 1020 - j), o2);
+		__stcs(reinterpret_cast<float4*>(dst + (2 * Q - 4) - j), o2);
 	}
 }
 
@@ -569,17 +638,21 @@ __device__ __forceinline__ int curve_mode(const FastTables* tb, uint32_t mapping
 	return ((prop >> c) & 1u) ? 2 : 1;
 }
 
+template <int Q0, int Q1>
 __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
+	using M = Map<Q0, Q1>;
+	constexpr int N0 = 4 * Q0, N1 = 4 * Q1;              // block sizes
+	constexpr int LPF0 = Q0 / 16, LPF1 = Q1 / 16;        // lanes per FFT
 	unsigned char* const smem = g_smem;
-	const FastTables* tb = reinterpret_cast<const FastTables*>(smem + kOffTabs);
-	const float* s_slope0 = reinterpret_cast<const float*>(smem + kOffSlope0);
-	const float* s_slope1 = reinterpret_cast<const float*>(smem + kOffSlope1);
-	const float2* s_tw1 = reinterpret_cast<const float2*>(smem + kOffTw1);      // 2048: pass L=512 (256 float2) | pass L=64 (32)
-	const float2* s_tw0 = reinterpret_cast<const float2*>(smem + kOffTw0);      // 256:  pass L=64 (32 float2)
-	const float2* s_rot1 = reinterpret_cast<const float2*>(smem + kOffRot1);
-	const float2* s_rot0 = reinterpret_cast<const float2*>(smem + kOffRot0);
-	uint32_t* s_recip = reinterpret_cast<uint32_t*>(smem + kOffRecip);
-	uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+	const FastTables* tb = reinterpret_cast<const FastTables*>(smem + M::kOffTabs);
+	const float* s_slope0 = reinterpret_cast<const float*>(smem + M::kOffSlope0);
+	const float* s_slope1 = reinterpret_cast<const float*>(smem + M::kOffSlope1);
+	const float2* s_tw1 = reinterpret_cast<const float2*>(smem + M::kOffTw1);
+	const float2* s_tw0 = reinterpret_cast<const float2*>(smem + M::kOffTw0);
+	const float2* s_rot1 = reinterpret_cast<const float2*>(smem + M::kOffRot1);
+	const float2* s_rot0 = reinterpret_cast<const float2*>(smem + M::kOffRot0);
+	uint32_t* s_recip = reinterpret_cast<uint32_t*>(smem + M::kOffRecip);
+	uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + M::kOffBar);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const DevBatchView& b = P.b;
@@ -588,18 +661,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	if(threadIdx.x == 0) {
 		mbar_init(s_bar, 1);
 		mbar_fence_init();
-		const uint32_t total = (uint32_t) sizeof(FastTables) + 1024u + 128u * 4u + 1024u * 4u + 288u * 8u + 32u * 8u + 512u * 8u + 64u * 8u;
+		constexpr uint32_t total = (uint32_t) sizeof(FastTables) + 1024u + 2u * Q0 * 4u + 2u * Q1 * 4u + tw8_count(Q1) * 8u + tw8_count(Q0) * 8u +
+		                           Q1 * 8u + Q0 * 8u + fp_count(Q1) * 8u + fp_count(Q0) * 8u;
 		mbar_expect_tx(s_bar, total);
-		tma_bulk_g2s(smem + kOffTabs, P.tabs, (uint32_t) sizeof(FastTables), s_bar);
-		tma_bulk_g2s(smem + kOffInvDb, b.inv_db, 1024u, s_bar);
-		tma_bulk_g2s(smem + kOffSlope0, P.slope[0], 128u * 4u, s_bar);
-		tma_bulk_g2s(smem + kOffSlope1, P.slope[1], 1024u * 4u, s_bar);
-		tma_bulk_g2s(smem + kOffTw1, P.tw8[1], 288u * 8u, s_bar);
-		tma_bulk_g2s(smem + kOffTw0, P.tw8[0], 32u * 8u, s_bar);
-		tma_bulk_g2s(smem + kOffRot1, P.rot[1], 512u * 8u, s_bar);
-		tma_bulk_g2s(smem + kOffRot0, P.rot[0], 64u * 8u, s_bar);
+		tma_bulk_g2s(smem + M::kOffTabs, P.tabs, (uint32_t) sizeof(FastTables), s_bar);
+		tma_bulk_g2s(smem + M::kOffInvDb, b.inv_db, 1024u, s_bar);
+		tma_bulk_g2s(smem + M::kOffSlope0, P.slope[0], 2u * Q0 * 4u, s_bar);
+		tma_bulk_g2s(smem + M::kOffSlope1, P.slope[1], 2u * Q1 * 4u, s_bar);
+		tma_bulk_g2s(smem + M::kOffTw1, P.tw8[1], tw8_count(Q1) * 8u, s_bar);
+		tma_bulk_g2s(smem + M::kOffTw0, P.tw8[0], tw8_count(Q0) * 8u, s_bar);
+		tma_bulk_g2s(smem + M::kOffRot1, P.rot[1], Q1 * 8u, s_bar);
+		tma_bulk_g2s(smem + M::kOffRot0, P.rot[0], Q0 * 8u, s_bar);
+		if(fp_count(Q1)) tma_bulk_g2s(smem + M::kOffFp1, P.fp[1], fp_count(Q1) * 8u, s_bar);
+		if(fp_count(Q0)) tma_bulk_g2s(smem + M::kOffFp0, P.fp[0], fp_count(Q0) * 8u, s_bar);
 	}
-	if(threadIdx.x < 4) reinterpret_cast<float*>(smem + kOffInvDb + 1024)[threadIdx.x] = 0.f;
+	if(threadIdx.x < 4) reinterpret_cast<float*>(smem + M::kOffInvDb + 1024)[threadIdx.x] = 0.f;
 	for(uint32_t d = threadIdx.x; d <= POV_FAST_MAX_X; d += kThreads)
 		s_recip[d] = (d < 2) ? 0xFFFFFFFFu : (uint32_t) ((0x100000000ull + d - 1) / d);
 	__syncthreads();
@@ -607,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 
 	// ---- warp-private areas ----
 	const uint32_t warp_bytes = (uint32_t) kWarpFixedBytes + P.curve_bytes;
-	unsigned char* wbase = smem + kOffWarps + (size_t) warp * warp_bytes;
+	unsigned char* wbase = smem + M::kOffWarps + (size_t) warp * warp_bytes;
 	float2* slotA = reinterpret_cast<float2*>(wbase);        // work area: three half regions A | B | C (see kSlotF2)
 	WPkt* wp = reinterpret_cast<WPkt*>(wbase + kWorkBytes);
 	unsigned char* fs = wbase + kWorkBytes + kPktCap * (int) sizeof(WPkt);
@@ -641,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 		const float* spec_base = b.spectra + spec0;
 		const uint64_t frame0 = pcm0;           // stream frame index of the run's first packet chunk
 		__syncwarp();
-		unwrap_run(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, lane);
+		unwrap_run(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, (uint32_t) N0, (uint32_t) N1, lane);
 
 		int prev_valid = 0, prev_n = 0, prev_right = 0;
 		const float* prev_lo = nullptr;
@@ -664,69 +740,63 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			if(first + count < run_n) {
 				const WPkt& nw = wp[first + count];
 				const uint32_t nmode = nw.meta & 0xffu;
-				const uint32_t nhalf = tb->mode_flag[nmode] ? 1024u : 128u;
+				const uint32_t nhalf = tb->mode_flag[nmode] ? 2u * Q1 : 2u * Q0;
 				const FastCouple* ncp = &tb->couple[tb->mode_map[nmode]][ch];
 				if(lane < (int) ncp->nl) prefetch_l2_bulk(spec_base + nw.spec_rel + (int) (ncp->ch[lane] * nhalf), nhalf * 4u);
 			}
-			// ================= one long packet (the whole warp is one 512-point FFT) or up to 8 short packets (four lanes
-			//                   per 64-point FFT): same code, geometry in registers =================
-			const int Qs = flag ? 512 : 64, Js = Qs >> 3;
-			const int lshift = flag ? 5 : 2;                      // log2(lanes per FFT) = log2(Q / 16)
-			const int f = lane >> lshift, u = lane & ((1 << lshift) - 1);
-			const uint32_t cstride = flag ? 0u : P.short_curve_stride, rcap = flag ? 32u : tb->short_posts_cap, nwords = flag ? 32u : 4u;
+			// ================= one long packet or a group of short packets: Q/16 lanes per FFT, same code for both classes,
+			//                   geometry in registers (256/2048: the whole warp is one 512-point FFT, or eight 64-point FFTs) ====
+			const int Qs = flag ? Q1 : Q0;
+			const int lpf = flag ? LPF1 : LPF0;
+			// lpf is a power of two. A long step holds ONE FFT: with fewer than 32 lanes per FFT the other lanes mirror it
+			// (same addresses, same values) instead of idling, so that every lane reaches the warp barriers of the passes
+			const int u = lane & (lpf - 1);
+			const int f = flag ? 0 : lane / lpf;
+			const uint32_t cstride = flag ? 0u : P.short_curve_stride, rcap = flag ? 32u : tb->short_posts_cap, nwords = (uint32_t) Qs / 16u;
 			for(int g = 0; g < count; ++g) {
 				const int md = curve_mode(tb, mapping, wp[first + g].meta >> 16, ch);
 				unsigned char* cv = curves + (size_t) g * cstride;
 				if(md == 0) build_records(F, fs + (first + g) * kFsStride, cv, rcap, nwords, s_recip, lane);
 				else flat_curve(cv, rcap, nwords, md == 1 ? 255u : 256u, lane);
 			}
-			const uint32_t Ts = smem_u32(T), Tfs = Ts + (uint32_t) f * (72u * 8u);
+			// FFT buffer of FFT f: Q/64 sub-FFT rows of 72 slots (one row for Q = 64)
+			const uint32_t Ts = smem_u32(T), Tfs = Ts + (uint32_t) f * (uint32_t) ((Qs >> 6) * 72 * 8);
 			const uint32_t rots = smem_u32(flag ? s_rot1 : s_rot0), tws = smem_u32(flag ? s_tw1 : s_tw0);
 			if(f < count)
 				spectral_dispatch(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u);
 			__syncwarp();
-			{
-				const uint32_t uu = (uint32_t) u, u2 = (uint32_t) Js - 1u - uu;
-				// pass 1: natural order -> A1 (stride 72 for Q = 512, 9 for Q = 64)
-				r8_pass(Tfs + uu * 8, Tfs + u2 * 8, Js, tws + uu * 16, tws + u2 * 16, 2 * Js, Tfs + uu * 8, Tfs + u2 * 8, flag ? 72 : 9);
-				if(flag) {
-					const uint32_t j0 = uu & 7u, k0 = uu >> 3;    // pass 2 of the 512-point FFT: A1 -> A2
-					r8_pass(Ts + (k0 * 72 + j0) * 8, Ts + ((k0 + 4) * 72 + j0) * 8, 8, tws + (256 + j0 * 2) * 8, tws + (256 + j0 * 2) * 8, 16,
-					        Ts + (j0 * 66 + k0) * 8, Ts + (j0 * 66 + k0 + 4) * 8, 8);
-				}
-				// last pass + post-rotation -> D (float2[Q] per FFT, packed back to back)
-				// long: lo half -> survivor slot, hi half -> slot B; short: D of FFT f packed at T + 64 f (lo | hi)
-				const uint32_t ia = flag ? uu * 8u : uu * 72u, ib = flag ? u2 * 8u : u2 * 72u;
-				const uint32_t lo = flag ? smem_u32(surv) : Ts + (uint32_t) f * (64u * 8u);
-				const uint32_t hi = flag ? smem_u32(slotB) : lo + 32u * 8u;
-				last_pass(Tfs + ia, Tfs + ib, flag ? 66 : 1, rots + uu * 8, rots + u2 * 8, Js, lo + uu * 8, lo + u2 * 8, hi + uu * 8, hi + u2 * 8);
+			// last pass output: long: lo half -> survivor slot, hi half -> slot B; short: D of FFT f packed at T + Q0 f (lo | hi)
+			if(flag) fft_passes<Q1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB));
+			else {
+				const uint32_t lo = Ts + (uint32_t) f * (uint32_t) (Q0 * 8);
+				fft_passes<Q0>(Tfs, u, tws, smem_u32(smem + M::kOffFp0), rots, lo, lo + (uint32_t) (Q0 / 2 * 8));
 			}
 
 			// ================= window + overlap-add + emit (hpp:1008-1059 in gather form) =================
-			const int n = flag ? 2048 : 256, Q = n / 4;
+			const int n = flag ? N1 : N0, Q = n / 4;
 			const float* Dstep = reinterpret_cast<const float*>(T);
 			const uint64_t chan0 = st.pcm_base + (uint64_t) ch * st.pcm_frames + frame0;
 			for(int g = 0; g < count; ++g) {
 				const WPkt& w = wp[first + g];
 				const uint32_t wflags = (w.meta >> 8) & 0xffu, emit = w.emit;
 				// hpp:844-847: short blocks always use blocksize0 slopes; long blocks follow their own prev/next flags
-				const int lc = (flag && (wflags & 1u)) ? 1024 : 128;
-				const int rc = (flag && (wflags & 2u)) ? 1024 : 128;
+				const int lc = (flag && (wflags & 1u)) ? N1 / 2 : N0 / 2;
+				const int rc = (flag && (wflags & 2u)) ? N1 / 2 : N0 / 2;
 				const float* cur_lo = flag ? reinterpret_cast<const float*>(surv) : Dstep + (size_t) g * 2 * Q;
 				const float* cur_hi = flag ? reinterpret_cast<const float*>(slotB) : cur_lo + Q;
 				const bool emits = prev_valid && emit > 0 && (run.first_packet + (uint32_t) (first + g)) != st.first_packet;
 				if(emits) {
 					const uint64_t chan_base = chan0 + w.pcm_rel;
-					if(planar && flag && prev_n == 2048 && lc == 1024 && prev_right == 1024 && emit == 1024u && (chan_base & 3ull) == 0) {
-						ola_long_long(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, lane);
+					if(planar && flag && prev_n == N1 && lc == N1 / 2 && prev_right == N1 / 2 && emit == (uint32_t) (N1 / 2) && (chan_base & 3ull) == 0) {
+						ola_long_long<Q1>(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, lane);
 					} else {
 						OlaGeom G;
 						G.Hp = prev_n / 4; G.H = Q;
 						G.shift = Q - prev_n / 4;
 						G.lc = lc; G.lb = Q - lc / 2;
 						G.pr = prev_right; G.rbp = prev_n / 4 - prev_right / 2;
-						G.slL = (lc == 1024) ? s_slope1 : s_slope0;
-						G.slR = (prev_right == 1024) ? s_slope1 : s_slope0;
+						G.slL = (lc == N1 / 2) ? s_slope1 : s_slope0;
+						G.slR = (prev_right == N1 / 2) ? s_slope1 : s_slope0;
 						for(uint32_t j = (uint32_t) lane; j < emit; j += 32u) {
 							const float v = ola_one(G, prev_lo, cur_hi, (int) j);
 							const uint64_t fidx = frame0 + w.pcm_rel + j;
@@ -738,11 +808,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				prev_valid = 1; prev_n = n; prev_right = rc; prev_lo = cur_lo;
 			}
 			if(!flag && prev_lo != reinterpret_cast<const float*>(surv)) {
-				// short step: move the last packet's D lo half (32 float2) into the survivor slot
+				// short step: move the last packet's D lo half (Q0/2 float2) into the survivor slot (ranges may overlap:
+				// every lane reads all of its elements before anyone writes)
+				constexpr int kPer = (Q0 / 2 + 31) / 32;
+				float2 v[kPer];
 				__syncwarp();
-				const float2 v = reinterpret_cast<const float2*>(prev_lo)[lane];
+#pragma unroll
+				for(int i = 0; i < kPer; ++i) v[i] = reinterpret_cast<const float2*>(prev_lo)[lane + 32 * i];
 				__syncwarp();
-				surv[lane] = v;
+#pragma unroll
+				for(int i = 0; i < kPer; ++i) surv[lane + 32 * i] = v[i];
 				__syncwarp();
 				prev_lo = reinterpret_cast<const float*>(surv);
 			}
@@ -754,43 +829,80 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 
 }  // namespace wk
 
-size_t warp_kernel_smem_bytes(uint32_t short_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out, uint32_t* short_stride_out) {
-	const uint32_t stride = short_posts_cap * 8u + 32u;        // records + 4 rank-table words
-	uint32_t group = 8;
-	uint32_t cb = 32u * 8u + 32u * 8u;                    // one long curve: 32 records + 32 rank-table words
+// ---- host side: geometry selection, shared-memory budget, launch -----------------------------------------------------
+static bool supported_block(uint32_t n) { return n == 256 || n == 512 || n == 1024 || n == 2048; }
+
+bool warp_kernel_supports(uint32_t bs0, uint32_t bs1) {
+	// instantiated pairs (Vorbis encoders use 256/2048 at 44.1-48 kHz, 512/1024 or 256/1024 at 16-22 kHz, 256/512 at 8 kHz)
+	if(!supported_block(bs0) || !supported_block(bs1) || bs0 >= bs1) return false;
+	return true;
+}
+
+template <int Q0, int Q1> static size_t smem_for(uint32_t cb) {
+	return (size_t) wk::Map<Q0, Q1>::kOffWarps + (size_t) wk::kWarps * ((size_t) wk::kWarpFixedBytes + cb);
+}
+
+size_t warp_kernel_smem_bytes(uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out,
+                              uint32_t* short_stride_out) {
+	const uint32_t Q0 = bs0 / 4, Q1 = bs1 / 4;
+	const uint32_t stride = short_posts_cap * 8u + (Q0 / 16u) * 8u;       // records + rank-table words of one short curve
+	uint32_t group = 512u / Q0;                                           // short FFTs a warp transforms at once (Q0/16 lanes each)
+	uint32_t cb = 32u * 8u + (Q1 / 16u) * 8u;                             // one long curve: 32 records + rank table
 	while(group > 1 && group * stride > wk::kCurveMax) --group;
 	if(group * stride > cb) cb = group * stride;
 	cb = (cb + 15u) & ~15u;
 	if(group_short_out) *group_short_out = group;
 	if(curve_bytes_out) *curve_bytes_out = cb;
 	if(short_stride_out) *short_stride_out = stride;
-	return (size_t) wk::kOffWarps + (size_t) wk::kWarps * ((size_t) wk::kWarpFixedBytes + cb);
+	switch(Q0 * 1024u + Q1) {
+		case 64u * 1024u + 128u:  return smem_for<64, 128>(cb);
+		case 64u * 1024u + 256u:  return smem_for<64, 256>(cb);
+		case 64u * 1024u + 512u:  return smem_for<64, 512>(cb);
+		case 128u * 1024u + 256u: return smem_for<128, 256>(cb);
+		case 128u * 1024u + 512u: return smem_for<128, 512>(cb);
+		case 256u * 1024u + 512u: return smem_for<256, 512>(cb);
+		default: return (size_t) 1 << 30;
+	}
 }
 
 uint32_t warp_kernel_max_run(void) { return (uint32_t) wk::kPktCap - 1u; }
 uint32_t warp_kernel_warps(void) { return (uint32_t) wk::kWarps; }
 
+template <int Q0, int Q1>
+static cudaError_t launch_geom(const wk::Params& P, uint32_t grid, size_t smem, cudaStream_t st) {
+	cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if(e != cudaSuccess) return e;
+	wk::k_warp_synth<Q0, Q1><<<grid, wk::kThreads, smem, st>>>(P);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
-                        uint32_t short_posts_cap, const float* const slope[2], const float2* const rot[2], const float2* const tw8[2],
-                        uint32_t* d_counter, int sm_count, cudaStream_t st, uint64_t* launches) {
+                        uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, const float* const slope[2], const float2* const rot[2],
+                        const float2* const tw8[2], const float2* const fp[2], uint32_t* d_counter, int sm_count, cudaStream_t st,
+                        uint64_t* launches) {
 	if(n_runs == 0) return cudaSuccess;
 	wk::Params P;
 	P.b = b; P.runs = runs; P.n_runs = n_runs; P.C = channels; P.n_items = n_runs * channels;
 	P.counter = d_counter; P.tabs = d_tabs;
-	for(int k = 0; k < 2; ++k) { P.slope[k] = slope[k]; P.rot[k] = rot[k]; P.tw8[k] = tw8[k]; }
-	const size_t smem = warp_kernel_smem_bytes(short_posts_cap, &P.group_short, &P.curve_bytes, &P.short_curve_stride);
+	for(int k = 0; k < 2; ++k) { P.slope[k] = slope[k]; P.rot[k] = rot[k]; P.tw8[k] = tw8[k]; P.fp[k] = fp[k]; }
+	const size_t smem = warp_kernel_smem_bytes(bs0, bs1, short_posts_cap, &P.group_short, &P.curve_bytes, &P.short_curve_stride);
 	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-	cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st);
 	if(e != cudaSuccess) return e;
-	e = cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st);
-	if(e != cudaSuccess) return e;
-	const uint32_t items = P.n_items;
 	uint32_t grid = (uint32_t) sm_count;
-	const uint32_t need = (items + wk::kWarps - 1) / wk::kWarps;
+	const uint32_t need = (P.n_items + wk::kWarps - 1) / wk::kWarps;
 	if(grid > need) grid = need;
-	wk::k_warp_synth<<<grid, wk::kThreads, smem, st>>>(P);
+	switch((bs0 / 4) * 1024u + bs1 / 4) {
+		case 64u * 1024u + 128u:  e = launch_geom<64, 128>(P, grid, smem, st); break;
+		case 64u * 1024u + 256u:  e = launch_geom<64, 256>(P, grid, smem, st); break;
+		case 64u * 1024u + 512u:  e = launch_geom<64, 512>(P, grid, smem, st); break;
+		case 128u * 1024u + 256u: e = launch_geom<128, 256>(P, grid, smem, st); break;
+		case 128u * 1024u + 512u: e = launch_geom<128, 512>(P, grid, smem, st); break;
+		case 256u * 1024u + 512u: e = launch_geom<256, 512>(P, grid, smem, st); break;
+		default: return cudaErrorInvalidConfiguration;
+	}
 	if(launches) ++*launches;
-	return cudaGetLastError();
+	return e;
 }
 
 }  // namespace pov

@@ -43,12 +43,15 @@ cudaError_t launch_fused(const DevBatchView& b, const DevRun* runs, uint32_t n_r
 size_t fused_smem_bytes(uint32_t max_channels, uint32_t max_blocksize, uint32_t min_blocksize, const uint32_t floor_cap[2],
                         uint32_t table_float2);
 // Warp-autonomous persistent kernel (kernel_warp.cu): single-setup batches with blocksizes 256/2048.
-size_t warp_kernel_smem_bytes(uint32_t short_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out, uint32_t* short_stride_out);
+bool warp_kernel_supports(uint32_t bs0, uint32_t bs1);     // block size pairs the warp kernel is instantiated for
+size_t warp_kernel_smem_bytes(uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out,
+                              uint32_t* short_stride_out);
 uint32_t warp_kernel_max_run(void);   // packets per run without the halo
 uint32_t warp_kernel_warps(void);     // resident warps per SM
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
-                        uint32_t short_posts_cap, const float* const slope[2], const float2* const rot[2], const float2* const tw8[2],
-                        uint32_t* d_counter, int sm_count, cudaStream_t st, uint64_t* launches);
+                        uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, const float* const slope[2], const float2* const rot[2],
+                        const float2* const tw8[2], const float2* const fp[2], uint32_t* d_counter, int sm_count, cudaStream_t st,
+                        uint64_t* launches);
 cudaError_t launch_mdct_backward(const DevSetup* dummy, uint32_t n, uint64_t count, const float* in, float* out,
                                  const float2* rot, const float2* fft, cudaStream_t st, uint64_t* launches);
 

@@ -139,7 +139,7 @@ def test_config3_5_1_coupling_order(ctx):
     _check_against_oracle(ctx, setup, batch, stages=True)
 
 
-@pytest.mark.parametrize("bs", [(256, 2048), (512, 1024), (64, 8192), (128, 128), (1024, 4096)])
+@pytest.mark.parametrize("bs", [(256, 2048), (512, 1024), (64, 8192), (128, 128), (1024, 4096), (256, 512), (1024, 2048)])
 def test_config4_mono_clips_blocksizes(ctx, bs):
     setup, batch = workloads.config4(clips=12, packets_per_clip=40, blocksizes=bs)
     _check_against_oracle(ctx, setup, batch, stages=(bs == (512, 1024)))
@@ -340,3 +340,20 @@ def test_empty_batch_is_a_no_op(ctx):
     ctx.run(bh)
     assert ctx.fetch_pcm(bh).size == 0
     bh.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [(256, 512), (256, 1024), (256, 2048), (512, 1024), (512, 2048), (1024, 2048)])
+def test_warp_kernel_block_size_pairs_stereo(ctx, bs):
+    """Every block-size pair the persistent warp kernel is instantiated for (radix-2 / radix-4 first passes for 512 and
+    1024, several FFTs per warp for the smaller sizes): stereo with coupling, mixed blocks, trimmed last packet."""
+    rng = np.random.default_rng(bs[0] * 7 + bs[1])
+    setup = workloads.make_setup(2, bs, 22050, couplings=[(0, 1)])
+    plans = [workloads.plan_stream(workloads.block_sequence(220, rng, p_short=0.15), setup.blocksize, trim_last=int(rng.integers(0, 30)))
+             for _ in range(3)]
+    batch = workloads.build_dense_batch(setup, plans, rng, p_unused=0.05)
+    batch.streams["setup_id"] = ctx.register_setup(setup)
+    bh = ctx.upload(batch)
+    assert ctx.kernel_name(bh) == "k_warp_synth"
+    bh.free()
+    _check_against_oracle(ctx, setup, batch, stages=True)
