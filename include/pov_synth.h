@@ -205,8 +205,9 @@ typedef struct pov_batch_handle pov_batch_handle;
 int  pov_batch_upload(pov_ctx* ctx, const pov_batch* batch, pov_batch_handle** out);
 /* Launch the production path: [residue apply] -> fused floor1/coupling/dot/IMDCT/window/OLA -> PCM arena (device). */
 int  pov_batch_run(pov_ctx* ctx, pov_batch_handle* h);
-/* Name of the kernel pov_batch_run launches for this batch: "k_warp_synth" (persistent warp-autonomous kernel,
- * single-setup 256/2048 batches), "k_fused_synth" (one CTA per run, any blocksizes) or "staged". Static string. */
+/* Name of the kernel pov_batch_run launches for this batch: "k_warp_synth" (persistent warp-autonomous kernel: block
+ * sizes 256/512/1024/2048, <= 32 posts per floor), "k_fused_synth" (one CTA per run, any block sizes) or "staged".
+ * Static string. */
 const char* pov_batch_kernel_name(const pov_ctx* ctx, const pov_batch_handle* h);
 /* Launch the staged path instead: one kernel per reference stage, every intermediate materialised in HBM so
  * that pov_batch_fetch_stage can return it. Produces the same PCM. */
