@@ -243,7 +243,7 @@ __device__ __forceinline__ void build_records(const FastFloor* __restrict__ F, c
 	const bool have = lane < posts;
 	const uint32_t mask = *reinterpret_cast<const uint32_t*>(fsp + 32);
 	const uint32_t yb = fsp[lane];
-	const uint32_t x0 = F->post[lane][3] & 0xffffu;
+	const uint32_t x0 = F->xs_sorted[lane];
 	const bool f = have && ((mask >> lane) & 1u);
 	const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
 	const uint32_t y0 = min(yb * F->multiplier, 1023u);
