@@ -268,11 +268,44 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 	uint64_t total = 0;
 	double* d_sum = nullptr;
 	double h_sum = 0;
-	pov_batch_handle* h = nullptr;
-	float* pinned = nullptr;
-	size_t pinned_cap = 0;
-	if(cudaMalloc(&d_sum, sizeof(double)) != cudaSuccess || cudaMemsetAsync(d_sum, 0, sizeof(double), ctx->stream) != cudaSuccess)
-		rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaMalloc failed");
+	// Two batch slots: while the GPU transforms chunk i and copies its PCM and status words to pinned host memory, the
+	// calling thread assembles and validates chunk i+1. A slot is checked (status words) and reused two chunks later.
+	struct Slot {
+		pov_ctx* ctx = nullptr;                    // slot 0: the caller's context; slot 1: a sibling context (own stream), so
+		                                           // that the pageable uploads of one chunk never wait for the other chunk's work
+		double* d_sum = nullptr;
+		pov_batch_handle* h = nullptr;
+		float* pinned = nullptr; size_t pinned_cap = 0;
+		uint32_t* status = nullptr; size_t status_cap = 0;
+		cudaEvent_t done = nullptr;
+		uint32_t n_packets = 0, first_file = 0;
+		bool busy = false;
+	} slot[2];
+	slot[0].ctx = ctx;
+	{
+		const char* e = nullptr;
+		if(pov_ctx_create(ctx->device, &slot[1].ctx, &e) != POV_OK) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: %s", e ? e : "sibling context");
+	}
+	for(auto& sl : slot) {
+		if(rc) break;
+		if(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventCreate failed");
+		else if(cudaMalloc(&sl.d_sum, sizeof(double)) != cudaSuccess || cudaMemsetAsync(sl.d_sum, 0, sizeof(double), sl.ctx->stream) != cudaSuccess)
+			rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaMalloc failed");
+	}
+	(void) d_sum;
+	auto retire = [&](Slot& sl) -> int {           // wait for a slot's chunk and turn its status words into the reference's error
+		if(!sl.busy) return POV_OK;
+		sl.busy = false;
+		if(cudaEventSynchronize(sl.done) != cudaSuccess) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: chunk failed on the device");
+		for(uint32_t p = 0; p < sl.n_packets; ++p)
+			if(sl.status[p]) {
+				const char* what = (sl.status[p] & POV_PKT_FLOOR_PREDICTED) ? "predicted <= range (hpp:536)"
+				                 : (sl.status[p] & POV_PKT_FLOOR_RANGE)     ? "floor[i] < 256 (hpp:587)"
+				                                                            : "temp.size() > 0 (hpp:739,748: VQ entry out of range)";
+				return pov_fail(ctx, POV_ERR_STREAM, "chunk at file %u, audio packet %u: check failed: %s", sl.first_file, p, what);
+			}
+		return POV_OK;
+	};
 
 	for(uint32_t ci = 0; ci < n_chunks && rc == POV_OK; ++ci) {
 		std::unique_ptr<Chunk> ck;
@@ -290,43 +323,68 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 			for(const StreamWork& st : ck->files[i]) {
 				if(!st.have_setup) continue;
 				uint32_t id = 0;
-				rc = register_stream_setup(ctx, st, &id);
-				if(rc) break;
+				rc = register_stream_setup(slot[ci & 1].ctx, st, &id);
+				if(rc) { if(slot[ci & 1].ctx != ctx) pov_fail(ctx, rc, "%s", pov_last_error(slot[ci & 1].ctx)); break; }
 				hb.append(st, id);
 				frames += st.frames;
 			}
 			if(frames_out) frames_out[ck->first_file + i] = frames;
 		}
 		if(rc || hb.packets.empty()) continue;
+		Slot& sl = slot[ci & 1];
+		pov_ctx* cx = sl.ctx;
+		rc = retire(sl);                           // the chunk that used this slot two iterations ago
+		if(rc) break;
 		pov_batch b = hb.view();
-		rc = pov_batch_upload(ctx, &b, &h);
-		if(!rc) rc = pov_batch_run(ctx, h);
+		rc = pov_batch_upload(cx, &b, &sl.h);      // pageable sources: staged by the runtime before the call returns
+		if(!rc) rc = pov_batch_run(cx, sl.h);
+		if(rc && cx != ctx) pov_fail(ctx, rc, "%s", pov_last_error(cx));
 		if(!rc) {
 			const size_t need = hb.pcm_floats * sizeof(float);
-			if(need > pinned_cap) {
-				if(pinned) cudaFreeHost(pinned);
-				pinned = nullptr;
-				pinned_cap = need + need / 4;
-				if(cudaMallocHost((void**) &pinned, pinned_cap) != cudaSuccess) { rc = pov_fail(ctx, POV_ERR_CUDA, "cudaMallocHost failed"); break; }
+			if(need > sl.pinned_cap) {
+				if(sl.pinned) cudaFreeHost(sl.pinned);
+				sl.pinned = nullptr;
+				sl.pinned_cap = need + need / 4;
+				if(cudaMallocHost((void**) &sl.pinned, sl.pinned_cap) != cudaSuccess) { rc = pov_fail(ctx, POV_ERR_CUDA, "cudaMallocHost failed"); break; }
 			}
-			cudaError_t e = pov_checksum_launch((const float*) pov_batch_pcm_dev(h), hb.pcm_floats, d_sum, ctx->stream, &ctx->launches);
+			const size_t sneed = hb.packets.size() * sizeof(uint32_t);
+			if(sneed > sl.status_cap) {
+				if(sl.status) cudaFreeHost(sl.status);
+				sl.status = nullptr;
+				sl.status_cap = sneed + sneed / 4;
+				if(cudaMallocHost((void**) &sl.status, sl.status_cap) != cudaSuccess) { rc = pov_fail(ctx, POV_ERR_CUDA, "cudaMallocHost failed"); break; }
+			}
+			cudaError_t e = pov_checksum_launch((const float*) pov_batch_pcm_dev(sl.h), hb.pcm_floats, sl.d_sum, cx->stream, &cx->launches);
 			if(e != cudaSuccess) { rc = pov_fail(ctx, POV_ERR_CUDA, "checksum kernel: %s", cudaGetErrorString(e)); break; }
-			rc = pov_batch_fetch_pcm(ctx, h, pinned, hb.pcm_floats, 1);      // delivery of the PCM to the host + sync
+			rc = pov_batch_fetch_pcm(cx, sl.h, sl.pinned, hb.pcm_floats, 0);       // delivery of the PCM to the host (asynchronous)
+			if(!rc && cudaMemcpyAsync(sl.status, sl.h->d_status.ptr, sneed, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess)
+				rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: status copy failed");
+			if(!rc && cudaEventRecord(sl.done, cx->stream) != cudaSuccess) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventRecord failed");
+			sl.n_packets = (uint32_t) hb.packets.size(); sl.first_file = ck->first_file; sl.busy = (rc == POV_OK);
 		}
-		if(!rc) rc = pov_batch_status(ctx, h, nullptr, 0);
 		total += hb.pcm_floats;
 	}
+	for(auto& sl : slot) { const int r2 = retire(sl); if(rc == POV_OK) rc = r2; }
 	stop.store(true);
 	{ std::lock_guard<std::mutex> lk(mu); cv_space.notify_all(); }
 	for(auto& t : pool) t.join();
-	if(rc == POV_OK && d_sum) {
-		if(cudaMemcpyAsync(&h_sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-		   cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+	for(auto& sl : slot) {
+		if(!sl.ctx) continue;
+		double part = 0;
+		if(rc == POV_OK && sl.d_sum &&
+		   (cudaMemcpyAsync(&part, sl.d_sum, sizeof(double), cudaMemcpyDeviceToHost, sl.ctx->stream) != cudaSuccess ||
+		    cudaStreamSynchronize(sl.ctx->stream) != cudaSuccess))
 			rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: checksum copy failed");
+		h_sum += part;
+		cudaStreamSynchronize(sl.ctx->stream);
+		if(sl.h) pov_batch_free(sl.ctx, sl.h);
+		if(sl.pinned) cudaFreeHost(sl.pinned);
+		if(sl.status) cudaFreeHost(sl.status);
+		if(sl.done) cudaEventDestroy(sl.done);
+		if(sl.d_sum) cudaFree(sl.d_sum);
+		ctx->launches += (sl.ctx != ctx) ? sl.ctx->launches : 0;
+		if(sl.ctx != ctx) pov_ctx_destroy(sl.ctx);
 	}
-	if(h) pov_batch_free(ctx, h);
-	if(pinned) cudaFreeHost(pinned);
-	if(d_sum) cudaFree(d_sum);
 	if(total_values_out) *total_values_out = total;
 	if(checksum_out) *checksum_out = h_sum;
 	return rc;
