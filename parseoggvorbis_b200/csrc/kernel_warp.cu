@@ -600,9 +600,9 @@ __device__ __forceinline__ float ola_one(const OlaGeom& G, const float* __restri
 
 // Long block after a long block, both slopes long: every sample has both terms and both windows. Lane produces
 // out[j..j+3] and out[1020-j..1023-j] (j < 512) from the same four vectors (TDAC symmetry of both frames and windows).
-template <int Q>
+template <int Q, bool kStrided>
 __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, const float* __restrict__ chi, const float* __restrict__ sl,
-                                              float* __restrict__ dst, int lane) {
+                                              float* __restrict__ dst, int stride, int lane) {
 	// n = 4Q: the chunk has 2Q samples, half of them (Q) below the centre; 8 samples per lane and iteration
 #pragma unroll
 	for(int i = 0; i < Q / 128; ++i) {
@@ -620,8 +620,15 @@ __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, con
 		o2.y = __fadd_rn(__fmul_rn(-p.y, wa.z), __fmul_rn(-c.z, wb.y));
 		o2.z = __fadd_rn(__fmul_rn(-p.z, wa.y), __fmul_rn(-c.y, wb.z));
 		o2.w = __fadd_rn(__fmul_rn(-p.w, wa.x), __fmul_rn(-c.x, wb.w));
-		__stcs(reinterpret_cast<float4*>(dst + j), o1);
-		__stcs(reinterpret_cast<float4*>(dst + (2 * Q - 4) - j), o2);
+		if constexpr(!kStrided) {
+			__stcs(reinterpret_cast<float4*>(dst + j), o1);
+			__stcs(reinterpret_cast<float4*>(dst + (2 * Q - 4) - j), o2);
+		} else {          // interleaved PCM: sample j of this channel lives at dst[j * channels]
+			float* a = dst + (size_t) j * stride;
+			float* b = dst + (size_t) ((2 * Q - 4) - j) * stride;
+			a[0] = o1.x; a[stride] = o1.y; a[2 * stride] = o1.z; a[3 * stride] = o1.w;
+			b[0] = o2.x; b[stride] = o2.y; b[2 * stride] = o2.z; b[3 * stride] = o2.w;
+		}
 	}
 }
 
@@ -638,7 +645,7 @@ __device__ __forceinline__ int curve_mode(const FastTables* tb, uint32_t mapping
 	return ((prop >> c) & 1u) ? 2 : 1;
 }
 
-template <int Q0, int Q1>
+template <int Q0, int Q1, bool kPlanar>
 __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	using M = Map<Q0, Q1>;
 	constexpr int N0 = 4 * Q0, N1 = 4 * Q1;              // block sizes
@@ -690,7 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	unsigned char* curves = wbase + kWarpFixedBytes;
 
 	const int C = (int) P.C;
-	const bool planar = (b.pcm_layout == POV_PCM_PLANAR);
+	constexpr bool planar = kPlanar;       // PCM layout is a template parameter: the interleaved address arithmetic stays out of the planar kernel
 
 	for(;;) {
 		uint32_t item = 0;
@@ -787,8 +794,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				const bool emits = prev_valid && emit > 0 && (run.first_packet + (uint32_t) (first + g)) != st.first_packet;
 				if(emits) {
 					const uint64_t chan_base = chan0 + w.pcm_rel;
-					if(planar && flag && prev_n == N1 && lc == N1 / 2 && prev_right == N1 / 2 && emit == (uint32_t) (N1 / 2) && (chan_base & 3ull) == 0) {
-						ola_long_long<Q1>(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, lane);
+					if(flag && prev_n == N1 && lc == N1 / 2 && prev_right == N1 / 2 && emit == (uint32_t) (N1 / 2) && (!planar || (chan_base & 3ull) == 0)) {
+						if constexpr(planar) ola_long_long<Q1, false>(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, 1, lane);
+						else ola_long_long<Q1, true>(prev_lo, cur_hi, s_slope1, b.pcm + st.pcm_base + (frame0 + w.pcm_rel) * (uint64_t) C + (uint64_t) ch, C, lane);
 					} else {
 						OlaGeom G;
 						G.Hp = prev_n / 4; G.H = Q;
@@ -870,9 +878,15 @@ uint32_t warp_kernel_warps(void) { return (uint32_t) wk::kWarps; }
 
 template <int Q0, int Q1>
 static cudaError_t launch_geom(const wk::Params& P, uint32_t grid, size_t smem, cudaStream_t st) {
-	cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	if(e != cudaSuccess) return e;
-	wk::k_warp_synth<Q0, Q1><<<grid, wk::kThreads, smem, st>>>(P);
+	if(P.b.pcm_layout == POV_PCM_PLANAR) {
+		cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		if(e != cudaSuccess) return e;
+		wk::k_warp_synth<Q0, Q1, true><<<grid, wk::kThreads, smem, st>>>(P);
+	} else {
+		cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		if(e != cudaSuccess) return e;
+		wk::k_warp_synth<Q0, Q1, false><<<grid, wk::kThreads, smem, st>>>(P);
+	}
 	return cudaGetLastError();
 }
 
