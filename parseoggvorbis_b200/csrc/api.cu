@@ -403,6 +403,9 @@ extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id
 	{
 		FastTables ft;
 		rec.fast_ok = build_fast_tables(s, floors, maps, rec.posts_cls, ft, rec.fast_short_cap);
+		rec.fast_max_nl = 1;
+		for(uint32_t m = 0; m < s->n_mappings && m < POV_FAST_MAX_MAPPINGS; ++m)
+			for(uint32_t c = 0; c < s->channels; ++c) rec.fast_max_nl = std::max<uint32_t>(rec.fast_max_nl, ft.couple[m][c].nl);
 		if(rec.fast_ok) CUDA_TRY(ctx, dev_upload((FastTables**) &rec.d_fast, &ft, 1, ctx->stream));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // ft lives on this stack frame
 	}
@@ -714,7 +717,7 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
 		for(const WarpGroup& g : h->warp_groups) {      // one persistent launch per setup (its tables live in shared memory)
 			const SetupRec& su = ctx->setups[g.setup];
 			CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr + g.first_run, g.n_runs, su.channels, su.d_fast, su.blocksize[0], su.blocksize[1],
-			                          su.fast_short_cap, su.dev.slope, su.dev.rot, su.dev.fft8, su.dev.fftp, ctx->d_counter, ctx->sm_count, ctx->stream,
+			                          su.fast_short_cap, su.fast_max_nl, su.dev.slope, su.dev.rot, su.dev.fft8, su.dev.fftp, ctx->d_counter, ctx->sm_count, ctx->stream,
 			                          &ctx->launches));
 		}
 		return POV_OK;

@@ -49,6 +49,7 @@ struct SetupRec {
 	// warp-autonomous kernel (kernel_warp.cu): eligible setups carry their compact tables
 	bool fast_ok = false;
 	uint32_t fast_short_cap = 4;
+	uint32_t fast_max_nl = 1;         // largest channel set a coupling program of this setup needs
 	const FastTables* d_fast = nullptr;
 	std::string image;            // canonical bytes, for de-duplication
 };

@@ -557,17 +557,19 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 	}
 }
 
-// picks the instantiation: <1> no coupling, <2,false> the stereo case (one step), generic otherwise
+// picks the instantiation: <1> no coupling, <2,false> the stereo case (one step), generic otherwise. kMaxNL (1, 2 or 4) is
+// the largest channel set any coupling program of the setup needs: variants beyond it are not even compiled in.
+template <int kMaxNL>
 __device__ __forceinline__ void spectral_dispatch(const FastCouple* cp, const float* base, int half, uint32_t curve_, uint32_t rec_cap,
                                                   uint32_t rot_, int Q, uint32_t Tf_, int u) {
 	const int o0 = (int) cp->ch[0] * half, o1 = (int) cp->ch[1] * half, o2 = (int) cp->ch[2] * half, o3 = (int) cp->ch[3] * half;
 	const uint32_t cps = smem_u32(cp);
 	const int nl = cp->nl;
-	if(nl == 1) spectral_stage<1, false>(base, o0, o0, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
-	else if(nl == 2 && cp->nsteps == 1) spectral_stage<2, false>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
-	else if(nl == 2) spectral_stage<2, true>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
-	else if(nl == 3) spectral_stage<3, true>(base, o0, o1, o2, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
-	else spectral_stage<4, true>(base, o0, o1, o2, o3, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	if(kMaxNL == 1 || nl == 1) spectral_stage<1, false>(base, o0, o0, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	else if(kMaxNL >= 2 && nl == 2 && cp->nsteps == 1) spectral_stage<2, false>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	else if(kMaxNL >= 2 && nl == 2) spectral_stage<2, true>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	else if(kMaxNL >= 3 && nl == 3) spectral_stage<3, true>(base, o0, o1, o2, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	else if(kMaxNL >= 3) spectral_stage<4, true>(base, o0, o1, o2, o3, curve_, rec_cap, rot_, Q, Tf_, u, cps);
 }
 
 // ---- overlap-add ---------------------------------------------------------------------------------------------------
@@ -645,7 +647,7 @@ __device__ __forceinline__ int curve_mode(const FastTables* tb, uint32_t mapping
 	return ((prop >> c) & 1u) ? 2 : 1;
 }
 
-template <int Q0, int Q1, bool kPlanar>
+template <int Q0, int Q1, bool kPlanar, int kMaxNL>
 __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	using M = Map<Q0, Q1>;
 	constexpr int N0 = 4 * Q0, N1 = 4 * Q1;              // block sizes
@@ -770,7 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			const uint32_t Ts = smem_u32(T), Tfs = Ts + (uint32_t) f * (uint32_t) ((Qs >> 6) * 72 * 8);
 			const uint32_t rots = smem_u32(flag ? s_rot1 : s_rot0), tws = smem_u32(flag ? s_tw1 : s_tw0);
 			if(f < count)
-				spectral_dispatch(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u);
+				spectral_dispatch<kMaxNL>(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u);
 			__syncwarp();
 			// last pass output: long: lo half -> survivor slot, hi half -> slot B; short: D of FFT f packed at T + Q0 f (lo | hi)
 			if(flag) fft_passes<Q1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB));
@@ -876,22 +878,29 @@ size_t warp_kernel_smem_bytes(uint32_t bs0, uint32_t bs1, uint32_t short_posts_c
 uint32_t warp_kernel_max_run(void) { return (uint32_t) wk::kPktCap - 1u; }
 uint32_t warp_kernel_warps(void) { return (uint32_t) wk::kWarps; }
 
-template <int Q0, int Q1>
-static cudaError_t launch_geom(const wk::Params& P, uint32_t grid, size_t smem, cudaStream_t st) {
-	if(P.b.pcm_layout == POV_PCM_PLANAR) {
-		cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		if(e != cudaSuccess) return e;
-		wk::k_warp_synth<Q0, Q1, true><<<grid, wk::kThreads, smem, st>>>(P);
-	} else {
-		cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		if(e != cudaSuccess) return e;
-		wk::k_warp_synth<Q0, Q1, false><<<grid, wk::kThreads, smem, st>>>(P);
-	}
+template <int Q0, int Q1, bool kPlanar, int kMaxNL>
+static cudaError_t launch_one(const wk::Params& P, uint32_t grid, size_t smem, cudaStream_t st) {
+	cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1, kPlanar, kMaxNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if(e != cudaSuccess) return e;
+	wk::k_warp_synth<Q0, Q1, kPlanar, kMaxNL><<<grid, wk::kThreads, smem, st>>>(P);
 	return cudaGetLastError();
 }
 
+template <int Q0, int Q1>
+static cudaError_t launch_geom(const wk::Params& P, uint32_t max_nl, uint32_t grid, size_t smem, cudaStream_t st) {
+	const int cls = max_nl <= 1 ? 1 : max_nl == 2 ? 2 : 4;
+	if(P.b.pcm_layout == POV_PCM_PLANAR) {
+		if(cls == 1) return launch_one<Q0, Q1, true, 1>(P, grid, smem, st);
+		if(cls == 2) return launch_one<Q0, Q1, true, 2>(P, grid, smem, st);
+		return launch_one<Q0, Q1, true, 4>(P, grid, smem, st);
+	}
+	if(cls == 1) return launch_one<Q0, Q1, false, 1>(P, grid, smem, st);
+	if(cls == 2) return launch_one<Q0, Q1, false, 2>(P, grid, smem, st);
+	return launch_one<Q0, Q1, false, 4>(P, grid, smem, st);
+}
+
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
-                        uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, const float* const slope[2], const float2* const rot[2],
+                        uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
                         const float2* const tw8[2], const float2* const fp[2], uint32_t* d_counter, int sm_count, cudaStream_t st,
                         uint64_t* launches) {
 	if(n_runs == 0) return cudaSuccess;
@@ -907,12 +916,12 @@ cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_ru
 	const uint32_t need = (P.n_items + wk::kWarps - 1) / wk::kWarps;
 	if(grid > need) grid = need;
 	switch((bs0 / 4) * 1024u + bs1 / 4) {
-		case 64u * 1024u + 128u:  e = launch_geom<64, 128>(P, grid, smem, st); break;
-		case 64u * 1024u + 256u:  e = launch_geom<64, 256>(P, grid, smem, st); break;
-		case 64u * 1024u + 512u:  e = launch_geom<64, 512>(P, grid, smem, st); break;
-		case 128u * 1024u + 256u: e = launch_geom<128, 256>(P, grid, smem, st); break;
-		case 128u * 1024u + 512u: e = launch_geom<128, 512>(P, grid, smem, st); break;
-		case 256u * 1024u + 512u: e = launch_geom<256, 512>(P, grid, smem, st); break;
+		case 64u * 1024u + 128u:  e = launch_geom<64, 128>(P, max_nl, grid, smem, st); break;
+		case 64u * 1024u + 256u:  e = launch_geom<64, 256>(P, max_nl, grid, smem, st); break;
+		case 64u * 1024u + 512u:  e = launch_geom<64, 512>(P, max_nl, grid, smem, st); break;
+		case 128u * 1024u + 256u: e = launch_geom<128, 256>(P, max_nl, grid, smem, st); break;
+		case 128u * 1024u + 512u: e = launch_geom<128, 512>(P, max_nl, grid, smem, st); break;
+		case 256u * 1024u + 512u: e = launch_geom<256, 512>(P, max_nl, grid, smem, st); break;
 		default: return cudaErrorInvalidConfiguration;
 	}
 	if(launches) ++*launches;
