@@ -143,12 +143,15 @@ __device__ __forceinline__ float uncouple_ang(float m, float a) {
 }
 
 // ---- floor curve block (warp private, shared memory) ------------------------------------------------------------
-// 8-byte segment record:  x = x0 | x1 << 11 | y0 << 22  (x1 = 2047: flat tail),  y = slope | descending << 31,
-//   slope = ceil(2^20 * |dy| / dx)   =>   y(x) = y0 +/- floor((x - x0) * |dy| / dx) = y0 +/- umulhi((x - x0) << 12, slope)
-// Exact: with k = x - x0 < dx <= 2^10 the excess k * (slope - 2^20 |dy|/dx) / 2^20 < dx / 2^20 <= 1/dx can never carry the
-// fractional part of k*|dy|/dx (<= 1 - 1/dx) over the next integer. |dy| <= 1023 keeps the slope below 2^30. Curves that
+// 8-byte segment record (a, b) of the segment [x0, x1) that starts at (x0, y0): the curve is y(x) = (a + x * b) >> 20 with
+//   S = ceil(2^20 * |dy| / dx),  b = +S (ascending) or -S (descending, two's complement),
+//   a = (y0 << 20) + (descending ? 2^20 - 1 : 0) - x0 * b        (all modulo 2^32; the true value stays below 2^31)
+// i.e. y0 + floor(k S / 2^20) going up and y0 - floor(k S / 2^20) = ceil-form (y0 2^20 - k S + 2^20 - 1) >> 20 going down,
+// k = x - x0, which are the reference's y0 +/- floor(k |dy| / dx) (Utils.hpp:122-137):
+// Exact: with k < dx <= 2^10 the excess k * (S - 2^20 |dy|/dx) / 2^20 < dx / 2^20 <= 1/dx can never carry the
+// fractional part of k*|dy|/dx (<= 1 - 1/dx) over the next integer. |dy| <= 1023 keeps S below 2^30. Curves that
 // violate these bounds also violate hpp:587 and are reported through the packet status word (samples unspecified, as in
-// the reference, which aborts the stream there).
+// the reference, which aborts the stream there). The flat tail after the last post is (y0 << 20, 0).
 // Block layout: uint2 rec[cap] | uint2 tab[n/64] (rank table, see build_records).
 // floor1 step 1 (amplitude unwrap, hpp:521-559) for ALL packets of a run at once: lane p owns packet p and walks its
 // posts serially (the neighbour DAG makes the posts of one curve sequential, but the <= 32 curves of a run are
@@ -260,7 +263,7 @@ __device__ __forceinline__ void build_records(const FastFloor* __restrict__ F, c
 	__syncwarp();
 	if(f) {
 		uint2 r;
-		if(last) r = make_uint2(x0 | (2047u << 11) | (y0 << 22), 0u);
+		if(last) r = make_uint2(y0 << 20, 0u);
 		else {
 			const bool down = y1 < y0;
 			const uint32_t ady = down ? y0 - y1 : y1 - y0, adx = x1 - x0;
@@ -269,7 +272,8 @@ __device__ __forceinline__ void build_records(const FastFloor* __restrict__ F, c
 			uint32_t q = __umulhi(N, recip[adx]);
 			if(q * adx > N) --q;
 			if(adx == 1u) q = N;
-			r = make_uint2(x0 | (x1 << 11) | (y0 << 22), q | (down ? 0x80000000u : 0u));
+			const uint32_t b = down ? 0u - q : q;
+			r = make_uint2((y0 << 20) + (down ? 0xFFFFFu : 0u) - x0 * b, b);
 		}
 		rec[rank] = r;
 		if((x0 >> 5) < nwords) atomicOr(&bits[2 * (x0 >> 5)], 1u << (x0 & 31u));
@@ -293,34 +297,9 @@ __device__ __forceinline__ void build_records(const FastFloor* __restrict__ F, c
 __device__ __forceinline__ void flat_curve(unsigned char* __restrict__ curve, uint32_t rec_cap, uint32_t nwords, uint32_t y, int lane) {
 	uint2* rec = reinterpret_cast<uint2*>(curve);
 	uint2* tab = rec + rec_cap;
-	if(lane == 0) rec[0] = make_uint2(0u | (2047u << 11) | (y << 22), 0u);
+	if(lane == 0) rec[0] = make_uint2(y << 20, 0u);
 	if((uint32_t) lane < nwords) tab[lane] = make_uint2(lane == 0 ? 1u : 0u, lane == 0 ? 0xFFFFFFFFu : 0u);
 	__syncwarp();
-}
-
-// Two consecutive bins x, x+1 (x even) of a curve as inverse-dB table values (hpp:586-589).
-__device__ __forceinline__ float2 curve_pair(const uint2* __restrict__ rec, const uint2* __restrict__ tab, uint32_t x,
-                                             const float* __restrict__ invdb) {
-	const uint2 t = tab[x >> 5];
-	const uint32_t s = t.y + __popc(t.x & (0xFFFFFFFFu >> (31u - (x & 31u))));
-	uint2 r = rec[s];
-	float2 out;
-	{
-		const uint32_t k = x - (r.x & 0x7ffu);
-		const uint32_t q = __umulhi(k << 12, r.y & 0x7fffffffu);
-		const uint32_t y0 = r.x >> 22;
-		const uint32_t y = ((int) r.y < 0) ? y0 - q : y0 + q;
-		out.x = invdb[y];
-	}
-	if(x + 1 >= ((r.x >> 11) & 0x7ffu)) r = rec[s + 1];
-	{
-		const uint32_t k = x + 1 - (r.x & 0x7ffu);
-		const uint32_t q = __umulhi(k << 12, r.y & 0x7fffffffu);
-		const uint32_t y0 = r.x >> 22;
-		const uint32_t y = ((int) r.y < 0) ? y0 - q : y0 + q;
-		out.y = invdb[y];
-	}
-	return out;
 }
 
 // Four consecutive bins x..x+3 (x a multiple of 4) of a curve as inverse-dB table values (hpp:586-589): one rank-table
@@ -336,11 +315,7 @@ __device__ __forceinline__ float4 curve_quad(const uint2* __restrict__ rec, cons
 #pragma unroll
 	for(int b = 0; b < 4; ++b) {
 		if(b > 0 && ((cross >> (b - 1)) & 1u)) r = rec[++s];
-		const uint32_t k = x + (uint32_t) b - (r.x & 0x7ffu);
-		const uint32_t q = __umulhi(k << 12, r.y & 0x7fffffffu);
-		const uint32_t y0 = r.x >> 22;
-		const uint32_t y = ((int) r.y < 0) ? y0 - q : y0 + q;
-		out[b] = invdb[y];
+		out[b] = invdb[(r.x + (x + (uint32_t) b) * r.y) >> 20];
 	}
 	return make_float4(out[0], out[1], out[2], out[3]);
 }
