@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--packets", type=int, default=4096, help="packets per stream")
     ap.add_argument("--distinct", type=int, default=4, help="independently generated streams (rest are replicas)")
     ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-depth", type=int, default=2, help="contexts (= streams) the end-to-end steps are pipelined over")
     ap.add_argument("--cpu-streams", type=int, default=0, help="streams of the CPU-baseline sample (0 = one per core)")
     ap.add_argument("--ref-decodes", type=int, default=40, help="reference arm: decodes per thread per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -297,20 +298,20 @@ def main():
 
     # ---- end-to-end leg: host buffers in, host PCM out, every step ----
     # Every step validates the descriptors, copies all input arenas from pinned host memory to the device, runs the
-    # kernel and copies the whole PCM arena back into pinned host memory. Steps are issued as a 2-deep pipeline on two
-    # contexts (= two CUDA streams), so that the H2D copy of step k+1 overlaps the D2H copy of step k on the two copy
+    # kernel and copies the whole PCM arena back into pinned host memory. Steps are issued as a pipeline over --e2e-depth
+    # contexts (= CUDA streams), so that the H2D copy of step k+1 overlaps the D2H copy of step k on the two copy
     # engines — the way a corpus decode streams batches through the device. Timed with the host clock around the whole
     # pipeline (barrier + synchronize on both sides), which includes every copy and every launch.
     e2e = None
     if not args.no_e2e:
-        depth = 2
+        depth = max(1, args.e2e_depth)
         pb, keep = pin_batch(batch)
-        ctxs = [ctx, SynthContext(local)]
-        pb2 = pb
+        ctxs = [ctx] + [SynthContext(local) for _ in range(depth - 1)]
         handles, outs = [bh], []
-        sid2 = ctxs[1].register_setup(setup)
-        assert sid2 == int(batch.streams["setup_id"][0])
-        handles.append(ctxs[1].upload(pb2))
+        for c in ctxs[1:]:
+            sid2 = c.register_setup(setup)
+            assert sid2 == int(batch.streams["setup_id"][0])
+            handles.append(c.upload(pb))
         for _ in range(depth):
             t_out = torch.empty(int(batch.pcm_floats), dtype=torch.float32, pin_memory=True)
             keep.append(t_out)
@@ -339,7 +340,7 @@ def main():
         e2e_drain()
         barrier()
         wall = time.perf_counter() - t0
-        e2e_ok = bool(np.array_equal(outs[0][:1 << 20], outs[1][:1 << 20])) if args.e2e_steps >= 2 else True
+        e2e_ok = all(bool(np.array_equal(outs[0][:1 << 20], o[:1 << 20])) for o in outs[1:min(depth, args.e2e_steps)])
         tt = torch.tensor([wall * 1e3], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -348,8 +349,9 @@ def main():
                "ms_per_step": float(tt.item()) / args.e2e_steps, "pipeline_depth": depth,
                "timing": "host clock around the pipelined steps (upload+run+fetch each), max over ranks",
                "outputs_identical_across_contexts": e2e_ok}
-        handles[1].free()
-        ctxs[1].close()
+        for c, h in list(zip(ctxs, handles))[1:]:
+            h.free()
+            c.close()
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
