@@ -187,9 +187,11 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 			const uint32_t val = __ldg(yp + i);
 			const bool up = y1 >= y0;
 			const uint32_t ady = up ? (y1 - y0) : (y0 - y1);
-			// floor(ady * dxn / adx) by multiplication with ceil(2^32/adx): exact while ady * dxn * adx < 2^32 (ady < 2^12)
-			const uint32_t e = ady * (t.y & 0xffffu);
-			const uint32_t off = (ady < 4096u) ? __umulhi(e, t.z) : e / (t.y >> 16);
+			// floor(ady * dxn / adx) by multiplication with m = ceil(2^32/adx): e = ady * dxn < 2^32 and m - 2^32/adx < 1 put the
+			// estimate at most one above the quotient, never below (adx >= 2: a post lies strictly between its neighbours)
+			const uint32_t e = ady * (t.y & 0xffffu), adx = t.y >> 16;
+			uint32_t off = __umulhi(e, t.z);
+			if(off * adx > e) --off;
 			const uint32_t predicted = up ? y0 + off : y0 - off;
 			if(predicted > range) bad |= POV_PKT_FLOOR_PREDICTED;
 			const uint32_t high_room = range - predicted, low_room = predicted;
