@@ -203,7 +203,7 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="independent config-2 streams per GPU per step")
     ap.add_argument("--packets", type=int, default=4096, help="packets per stream")
     ap.add_argument("--distinct", type=int, default=4, help="independently generated streams (rest are replicas)")
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--e2e-depth", type=int, default=2, help="contexts (= streams) the end-to-end steps are pipelined over")
     ap.add_argument("--cpu-streams", type=int, default=0, help="streams of the CPU-baseline sample (0 = one per core)")
     ap.add_argument("--ref-decodes", type=int, default=40, help="reference arm: decodes per thread per step")
