@@ -115,6 +115,7 @@ extern "C" void pov_ctx_destroy(pov_ctx* ctx) {
 	if(!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	if(ctx->corpus && ctx->corpus_free) { ctx->corpus_free(ctx->corpus); ctx->corpus = nullptr; }
 	for(auto& s : ctx->setups) free_setup(s);
 	for(auto& kv : ctx->blk_tables) { cudaFree((void*) kv.second.d_rot); cudaFree((void*) kv.second.d_fft); cudaFree((void*) kv.second.d_fftp); cudaFree((void*) kv.second.d_fft8); cudaFree((void*) kv.second.d_slope); }
 	cudaFree((void*) ctx->d_setups);

@@ -68,6 +68,8 @@ struct pov_ctx {
 	std::map<uint32_t, BlockTables> blk_tables;
 	std::map<std::string, uint32_t> setup_by_key;   // raw header bytes of a parsed stream -> setup id (front end)
 	DevBuf mdct_in, mdct_out;
+	void* corpus = nullptr;                 // what pov_decode_corpus keeps between calls (front_end.cpp: sibling context, slots, pinned pool)
+	void (*corpus_free)(void*) = nullptr;
 	char err[512] = {0};
 };
 

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <map>
@@ -115,6 +116,7 @@ struct HostBatch {
 		b.pcm_floats = pcm_floats;
 		return b;
 	}
+	void clear() { streams.clear(); packets.clear(); ys.clear(); payload.clear(); pcm_floats = 0; }
 	void append(const StreamWork& st, uint32_t setup_id) {
 		pov_stream rec;
 		memset(&rec, 0, sizeof rec);
@@ -218,45 +220,194 @@ extern "C" void pov_decoded_free(pov_decoded* d) {
 // ---------------------------------------------------------------------------------------------------------------
 // corpus decode: `host_threads` front-end workers parse files into chunks, the calling thread feeds the GPU
 // ---------------------------------------------------------------------------------------------------------------
+cudaError_t pov_checksum_launch(const float* pcm, uint64_t n, double* d_sum, cudaStream_t st, uint64_t* launches);
+
 namespace {
+struct PinnedBuf { uint8_t* p = nullptr; size_t cap = 0; };
+
+// A chunk leaves its worker as one assembled batch in pinned host memory: the calling thread only turns the chunk-local
+// setup numbers into registered setup ids (one map lookup per distinct setup, normally one per chunk), validates the
+// descriptors and queues the copies, which then run as plain DMA.
 struct Chunk {
 	uint32_t first_file = 0, n_files = 0;
-	std::vector<std::vector<StreamWork>> files;
+	PinnedBuf buf;                             // streams | packets | ys | payload, each 16-byte aligned
+	pov_batch view;                            // pointers into buf; pov_stream::setup_id = index into `setups` until patched
+	pov_stream* streams = nullptr;             // writable alias of view.streams
+	std::vector<StreamWork> setups;            // one representative stream (headers only) per distinct setup
+	std::vector<uint64_t> frames;              // per file
 	std::string error;
 };
-}  // namespace
 
-cudaError_t pov_checksum_launch(const float* pcm, uint64_t n, double* d_sum, cudaStream_t st, uint64_t* launches);
+// What pov_decode_corpus keeps between calls on a context: the sibling context (second stream), the two batch slots with
+// their device arenas and pinned PCM buffers, and the pool of pinned staging buffers the workers assemble chunks into.
+struct CorpusState {
+	int device = 0;
+	pov_ctx* sibling = nullptr;
+	struct Slot {
+		pov_ctx* ctx = nullptr;                // slot 0: the caller's context; slot 1: the sibling, so that the copies of one
+		                                       // chunk never wait for the other chunk's work
+		double* d_sum = nullptr;
+		pov_batch_handle* h = nullptr;
+		float* pinned = nullptr; size_t pinned_cap = 0;
+		uint32_t* status = nullptr; size_t status_cap = 0;
+		cudaEvent_t done = nullptr;
+		cudaEvent_t t_begin = nullptr, t_kernels = nullptr, t_end = nullptr;   // POV_CORPUS_TIMING only
+		uint32_t n_packets = 0, first_file = 0;
+		std::unique_ptr<Chunk> in_flight;      // its pinned buffer is the source of copies that may still be running
+		bool busy = false;
+	} slot[2];
+	std::mutex pmu;
+	std::condition_variable pcv;
+	std::vector<PinnedBuf> free_bufs;
+	uint32_t n_bufs = 0, max_bufs = 0;
+
+	PinnedBuf acquire(size_t need, const std::atomic<bool>& stop) {
+		PinnedBuf b;
+		{
+			std::unique_lock<std::mutex> lk(pmu);
+			pcv.wait(lk, [&] { return !free_bufs.empty() || n_bufs < max_bufs || stop.load(); });
+			if(!free_bufs.empty()) { b = free_bufs.back(); free_bufs.pop_back(); }
+			else if(n_bufs < max_bufs) ++n_bufs;
+			else return b;                         // stopping
+		}
+		if(b.cap < need) {
+			if(b.p) cudaFreeHost(b.p);
+			b.p = nullptr; b.cap = need + need / 4;
+			if(cudaHostAlloc((void**) &b.p, b.cap, cudaHostAllocDefault) != cudaSuccess) {
+				b.p = nullptr; b.cap = 0;
+				std::lock_guard<std::mutex> lk(pmu);
+				--n_bufs;                              // the buffer this call stood for no longer exists
+				pcv.notify_one();
+			}
+		}
+		return b;
+	}
+	void release(PinnedBuf b) {
+		if(!b.p) return;
+		std::lock_guard<std::mutex> lk(pmu);
+		free_bufs.push_back(b);
+		pcv.notify_one();
+	}
+	~CorpusState() {
+		cudaSetDevice(device);
+		for(auto& sl : slot) {
+			if(!sl.ctx) continue;
+			cudaStreamSynchronize(sl.ctx->stream);
+			if(sl.in_flight) { if(sl.in_flight->buf.p) cudaFreeHost(sl.in_flight->buf.p); sl.in_flight.reset(); }
+			if(sl.h) pov_batch_free(sl.ctx, sl.h);
+			if(sl.pinned) cudaFreeHost(sl.pinned);
+			if(sl.status) cudaFreeHost(sl.status);
+			if(sl.done) cudaEventDestroy(sl.done);
+			if(sl.t_begin) { cudaEventDestroy(sl.t_begin); cudaEventDestroy(sl.t_kernels); cudaEventDestroy(sl.t_end); }
+			if(sl.d_sum) cudaFree(sl.d_sum);
+		}
+		for(auto& b : free_bufs) cudaFreeHost(b.p);
+		if(sibling) pov_ctx_destroy(sibling);
+	}
+};
+void corpus_state_free(void* p) { delete (CorpusState*) p; }
+
+inline size_t align16(size_t x) { return (x + 15) & ~(size_t) 15; }
+}  // namespace
 
 extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* data, const size_t* len,
                                  uint32_t host_threads, uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out) {
 	if(!ctx || (n_files && (!data || !len))) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	if(host_threads == 0) host_threads = std::max(1u, std::thread::hardware_concurrency());
-	const uint32_t files_per_chunk = 64;
+	uint32_t files_per_chunk = 64;
+	if(const char* e = getenv("POV_CORPUS_CHUNK")) files_per_chunk = std::max(1, atoi(e));
 	const uint32_t n_chunks = (n_files + files_per_chunk - 1) / files_per_chunk;
+	const uint32_t max_ready = std::max<uint32_t>(4, 2 * host_threads);
+
+	// ---- resources that outlive the call ----
+	int rc = POV_OK;
+	if(!ctx->corpus) {
+		std::unique_ptr<CorpusState> cs(new CorpusState());
+		cs->device = ctx->device;
+		const char* e = nullptr;
+		if(pov_ctx_create(ctx->device, &cs->sibling, &e) != POV_OK) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: %s", e ? e : "sibling context");
+		cs->slot[0].ctx = ctx; cs->slot[1].ctx = cs->sibling;
+		for(auto& sl : cs->slot) {
+			if(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess || cudaMalloc(&sl.d_sum, sizeof(double)) != cudaSuccess)
+				return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventCreate / cudaMalloc failed");
+		}
+		ctx->corpus = cs.release();
+		ctx->corpus_free = corpus_state_free;
+	}
+	CorpusState& cs = *(CorpusState*) ctx->corpus;
+	cs.max_bufs = std::max(cs.max_bufs, max_ready + host_threads + 3);       // queued + being filled + two in flight + one spare
+	for(auto& sl : cs.slot)
+		if(cudaMemsetAsync(sl.d_sum, 0, sizeof(double), sl.ctx->stream) != cudaSuccess) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaMemset failed");
+	const uint64_t sibling_launches0 = cs.sibling->launches;
+
 	std::atomic<uint32_t> next_chunk(0);
 	std::mutex mu;
 	std::condition_variable cv_ready, cv_space;
 	std::map<uint32_t, std::unique_ptr<Chunk>> ready;    // by chunk index
-	const size_t max_ready = std::max<size_t>(4, 2 * host_threads);
+	uint32_t consumed = 0;                               // chunks handed to the calling thread so far (guarded by mu)
 	std::atomic<bool> stop(false);
 
 	auto worker = [&]() {
+		cudaSetDevice(ctx->device);
+		HostBatch hb;
+		std::vector<StreamWork> file;
 		for(;;) {
 			const uint32_t ci = next_chunk.fetch_add(1);
 			if(ci >= n_chunks || stop.load()) return;
 			std::unique_ptr<Chunk> ck(new Chunk());
+			memset(&ck->view, 0, sizeof ck->view);
 			ck->first_file = ci * files_per_chunk;
 			ck->n_files = std::min(files_per_chunk, n_files - ck->first_file);
-			ck->files.resize(ck->n_files);
+			ck->frames.assign(ck->n_files, 0);
+			hb.clear();
 			for(uint32_t i = 0; i < ck->n_files && ck->error.empty(); ++i) {
 				ParseError err;
-				if(!parse_ogg_file(data[ck->first_file + i], len[ck->first_file + i], ck->files[i], err))
+				file.clear();
+				if(!parse_ogg_file(data[ck->first_file + i], len[ck->first_file + i], file, err)) {
 					ck->error = "file " + std::to_string(ck->first_file + i) + ": check failed: " + err.msg;
+					break;
+				}
+				for(StreamWork& st : file) {
+					if(!st.have_setup) continue;
+					uint32_t k = 0;
+					while(k < ck->setups.size() && ck->setups[k].setup_key != st.setup_key) ++k;
+					hb.append(st, k);
+					ck->frames[i] += st.frames;
+					if(k == ck->setups.size()) {
+						st.packets.clear(); st.ys.clear(); st.payload.clear();
+						ck->setups.push_back(std::move(st));
+					}
+				}
 			}
+			if(ck->error.empty() && !hb.packets.empty()) {
+				// pageable vectors -> one pinned buffer (this copy runs on the worker, the DMA later needs no staging)
+				const size_t o_st = 0, o_pk = o_st + align16(hb.streams.size() * sizeof(pov_stream)),
+				             o_ys = o_pk + align16(hb.packets.size() * sizeof(pov_packet)), o_pl = o_ys + align16(hb.ys.size() * sizeof(uint16_t)),
+				             need = o_pl + align16(hb.payload.size());
+				ck->buf = cs.acquire(need, stop);
+				if(!ck->buf.p) { if(!stop.load()) ck->error = "pov_decode_corpus: pinned staging buffer allocation failed"; }
+				else {
+					uint8_t* q = ck->buf.p;
+					memcpy(q + o_st, hb.streams.data(), hb.streams.size() * sizeof(pov_stream));
+					memcpy(q + o_pk, hb.packets.data(), hb.packets.size() * sizeof(pov_packet));
+					memcpy(q + o_ys, hb.ys.data(), hb.ys.size() * sizeof(uint16_t));
+					memcpy(q + o_pl, hb.payload.data(), hb.payload.size());
+					pov_batch& b = ck->view;
+					b.input_kind = POV_INPUT_ENTRIES; b.pcm_layout = POV_PCM_PLANAR;
+					ck->streams = (pov_stream*) (q + o_st);
+					b.n_streams = (uint32_t) hb.streams.size(); b.streams = ck->streams;
+					b.n_packets = (uint32_t) hb.packets.size(); b.packets = (const pov_packet*) (q + o_pk);
+					b.ys = (const uint16_t*) (q + o_ys); b.n_ys = hb.ys.size();
+					b.payload = q + o_pl; b.payload_bytes = hb.payload.size();
+					b.pcm_floats = hb.pcm_floats;
+				}
+			}
+			// Back-pressure by chunk INDEX, not by count: the chunk the consumer is waiting for always passes, however many
+			// later chunks the other workers have finished in the meantime (a count limit can fill the queue with later chunks
+			// and then block the one worker that holds the chunk everybody is waiting for).
 			std::unique_lock<std::mutex> lk(mu);
-			cv_space.wait(lk, [&] { return ready.size() < max_ready || stop.load(); });
+			cv_space.wait(lk, [&] { return ci < consumed + max_ready || stop.load(); });
 			ready[ci] = std::move(ck);
 			cv_ready.notify_all();
 		}
@@ -264,39 +415,24 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 	std::vector<std::thread> pool;
 	for(uint32_t t = 0; t < host_threads; ++t) pool.emplace_back(worker);
 
-	int rc = POV_OK;
 	uint64_t total = 0;
-	double* d_sum = nullptr;
 	double h_sum = 0;
 	// Two batch slots: while the GPU transforms chunk i and copies its PCM and status words to pinned host memory, the
-	// calling thread assembles and validates chunk i+1. A slot is checked (status words) and reused two chunks later.
-	struct Slot {
-		pov_ctx* ctx = nullptr;                    // slot 0: the caller's context; slot 1: a sibling context (own stream), so
-		                                           // that the pageable uploads of one chunk never wait for the other chunk's work
-		double* d_sum = nullptr;
-		pov_batch_handle* h = nullptr;
-		float* pinned = nullptr; size_t pinned_cap = 0;
-		uint32_t* status = nullptr; size_t status_cap = 0;
-		cudaEvent_t done = nullptr;
-		uint32_t n_packets = 0, first_file = 0;
-		bool busy = false;
-	} slot[2];
-	slot[0].ctx = ctx;
-	{
-		const char* e = nullptr;
-		if(pov_ctx_create(ctx->device, &slot[1].ctx, &e) != POV_OK) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: %s", e ? e : "sibling context");
-	}
-	for(auto& sl : slot) {
-		if(rc) break;
-		if(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventCreate failed");
-		else if(cudaMalloc(&sl.d_sum, sizeof(double)) != cudaSuccess || cudaMemsetAsync(sl.d_sum, 0, sizeof(double), sl.ctx->stream) != cudaSuccess)
-			rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaMalloc failed");
-	}
-	(void) d_sum;
+	// calling thread validates and queues chunk i+1. A slot is checked (status words) and reused two chunks later.
+	typedef CorpusState::Slot Slot;
+	const bool timing = getenv("POV_CORPUS_TIMING") != nullptr;
+	double g_copy_in_kernels = 0, g_copy_out = 0;
+	if(timing) for(auto& sl : cs.slot) if(!sl.t_begin) { cudaEventCreate(&sl.t_begin); cudaEventCreate(&sl.t_kernels); cudaEventCreate(&sl.t_end); }
 	auto retire = [&](Slot& sl) -> int {           // wait for a slot's chunk and turn its status words into the reference's error
 		if(!sl.busy) return POV_OK;
 		sl.busy = false;
-		if(cudaEventSynchronize(sl.done) != cudaSuccess) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: chunk failed on the device");
+		const bool ok = cudaEventSynchronize(sl.done) == cudaSuccess;
+		if(timing && ok && sl.n_packets) {
+			float a = 0, b = 0;
+			if(cudaEventElapsedTime(&a, sl.t_begin, sl.t_kernels) == cudaSuccess && cudaEventElapsedTime(&b, sl.t_kernels, sl.t_end) == cudaSuccess) { g_copy_in_kernels += a; g_copy_out += b; }
+		}
+		if(sl.in_flight) { cs.release(sl.in_flight->buf); sl.in_flight.reset(); }
+		if(!ok) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: chunk failed on the device");
 		for(uint32_t p = 0; p < sl.n_packets; ++p)
 			if(sl.status[p]) {
 				const char* what = (sl.status[p] & POV_PKT_FLOOR_PREDICTED) ? "predicted <= range (hpp:536)"
@@ -307,84 +443,100 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 		return POV_OK;
 	};
 
+	// POV_CORPUS_TIMING=1: where the calling thread's time goes (stderr), to tell a starved consumer from a slow one
+	double t_wait = 0, t_retire = 0, t_upload = 0, t_run = 0, t_fetch = 0;
+	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t_begin = now();
 	for(uint32_t ci = 0; ci < n_chunks && rc == POV_OK; ++ci) {
 		std::unique_ptr<Chunk> ck;
+		double t0 = now();
 		{
 			std::unique_lock<std::mutex> lk(mu);
 			cv_ready.wait(lk, [&] { return ready.count(ci) != 0; });
 			ck = std::move(ready[ci]);
 			ready.erase(ci);
+			consumed = ci + 1;
 			cv_space.notify_all();
 		}
-		if(!ck->error.empty()) { rc = pov_fail(ctx, POV_ERR_STREAM, "%s", ck->error.c_str()); break; }
-		HostBatch hb;
-		for(uint32_t i = 0; i < ck->n_files && rc == POV_OK; ++i) {
-			uint64_t frames = 0;
-			for(const StreamWork& st : ck->files[i]) {
-				if(!st.have_setup) continue;
-				uint32_t id = 0;
-				rc = register_stream_setup(slot[ci & 1].ctx, st, &id);
-				if(rc) { if(slot[ci & 1].ctx != ctx) pov_fail(ctx, rc, "%s", pov_last_error(slot[ci & 1].ctx)); break; }
-				hb.append(st, id);
-				frames += st.frames;
-			}
-			if(frames_out) frames_out[ck->first_file + i] = frames;
-		}
-		if(rc || hb.packets.empty()) continue;
-		Slot& sl = slot[ci & 1];
+		t_wait += now() - t0; t0 = now();
+		if(!ck->error.empty()) { rc = pov_fail(ctx, POV_ERR_STREAM, "%s", ck->error.c_str()); cs.release(ck->buf); break; }
+		if(frames_out) for(uint32_t i = 0; i < ck->n_files; ++i) frames_out[ck->first_file + i] = ck->frames[i];
+		if(ck->view.n_packets == 0) { cs.release(ck->buf); continue; }
+		Slot& sl = cs.slot[ci & 1];
 		pov_ctx* cx = sl.ctx;
+		std::vector<uint32_t> ids(ck->setups.size(), 0);
+		for(size_t k = 0; k < ck->setups.size() && rc == POV_OK; ++k) {
+			rc = register_stream_setup(cx, ck->setups[k], &ids[k]);
+			if(rc && cx != ctx) pov_fail(ctx, rc, "%s", pov_last_error(cx));
+		}
+		if(rc) { cs.release(ck->buf); break; }
+		for(uint32_t i = 0; i < ck->view.n_streams; ++i) ck->streams[i].setup_id = ids[ck->streams[i].setup_id];
 		rc = retire(sl);                           // the chunk that used this slot two iterations ago
-		if(rc) break;
-		pov_batch b = hb.view();
-		rc = pov_batch_upload(cx, &b, &sl.h);      // pageable sources: staged by the runtime before the call returns
+		if(rc) { cs.release(ck->buf); break; }
+		t_retire += now() - t0; t0 = now();
+		const pov_batch b = ck->view;
+		const uint64_t pcm_floats = b.pcm_floats;
+		const uint32_t n_packets = b.n_packets;
+		if(timing) cudaEventRecord(sl.t_begin, cx->stream);
+		rc = pov_batch_upload(cx, &b, &sl.h);      // pinned sources: the copies are queued, the chunk stays alive until retire()
+		sl.in_flight = std::move(ck);
+		sl.busy = true;                            // from here on retire() has to wait for the stream before the buffer is reused
+		sl.n_packets = 0;
+		cudaEventRecord(sl.done, cx->stream);
+		t_upload += now() - t0; t0 = now();
 		if(!rc) rc = pov_batch_run(cx, sl.h);
+		t_run += now() - t0; t0 = now();
 		if(rc && cx != ctx) pov_fail(ctx, rc, "%s", pov_last_error(cx));
 		if(!rc) {
-			const size_t need = hb.pcm_floats * sizeof(float);
+			const size_t need = pcm_floats * sizeof(float);
 			if(need > sl.pinned_cap) {
 				if(sl.pinned) cudaFreeHost(sl.pinned);
 				sl.pinned = nullptr;
 				sl.pinned_cap = need + need / 4;
-				if(cudaMallocHost((void**) &sl.pinned, sl.pinned_cap) != cudaSuccess) { rc = pov_fail(ctx, POV_ERR_CUDA, "cudaMallocHost failed"); break; }
+				if(cudaMallocHost((void**) &sl.pinned, sl.pinned_cap) != cudaSuccess) { sl.pinned_cap = 0; rc = pov_fail(ctx, POV_ERR_CUDA, "cudaMallocHost failed"); break; }
 			}
-			const size_t sneed = hb.packets.size() * sizeof(uint32_t);
+			const size_t sneed = (size_t) n_packets * sizeof(uint32_t);
 			if(sneed > sl.status_cap) {
 				if(sl.status) cudaFreeHost(sl.status);
 				sl.status = nullptr;
 				sl.status_cap = sneed + sneed / 4;
-				if(cudaMallocHost((void**) &sl.status, sl.status_cap) != cudaSuccess) { rc = pov_fail(ctx, POV_ERR_CUDA, "cudaMallocHost failed"); break; }
+				if(cudaMallocHost((void**) &sl.status, sl.status_cap) != cudaSuccess) { sl.status_cap = 0; rc = pov_fail(ctx, POV_ERR_CUDA, "cudaMallocHost failed"); break; }
 			}
-			cudaError_t e = pov_checksum_launch((const float*) pov_batch_pcm_dev(sl.h), hb.pcm_floats, sl.d_sum, cx->stream, &cx->launches);
+			cudaError_t e = pov_checksum_launch((const float*) pov_batch_pcm_dev(sl.h), pcm_floats, sl.d_sum, cx->stream, &cx->launches);
 			if(e != cudaSuccess) { rc = pov_fail(ctx, POV_ERR_CUDA, "checksum kernel: %s", cudaGetErrorString(e)); break; }
-			rc = pov_batch_fetch_pcm(cx, sl.h, sl.pinned, hb.pcm_floats, 0);       // delivery of the PCM to the host (asynchronous)
+			if(timing) cudaEventRecord(sl.t_kernels, cx->stream);
+			rc = pov_batch_fetch_pcm(cx, sl.h, sl.pinned, pcm_floats, 0);       // delivery of the PCM to the host (asynchronous)
 			if(!rc && cudaMemcpyAsync(sl.status, sl.h->d_status.ptr, sneed, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess)
 				rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: status copy failed");
+			if(timing) cudaEventRecord(sl.t_end, cx->stream);
 			if(!rc && cudaEventRecord(sl.done, cx->stream) != cudaSuccess) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventRecord failed");
-			sl.n_packets = (uint32_t) hb.packets.size(); sl.first_file = ck->first_file; sl.busy = (rc == POV_OK);
+			if(!rc) { sl.n_packets = n_packets; sl.first_file = sl.in_flight->first_file; }
 		}
-		total += hb.pcm_floats;
+		total += pcm_floats;
+		t_fetch += now() - t0;
 	}
-	for(auto& sl : slot) { const int r2 = retire(sl); if(rc == POV_OK) rc = r2; }
+	for(auto& sl : cs.slot) { const int r2 = retire(sl); if(rc == POV_OK) rc = r2; }
+	if(timing)
+		fprintf(stderr, "pov_decode_corpus: %u chunks in %.3f s on the calling thread: wait for parsed chunks %.3f, "
+		        "setup ids + wait for the slot %.3f, validate+queue upload %.3f, launch %.3f, fetch/issue %.3f; on the streams (sum over chunks): "
+		        "copy in + kernels %.3f s, copy out %.3f s\n",
+		        n_chunks, now() - t_begin, t_wait, t_retire, t_upload, t_run, t_fetch, g_copy_in_kernels * 1e-3, g_copy_out * 1e-3);
 	stop.store(true);
 	{ std::lock_guard<std::mutex> lk(mu); cv_space.notify_all(); }
+	{ std::lock_guard<std::mutex> lk(cs.pmu); cs.pcv.notify_all(); }
 	for(auto& t : pool) t.join();
-	for(auto& sl : slot) {
-		if(!sl.ctx) continue;
+	for(auto& kv : ready) if(kv.second) cs.release(kv.second->buf);          // chunks nobody consumed (error paths)
+	ready.clear();
+	for(auto& sl : cs.slot) {
 		double part = 0;
-		if(rc == POV_OK && sl.d_sum &&
+		if(rc == POV_OK &&
 		   (cudaMemcpyAsync(&part, sl.d_sum, sizeof(double), cudaMemcpyDeviceToHost, sl.ctx->stream) != cudaSuccess ||
 		    cudaStreamSynchronize(sl.ctx->stream) != cudaSuccess))
 			rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: checksum copy failed");
 		h_sum += part;
 		cudaStreamSynchronize(sl.ctx->stream);
-		if(sl.h) pov_batch_free(sl.ctx, sl.h);
-		if(sl.pinned) cudaFreeHost(sl.pinned);
-		if(sl.status) cudaFreeHost(sl.status);
-		if(sl.done) cudaEventDestroy(sl.done);
-		if(sl.d_sum) cudaFree(sl.d_sum);
-		ctx->launches += (sl.ctx != ctx) ? sl.ctx->launches : 0;
-		if(sl.ctx != ctx) pov_ctx_destroy(sl.ctx);
 	}
+	ctx->launches += cs.sibling->launches - sibling_launches0;
 	if(total_values_out) *total_values_out = total;
 	if(checksum_out) *checksum_out = h_sum;
 	return rc;

@@ -375,66 +375,103 @@ static bool parse_setup_packet(const uint8_t* p, size_t len, VorbisSetup& s, con
 // audio packet -> descriptors: hpp:1128-1211 (mode/window, floor Y reads, residue classification + cascade walk)
 // and the emit bookkeeping of VorbisStreamDecodeState (hpp:1019-1059, 1061-1067)
 // ---------------------------------------------------------------------------------------------------------------
-static void put_u32(std::vector<uint8_t>& v, uint32_t x) { const uint8_t* p = (const uint8_t*) &x; v.insert(v.end(), p, p + 4); }
-static void pad4(std::vector<uint8_t>& v) { while(v.size() & 3) v.push_back(0); }
-
+// The walk is the reference's (hpp:697-760): 8 passes over the partitions, a classification word every cb.dim partitions
+// in pass 0, then per partition and channel the vectors of the (class, pass) book. The hot loop keeps the bit position in
+// a register, decodes through the 10-bit first-level tables in place and writes the entry numbers straight into a
+// per-thread scratch array sized for the worst case (every partition coded in every pass with one-dimensional vectors).
 static bool decode_residue_submap(BitCursor& br, const VorbisSetup& s, const ResidueSetup& r, uint32_t nch, const uint8_t* used,
                                   uint32_t vlen, std::vector<uint8_t>& payload, const Fail& fail) {
 	// header: n_entries (patched at the end), cls[nch][parts], entries
 	const uint32_t lb = std::min(r.begin, vlen), le = std::min(r.end, vlen);
 	const uint32_t parts = (le - lb) / r.partition_size;
 	const size_t head = payload.size();
-	put_u32(payload, 0);
-	const size_t cls_at = payload.size();
-	payload.resize(cls_at + (((size_t) nch * parts + 3) & ~(size_t) 3), 0);
+	const size_t cls_bytes = ((size_t) nch * parts + 3) & ~(size_t) 3;
+	payload.resize(head + 4 + cls_bytes, 0);
+	const size_t cls_at = head + 4;
 	if(le == lb) return true;                            // hpp:704-705: nothing to read, no bits consumed
 	REQUIRE(r.classbook < s.books.size(), "residue: classbook out of range (hpp:700)");
 	const HuffBook& cb = s.books[r.classbook];
 	const uint32_t cw = cb.dim;
-	std::vector<uint8_t> cls((size_t) nch * (parts + cw), 0);
-	std::vector<uint32_t> entries;
-	entries.reserve((size_t) parts * nch * 8);
+	const uint32_t row = parts + cw;                     // classification row of one channel (a last word may overhang)
+	static thread_local std::vector<uint8_t> cls_buf;
+	static thread_local std::vector<uint32_t> ent_buf;
+	if(cls_buf.size() < (size_t) nch * row) cls_buf.resize((size_t) nch * row);
+	const size_t worst = (size_t) 8 * parts * nch * r.partition_size;
+	if(ent_buf.size() < worst) ent_buf.resize(worst);
+	uint8_t* cls = cls_buf.data();
+	memset(cls, 0, (size_t) nch * row);
+	uint32_t* out = ent_buf.data();
+	// (class, pass) -> book, vectors per partition; resolved once per call (<= 64 * 8 slots, a few used)
+	const HuffBook* vbook[POV_MAX_CLASSES * 8];
+	uint32_t vcount[POV_MAX_CLASSES * 8];
+	for(uint32_t i = 0; i < r.n_class * 8; ++i) {
+		const uint32_t book = r.books[i];
+		vbook[i] = nullptr; vcount[i] = 0;
+		if(book == POV_NO_BOOK || book >= s.books.size()) continue;      // out of range: reported when (if) it is used
+		vbook[i] = &s.books[book];
+		vcount[i] = r.partition_size / vbook[i]->dim;                    // dim | partition_size checked at setup conversion
+	}
+	const uint8_t* const data = br.data;
+	const uint64_t nbits = br.nbits, safe_end = nbits >= 64 ? nbits - 63 : 0;     // pos < safe_end: 8 readable bytes at the cursor
+	uint64_t pos = br.pos;
+	constexpr uint32_t kMask = (1u << HuffBook::kFastBits) - 1;
 	for(uint32_t pass = 0; pass < 8; ++pass) {
 		uint32_t pc = 0;
 		while(pc < parts) {
 			if(pass == 0) {
 				for(uint32_t j = 0; j < nch; ++j) {
 					if(!used[j]) continue;
+					br.pos = pos;
 					uint32_t t = cb.decode(br);
-					for(uint32_t i = cw; i > 0; --i) { cls[(size_t) j * (parts + cw) + i - 1 + pc] = (uint8_t) (t % r.n_class); t /= r.n_class; }
+					pos = br.pos;
+					for(uint32_t i = cw; i > 0; --i) { cls[(size_t) j * row + i - 1 + pc] = (uint8_t) (t % r.n_class); t /= r.n_class; }
 				}
 			}
 			for(uint32_t i = 0; i < cw && pc < parts; ++i, ++pc) {
 				for(uint32_t j = 0; j < nch; ++j) {
 					if(!used[j]) continue;
-					const uint32_t book = r.books[(uint32_t) cls[(size_t) j * (parts + cw) + pc] * 8 + pass];
+					const uint32_t slot = (uint32_t) cls[(size_t) j * row + pc] * 8 + pass;
+					const uint32_t book = r.books[slot];
 					if(book == POV_NO_BOOK) continue;
-					REQUIRE(book < s.books.size(), "residue: VQ book out of range");
-					const HuffBook& vb = s.books[book];
-					const uint32_t nvec = r.partition_size / vb.dim;     // dim | partition_size checked at setup conversion
-					for(uint32_t k = 0; k < nvec; ++k) {
-						const uint32_t e = vb.decode(br);
-						REQUIRE(vb.lookup_type != 0 && e < vb.n_entries, "residue: invalid VQ entry (hpp:369-370,739,748)");
-						entries.push_back(e);
+					REQUIRE(vbook[slot] != nullptr, "residue: VQ book out of range");
+					const HuffBook& vb = *vbook[slot];
+					REQUIRE(vb.lookup_type != 0 || vcount[slot] == 0, "residue: invalid VQ entry (hpp:369-370,739,748)");
+					const uint32_t* fast = vb.fast.data();
+					for(uint32_t k = vcount[slot]; k > 0; --k) {
+						uint32_t e;
+						uint32_t f = 0;
+						if(pos < safe_end) {                         // one unaligned load
+							uint64_t w;
+							memcpy(&w, data + (pos >> 3), 8);
+							f = fast[(uint32_t) (w >> (pos & 7)) & kMask];
+						}
+						if(f & 63) { pos += f & 63; e = f >> 6; }
+						else {                                        // long codeword or the tail of the packet
+							br.pos = pos;
+							e = vb.decode(br);
+							pos = br.pos;
+							REQUIRE(e < vb.n_entries, "residue: invalid VQ entry (hpp:369-370,739,748)");
+						}
+						*out++ = e;
 					}
 				}
 			}
 		}
 	}
-	for(uint32_t j = 0; j < nch; ++j) memcpy(&payload[cls_at + (size_t) j * parts], &cls[(size_t) j * (parts + cw)], parts);
-	const uint32_t ne = (uint32_t) entries.size();
+	br.pos = pos;
+	if(pos > nbits) br.overrun = true;
+	for(uint32_t j = 0; j < nch; ++j) memcpy(&payload[cls_at + (size_t) j * parts], &cls[(size_t) j * row], parts);
+	const uint32_t ne = (uint32_t) (out - ent_buf.data());
 	memcpy(&payload[head], &ne, 4);
+	const size_t at = payload.size();
 	if(s.entry_bits == 16) {
-		const size_t at = payload.size();
-		payload.resize(at + (size_t) ne * 2);
+		payload.resize(at + (((size_t) ne * 2 + 3) & ~(size_t) 3), 0);
 		uint16_t* o = (uint16_t*) &payload[at];
-		for(uint32_t i = 0; i < ne; ++i) o[i] = (uint16_t) entries[i];
+		for(uint32_t i = 0; i < ne; ++i) o[i] = (uint16_t) ent_buf[i];
 	} else {
-		const size_t at = payload.size();
 		payload.resize(at + (size_t) ne * 4);
-		memcpy(&payload[at], entries.data(), (size_t) ne * 4);
+		memcpy(&payload[at], ent_buf.data(), (size_t) ne * 4);
 	}
-	pad4(payload);
 	return true;
 }
 

@@ -10,6 +10,7 @@
 
 #include <stdint.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -61,9 +62,24 @@ struct MappingSetup {
 };
 struct ModeSetup { uint8_t blockflag = 0, mapping = 0; };
 
+// The codebooks of a setup (decode tables + VQ arenas, ~0.5 MB for the stereo fixture) are immutable once the setup
+// header is parsed: copies of a setup (one per decoded file of a corpus) share them.
+class BookTable {
+	std::shared_ptr<std::vector<HuffBook>> p_ = std::make_shared<std::vector<HuffBook>>();
+public:
+	void resize(size_t n) { p_ = std::make_shared<std::vector<HuffBook>>(n); }     // a fresh table, never the shared one
+	size_t size() const { return p_->size(); }
+	const HuffBook& operator[](size_t i) const { return (*p_)[i]; }
+	HuffBook& operator[](size_t i) { return (*p_)[i]; }
+	std::vector<HuffBook>::iterator begin() { return p_->begin(); }
+	std::vector<HuffBook>::iterator end() { return p_->end(); }
+	std::vector<HuffBook>::const_iterator begin() const { return p_->begin(); }
+	std::vector<HuffBook>::const_iterator end() const { return p_->end(); }
+};
+
 struct VorbisSetup {
 	uint32_t channels = 0, sample_rate = 0, blocksize[2] = {0, 0};
-	std::vector<HuffBook> books;
+	BookTable books;
 	std::vector<Floor1Setup> floors;
 	std::vector<ResidueSetup> residues;
 	std::vector<MappingSetup> mappings;

@@ -99,6 +99,24 @@ def test_corpus_decode_matches_single_file(ctx, golden):
     assert abs(chk - exp_chk) <= 1e-3 * max(1.0, abs(exp_chk)) + 0.05
 
 
+def test_corpus_decode_reuses_its_state_and_survives_a_bad_file(ctx, golden):
+    """pov_decode_corpus keeps its sibling context, slots and pinned staging pool on the context: a second call with
+    another thread count gives the same answer, a corrupt file is reported with the reference's message shape, and the
+    context keeps working afterwards."""
+    good = [_load("stereo44khz")] * 200
+    f1, t1, c1 = ctx.decode_corpus(good, host_threads=3)
+    f2, t2, c2 = ctx.decode_corpus(good, host_threads=16)       # more threads than chunks
+    assert list(f1) == list(f2) and t1 == t2 and abs(c1 - c2) <= 1e-6 * max(1.0, abs(c1))
+    assert t1 == 200 * golden["stereo44khz"]["pcm"].size
+    bad = bytearray(good[0]); bad[9000] ^= 0xFF                   # inside an audio page: the page CRC no longer matches
+    files = list(good[:100]) + [bytes(bad)] + list(good[:100])
+    with pytest.raises(RuntimeError) as ei:
+        ctx.decode_corpus(files, host_threads=8)
+    assert "file 100" in str(ei.value) and "check failed" in str(ei.value)
+    f3, t3, c3 = ctx.decode_corpus(good, host_threads=5)
+    assert list(f3) == list(f1) and t3 == t1 and abs(c3 - c1) <= 1e-6 * max(1.0, abs(c1))
+
+
 def test_reference_shaped_entry_point():
     L = lib.load()
     data = _load("mono44khz")

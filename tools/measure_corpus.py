@@ -29,7 +29,9 @@ def main():
     lo, hi = sharding.shard_range(a.files, world, rank)
     files = [ogg] * (hi - lo)
     ctx = SynthContext(local)
-    ctx.decode_corpus(files[:64], a.threads)            # warm-up: tables, allocations
+    # warm-up: tables, device arenas and the pinned staging pool of a long-lived decoder (pov_decode_corpus keeps them on the
+    # context); 2048 files = 32 chunks is enough for every worker to have allocated its staging buffers
+    ctx.decode_corpus(files[:min(2048, len(files))], a.threads)
     t0 = time.perf_counter()
     frames, total, chk = ctx.decode_corpus(files, a.threads)
     dt = time.perf_counter() - t0
