@@ -447,6 +447,8 @@ static void release_batch(pov_batch_handle* h) {
 	h->d_stage_off.release(); h->d_runs.release(); h->d_pcm.release(); h->d_status.release(); h->d_spectra.release();
 	h->st_final_ys.release(); h->st_flag.release(); h->st_floor.release(); h->st_floor_out.release();
 	h->st_env.release(); h->st_mdct.release();
+	if(h->h_derived) { cudaFreeHost(h->h_derived); h->h_derived = nullptr; h->h_derived_cap = 0; }
+	if(h->derived_copied) { cudaEventDestroy(h->derived_copied); h->derived_copied = nullptr; }
 }
 
 extern "C" void pov_batch_free(pov_ctx* ctx, pov_batch_handle* h) {
@@ -639,8 +641,23 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	CUDA_TRY(ctx, up(h->d_packets, b->packets, sizeof(pov_packet) * P));
 	CUDA_TRY(ctx, up(h->d_ys, b->ys, sizeof(uint16_t) * b->n_ys));
 	CUDA_TRY(ctx, up(h->d_payload, b->payload, b->payload_bytes));
-	CUDA_TRY(ctx, up(h->d_spec_off, h->spec_off.data(), sizeof(uint64_t) * P));
-	CUDA_TRY(ctx, up(h->d_runs, h->runs.data(), sizeof(DevRun) * h->runs.size()));
+	{
+		const size_t b_spec = sizeof(uint64_t) * P, o_runs = (b_spec + 15) & ~(size_t) 15, b_runs = sizeof(DevRun) * h->runs.size();
+		const size_t need = std::max<size_t>(o_runs + b_runs, 16);
+		if(h->derived_copied) CUDA_TRY(ctx, cudaEventSynchronize(h->derived_copied));     // the previous upload through this handle has read them
+		else CUDA_TRY(ctx, cudaEventCreateWithFlags(&h->derived_copied, cudaEventDisableTiming));
+		if(need > h->h_derived_cap) {
+			if(h->h_derived) cudaFreeHost(h->h_derived);
+			h->h_derived = nullptr; h->h_derived_cap = 0;
+			CUDA_TRY(ctx, cudaHostAlloc(&h->h_derived, need + need / 4, cudaHostAllocDefault));
+			h->h_derived_cap = need + need / 4;
+		}
+		if(b_spec) memcpy(h->h_derived, h->spec_off.data(), b_spec);
+		if(b_runs) memcpy((uint8_t*) h->h_derived + o_runs, h->runs.data(), b_runs);
+		CUDA_TRY(ctx, up(h->d_spec_off, h->h_derived, b_spec));
+		CUDA_TRY(ctx, up(h->d_runs, (uint8_t*) h->h_derived + o_runs, b_runs));
+		CUDA_TRY(ctx, cudaEventRecord(h->derived_copied, st));
+	}
 	CUDA_TRY(ctx, h->d_pcm.reserve(std::max<size_t>(sizeof(float) * b->pcm_floats, 16)));
 	CUDA_TRY(ctx, h->d_status.reserve(std::max<size_t>(sizeof(uint32_t) * P, 16)));
 	CUDA_TRY(ctx, cudaMemsetAsync(h->d_status.ptr, 0, sizeof(uint32_t) * P, st));

@@ -90,6 +90,10 @@ struct pov_batch_handle {
 	std::vector<DevRun> runs;
 	DevBuf d_streams, d_packets, d_ys, d_payload, d_spec_off, d_stage_off, d_runs, d_pcm, d_status, d_spectra;
 	DevBuf st_final_ys, st_flag, st_floor, st_floor_out, st_env, st_mdct;
+	// pinned copy of the derived arrays (spec_off | runs): sources of asynchronous copies, so they must not be pageable
+	// (a pageable source makes the "async" copy wait for the stream) and must outlive the copy (derived_copied)
+	void* h_derived = nullptr; size_t h_derived_cap = 0;
+	cudaEvent_t derived_copied = nullptr;
 };
 
 struct StageHost {                // whole stage arrays on the host (debug dump writer)
