@@ -244,7 +244,9 @@ int  pov_ogg_vorbis_decode_memory(pov_ctx* ctx, const uint8_t* data, size_t len,
                                   pov_decoded* out);
 void pov_decoded_free(pov_decoded* d);
 
-/* Decode a corpus of independent files with `host_threads` front-end threads feeding this context's GPU.
+/* Decode a corpus of independent files with `host_threads` front-end threads (0 = all cores but one, which is left to
+ * the calling thread) feeding this context's GPU. The context keeps the sibling stream, device arenas and pinned
+ * staging buffers of the call for the next one; POV_CORPUS_TIMING=1 prints where the calling thread's time went.
  * Returns per-file frame counts (frames_out[n_files], may be NULL) and the total number of PCM values. */
 int  pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* data, const size_t* len,
                        uint32_t host_threads, uint64_t* frames_out, uint64_t* total_values_out,

@@ -314,7 +314,9 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
                                  uint32_t host_threads, uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out) {
 	if(!ctx || (n_files && (!data || !len))) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
-	if(host_threads == 0) host_threads = std::max(1u, std::thread::hardware_concurrency());
+	// automatic: every core but one — the calling thread validates, queues and retires chunks and must not be time-sliced
+	// against the parsers (measured on 16 cores: 15 workers 6.8e9 samples/s and stable, 16 workers 2.6-3.7e9)
+	if(host_threads == 0) { const uint32_t hc = std::thread::hardware_concurrency(); host_threads = hc > 1 ? hc - 1 : 1; }
 	uint32_t files_per_chunk = 64;
 	if(const char* e = getenv("POV_CORPUS_CHUNK")) files_per_chunk = std::max(1, atoi(e));
 	const uint32_t n_chunks = (n_files + files_per_chunk - 1) / files_per_chunk;

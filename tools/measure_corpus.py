@@ -28,15 +28,17 @@ def main():
     ogg = open(os.path.join(ROOT, "tests", "golden", "test.stereo44khz.ogg"), "rb").read()
     lo, hi = sharding.shard_range(a.files, world, rank)
     files = [ogg] * (hi - lo)
+    # host threads of this rank: its share of the node's cores, minus one for the thread that feeds the GPU
+    threads = a.threads or max(1, (os.cpu_count() or 2) // world - 1)
     ctx = SynthContext(local)
     # warm-up: tables, device arenas and the pinned staging pool of a long-lived decoder (pov_decode_corpus keeps them on the
     # context); 2048 files = 32 chunks is enough for every worker to have allocated its staging buffers
-    ctx.decode_corpus(files[:min(2048, len(files))], a.threads)
+    ctx.decode_corpus(files[:min(2048, len(files))], threads)
     t0 = time.perf_counter()
-    frames, total, chk = ctx.decode_corpus(files, a.threads)
+    frames, total, chk = ctx.decode_corpus(files, threads)
     dt = time.perf_counter() - t0
     out = {"config": "config5: stereo fixture x %d (rank %d/%d decodes %d files)" % (a.files, rank, world, hi - lo),
-           "host_threads": a.threads or os.cpu_count(), "samples": total, "seconds": dt, "samples_per_s": total / dt,
+           "host_threads": threads, "samples": total, "seconds": dt, "samples_per_s": total / dt,
            "frames_per_file": int(frames[0]) if len(frames) else 0, "checksum": chk}
     if rank == 0 and not a.no_reference:
         exe = os.path.join(ROOT, "oracle", "_ref", "ref_decode_bench")
