@@ -139,30 +139,34 @@ __global__ void __launch_bounds__(kResThreads) k_residue_apply(DevBatchView b, f
 			if(threadIdx.x == blockDim.x - 1) s_carry += s_scan[threadIdx.x];
 			__syncthreads();
 		}
-		// apply: one thread per (partition, channel), passes in order
-		for(uint32_t w = threadIdx.x; w < parts * vch; w += blockDim.x) {
+		// apply: one thread per BIN. A bin receives at most one addend per pass (hpp:734-752), so it can gather its own
+		// addends in pass order: the same additions, in the same order, as the reference's vector-by-vector accumulation
+		// (which starts from the zero-initialised vector), with every thread of the block busy instead of one per partition.
+		for(uint32_t idx = threadIdx.x; idx < parts * vch * psize; idx += blockDim.x) {
+			const uint32_t o = idx % psize, w = idx / psize;
 			const uint32_t j = w % vch, part = w / vch;
 			const bool ch_used = (rs.type == 2) ? true : ((used >> chs[j]) & 1);
 			if(!ch_used) continue;
-			float* v = acc + (size_t) j * vlen + lb + part * psize;
 			const uint32_t cl = cls[j * parts + part];
+			float sum = 0.f;
 			for(uint32_t pass = 0; pass < 8; ++pass) {
 				const uint32_t book = rs.books[cl * 8 + pass];
 				if(book == POV_NO_BOOK) continue;
 				if(book >= su.n_codebooks) { bad |= POV_PKT_VQ_ENTRY; continue; }
 				const DevCodebook cb = su.codebooks[book];
 				const uint32_t nvec = psize / cb.dim;
-				uint32_t cur = cursor[(pass * parts + part) * vch + j];
-				for(uint32_t k = 0; k < nvec; ++k, ++cur) {
-					if(cur >= n_entries) { bad |= POV_PKT_VQ_ENTRY; break; }
-					const uint32_t e = (su.entry_bits == 16) ? reinterpret_cast<const uint16_t*>(ent)[cur]
-					                                         : reinterpret_cast<const uint32_t*>(ent)[cur];
-					if(cb.lookup_type == 0 || e >= cb.n_entries) { bad |= POV_PKT_VQ_ENTRY; continue; }
-					const float* vec = cb.vq + (size_t) e * cb.dim;
-					if(rs.type == 0) for(uint32_t l = 0; l < cb.dim; ++l) v[k + l * nvec] += __ldg(&vec[l]);
-					else             for(uint32_t l = 0; l < cb.dim; ++l) v[k * cb.dim + l] += __ldg(&vec[l]);
-				}
+				// type 0: v[k + l*nvec] (hpp:734-743); types 1/2: v[k*dim + l] (hpp:744-752)
+				uint32_t k, l;
+				if(rs.type == 0) { l = o / nvec; k = o - l * nvec; if(nvec == 0 || l >= cb.dim) continue; }
+				else { k = o / cb.dim; l = o - k * cb.dim; if(k >= nvec) continue; }
+				const uint32_t cur = cursor[(pass * parts + part) * vch + j] + k;
+				if(cur >= n_entries) { bad |= POV_PKT_VQ_ENTRY; continue; }
+				const uint32_t e = (su.entry_bits == 16) ? reinterpret_cast<const uint16_t*>(ent)[cur]
+				                                         : reinterpret_cast<const uint32_t*>(ent)[cur];
+				if(cb.lookup_type == 0 || e >= cb.n_entries) { bad |= POV_PKT_VQ_ENTRY; continue; }
+				sum += __ldg(&cb.vq[(size_t) e * cb.dim + l]);
 			}
+			acc[(size_t) j * vlen + lb + part * psize + o] = sum;
 		}
 		__syncthreads();
 		// scatter to the channel-major dense layout (de-interleave for type 2, hpp:690-692)
