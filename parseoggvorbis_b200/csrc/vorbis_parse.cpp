@@ -575,6 +575,9 @@ static bool parse_id_packet(const uint8_t* p, size_t len, VorbisSetup& s, const 
 	REQUIRE(h[22] == 1, "id header: framing flag (hpp:1292)");
 	REQUIRE(rd32(h) == 0, "id header: vorbis_version != 0 (hpp:1293)");
 	s.channels = h[4];
+	// the reference takes any uint8_t channel count (hpp:107); this build's descriptors carry per-channel bit masks and
+	// fixed [POV_MAX_CHANNELS] arrays, so more channels are refused here, before any audio packet is walked
+	REQUIRE(s.channels >= 1 && s.channels <= POV_MAX_CHANNELS, "id header: %u channels (this build supports 1..%u)", s.channels, POV_MAX_CHANNELS);
 	s.sample_rate = rd32(h + 5);
 	s.blocksize[0] = 1u << (h[21] & 15);
 	s.blocksize[1] = 1u << (h[21] >> 4);
