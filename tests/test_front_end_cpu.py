@@ -104,6 +104,29 @@ def test_error_behaviour_matches_reference_library():
         assert (ref_rc != 0) == (ours_rc != 0), (len(data), err.value)
 
 
+def _ogg_crc(page: bytes) -> int:
+    crc = 0
+    for byte in page:     # poly 0x04c11db7, MSB first, init 0 (hpp:92-98)
+        crc ^= byte << 24
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x04C11DB7) & 0xFFFFFFFF if crc & 0x80000000 else (crc << 1) & 0xFFFFFFFF
+    return crc
+
+
+def test_more_channels_than_the_descriptors_hold_are_refused_in_the_id_header():
+    """The reference takes any uint8 channel count (hpp:107); this build's descriptors hold 8. A stream that announces
+    more must be refused at its id header, before an audio packet is walked with per-channel arrays of 8."""
+    data = bytearray(_load("mono44khz"))
+    nseg = data[26]
+    body = sum(data[27:27 + nseg])
+    first = 27 + nseg                     # id packet: 0x01 "vorbis" version(4) channels(1) ...
+    assert data[first:first + 7] == b"\x01vorbis"
+    data[first + 11] = 9
+    page = bytearray(data[:first + body]); page[22:26] = b"\0\0\0\0"
+    data[22:26] = _ogg_crc(bytes(page)).to_bytes(4, "little")
+    _expect_error(data, "9 channels")
+
+
 def test_crc_known_answer():
     # Ogg CRC of the first page of the bundled fixture equals the value stored in its header (hpp:92-98)
     data = _load("stereo44khz")
