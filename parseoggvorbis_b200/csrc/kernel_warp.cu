@@ -719,8 +719,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			float2* T = slotA + par * kSlotF2;                       // A+B or B+C
 			float2* surv = slotA + par * (2 * kSlotF2);              // A or C: where this step's last D lo half stays
 			float2* slotB = slotA + kSlotF2;
+			// A long FFT of Q1 < 512 points needs fewer than 32 lanes: such long packets are transformed 512/Q1 at a time, exactly
+			// like the groups of short packets (D of FFT f packed at T + Q f, last lo half moved to the survivor slot).
+			constexpr bool kLongGrouped = LPF1 < 32;
+			constexpr int kGroupLong = 32 / LPF1;
+			const bool grouped = !flag || kLongGrouped;
 			int count = 1;
-			if(!flag) while(count < (int) P.group_short && first + count < run_n && (wp[first + count].meta & 0xffu) == mode) ++count;
+			{
+				const int cap = flag ? (kLongGrouped ? kGroupLong : 1) : (int) P.group_short;
+				while(count < cap && first + count < run_n && (wp[first + count].meta & 0xffu) == mode) ++count;
+			}
 
 			// pull the next step's spectra towards L2 while this step computes: one 128-byte line per lane and channel
 			if(first + count < run_n) {
@@ -730,15 +738,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				const FastCouple* ncp = &tb->couple[tb->mode_map[nmode]][ch];
 				if(lane < (int) ncp->nl) prefetch_l2_bulk(spec_base + nw.spec_rel + (int) (ncp->ch[lane] * nhalf), nhalf * 4u);
 			}
-			// ================= one long packet or a group of short packets: Q/16 lanes per FFT, same code for both classes,
+			// ================= one 2048-sample packet or a group of smaller packets: Q/16 lanes per FFT, same code for all classes,
 			//                   geometry in registers (256/2048: the whole warp is one 512-point FFT, or eight 64-point FFTs) ====
 			const int Qs = flag ? Q1 : Q0;
 			const int lpf = flag ? LPF1 : LPF0;
-			// lpf is a power of two. A long step holds ONE FFT: with fewer than 32 lanes per FFT the other lanes mirror it
-			// (same addresses, same values) instead of idling, so that every lane reaches the warp barriers of the passes
+			// lpf is a power of two; lanes whose FFT index f is beyond the group (f >= count) still walk the passes on their own
+			// (unused) part of the work area, so that every lane reaches the warp barriers
 			const int u = lane & (lpf - 1);
-			const int f = flag ? 0 : lane / lpf;
-			const uint32_t cstride = flag ? 0u : P.short_curve_stride, rcap = flag ? 32u : tb->short_posts_cap, nwords = (uint32_t) Qs / 16u;
+			const int f = lane / lpf;                    // 0 for a whole-warp FFT
+			constexpr uint32_t kLongCurveBytes = 32u * 8u + (uint32_t) (Q1 / 16) * 8u;
+			const uint32_t cstride = flag ? (kLongGrouped ? kLongCurveBytes : 0u) : P.short_curve_stride, rcap = flag ? 32u : tb->short_posts_cap,
+			               nwords = (uint32_t) Qs / 16u;
 			for(int g = 0; g < count; ++g) {
 				const int md = curve_mode(tb, mapping, wp[first + g].meta >> 16, ch);
 				unsigned char* cv = curves + (size_t) g * cstride;
@@ -752,8 +762,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				spectral_dispatch<kMaxNL>(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u);
 			__syncwarp();
 			// last pass output: long: lo half -> survivor slot, hi half -> slot B; short: D of FFT f packed at T + Q0 f (lo | hi)
-			if(flag) fft_passes<Q1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB));
-			else {
+			if(flag && !kLongGrouped) fft_passes<Q1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB));
+			else if(flag) {
+				const uint32_t lo = Ts + (uint32_t) f * (uint32_t) (Q1 * 8);
+				fft_passes<Q1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, lo, lo + (uint32_t) (Q1 / 2 * 8));
+			} else {
 				const uint32_t lo = Ts + (uint32_t) f * (uint32_t) (Q0 * 8);
 				fft_passes<Q0>(Tfs, u, tws, smem_u32(smem + M::kOffFp0), rots, lo, lo + (uint32_t) (Q0 / 2 * 8));
 			}
@@ -768,8 +781,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				// hpp:844-847: short blocks always use blocksize0 slopes; long blocks follow their own prev/next flags
 				const int lc = (flag && (wflags & 1u)) ? N1 / 2 : N0 / 2;
 				const int rc = (flag && (wflags & 2u)) ? N1 / 2 : N0 / 2;
-				const float* cur_lo = flag ? reinterpret_cast<const float*>(surv) : Dstep + (size_t) g * 2 * Q;
-				const float* cur_hi = flag ? reinterpret_cast<const float*>(slotB) : cur_lo + Q;
+				const float* cur_lo = !grouped ? reinterpret_cast<const float*>(surv) : Dstep + (size_t) g * 2 * Q;
+				const float* cur_hi = !grouped ? reinterpret_cast<const float*>(slotB) : cur_lo + Q;
 				const bool emits = prev_valid && emit > 0 && (run.first_packet + (uint32_t) (first + g)) != st.first_packet;
 				if(emits) {
 					const uint64_t chan_base = chan0 + w.pcm_rel;
@@ -794,17 +807,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				}
 				prev_valid = 1; prev_n = n; prev_right = rc; prev_lo = cur_lo;
 			}
-			if(!flag && prev_lo != reinterpret_cast<const float*>(surv)) {
-				// short step: move the last packet's D lo half (Q0/2 float2) into the survivor slot (ranges may overlap:
+			if(grouped && prev_lo != reinterpret_cast<const float*>(surv)) {
+				// grouped step: move the last packet's D lo half (Q/2 float2) into the survivor slot (ranges may overlap:
 				// every lane reads all of its elements before anyone writes)
-				constexpr int kPer = (Q0 / 2 + 31) / 32;
+				constexpr int kPer0 = (Q0 / 2 + 31) / 32, kPer1 = kLongGrouped ? (Q1 / 2 + 31) / 32 : 1;
+				constexpr int kPer = kPer0 > kPer1 ? kPer0 : kPer1;
+				const int per = flag ? kPer1 : kPer0;       // elements beyond Q/2 are never read back, but stay inside the work area
 				float2 v[kPer];
 				__syncwarp();
 #pragma unroll
-				for(int i = 0; i < kPer; ++i) v[i] = reinterpret_cast<const float2*>(prev_lo)[lane + 32 * i];
+				for(int i = 0; i < kPer; ++i) if(i < per) v[i] = reinterpret_cast<const float2*>(prev_lo)[lane + 32 * i];
 				__syncwarp();
 #pragma unroll
-				for(int i = 0; i < kPer; ++i) surv[lane + 32 * i] = v[i];
+				for(int i = 0; i < kPer; ++i) if(i < per) surv[lane + 32 * i] = v[i];
 				__syncwarp();
 				prev_lo = reinterpret_cast<const float*>(surv);
 			}
@@ -835,6 +850,7 @@ size_t warp_kernel_smem_bytes(uint32_t bs0, uint32_t bs1, uint32_t short_posts_c
 	const uint32_t stride = short_posts_cap * 8u + (Q0 / 16u) * 8u;       // records + rank-table words of one short curve
 	uint32_t group = 512u / Q0;                                           // short FFTs a warp transforms at once (Q0/16 lanes each)
 	uint32_t cb = 32u * 8u + (Q1 / 16u) * 8u;                             // one long curve: 32 records + rank table
+	if(Q1 < 512u) cb *= 512u / Q1;                                         // long packets of < 512 points are grouped too (kLongGrouped)
 	while(group > 1 && group * stride > wk::kCurveMax) --group;
 	if(group * stride > cb) cb = group * stride;
 	cb = (cb + 15u) & ~15u;
