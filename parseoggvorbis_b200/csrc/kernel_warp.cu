@@ -1,4 +1,4 @@
-// Production path for the common 256/2048 setups: a persistent, warp-autonomous synthesis kernel.
+// Production path for every pair of block sizes from {256, 512, 1024, 2048}: a persistent, warp-autonomous synthesis kernel.
 //
 //   floor1 unwrap/render -> nonzero propagate -> inverse coupling -> floor multiply -> inverse MDCT
 //   -> window -> overlap-add -> PCM
@@ -6,7 +6,7 @@
 //  521-591, 1174-1180, 1213-1268, 1008-1059; the IMDCT contract is src/mdct.h:105.)
 //
 // Design (see DESIGN.md "kernel_warp"):
-//   * One CTA per SM, 16 warps, resident for the whole launch. Every table a packet needs (inverse-dB table, window
+//   * One CTA per SM, 20 warps (96 registers each), resident for the whole launch. Every table a packet needs (inverse-dB table, window
 //     slopes, FFT twiddles, DCT-IV rotations, floor neighbour tables, coupling programs) is brought
 //     into shared memory ONCE per CTA with TMA bulk copies and shared by all warps.
 //   * The unit of work is (run of <= 31 consecutive packets of one stream, one channel), taken from a global atomic
@@ -15,9 +15,10 @@
 //     (they are L1/L2 hits: the sibling warp reads the same lines), so warps never exchange data.
 //   * The Q = n/4 point complex FFT of a long block lives in registers: 16 points per lane, three radix-8 passes,
 //     two transposes through a warp-private shared buffer whose layouts make every access conflict free.
-//     Spectra are read straight from HBM with 64-bit loads arranged so that the two bins a pre-rotated point needs
-//     arrive in the same lane (points j and Q-1-j are handled together); the post-rotation uses the same pairing to
-//     emit the D array with 64-bit stores.
+//     Spectra are read straight from HBM with 128-bit loads arranged so that the bins a pair of pre-rotated points and
+//     their mirror images need arrive in the same lane (points 2q, 2q+1, Q-2-2q, Q-1-2q are handled together); the
+//     post-rotation pairs butterflies k and Q-1-k to emit the D array with 64-bit stores. Smaller FFTs (Q = 64..256) use
+//     Q/16 lanes each and are transformed several packets at a time.
 //   * Overlap-add exploits the TDAC symmetry: one lane produces samples j..j+3 and n/2-4-j..n/2-1-j from the same four
 //     128-bit shared loads, halving the shared-memory traffic of the window stage.
 // HBM traffic is the algorithmic minimum: every spectrum is read once, every PCM sample written once (+ one halo
@@ -332,8 +333,8 @@ __device__ __forceinline__ float4 curve_quad(const uint2* __restrict__ rec, cons
 //   pass 1 (over j1): lane u owns butterflies j0 = u and 7-u                in: j0 + 8 j1        out A1[k0*9 + j0]
 //   pass 2 (over j0): lane u owns butterflies k0 = u and 7-u                in: A1               out D as float2[Q] at f*64
 // Every access of a pass is either contiguous over the lanes or hits 16 distinct 8-byte bank pairs per half warp.
-// The passes are size-generic and NOT inlined: all block sizes share ~500 instructions of FFT code, which keeps the hot
-// loop of 16 independently running warps inside the instruction cache.
+// Every pass has one call site per block class and is inlined (no call ABI, strides become immediates); the hot loop of
+// the 20 independently running warps is ~1700 instructions, just inside the 32 KB L1.5 instruction cache.
 __device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ tw, int half) {   // tw: (W^j, W^2j); tw + half: (W^3j, W^4j)
 	const float4 w12 = *reinterpret_cast<const float4*>(tw), w34 = *reinterpret_cast<const float4*>(tw + half);
 	const float2 w1 = make_float2(w12.x, w12.y), w2 = make_float2(w12.z, w12.w);
