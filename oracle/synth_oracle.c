@@ -322,6 +322,34 @@ void por_imdct_fast(const float* in, uint32_t n, float* out) {
  * window — src/ParseOggVorbis.hpp:837-862. The reference mixes float and double: x is rounded to float, the
  * products are formed in double, sinf() then takes the float conversion of that double.
  * ---------------------------------------------------------------------------------------------------------- */
+/* The reference's own transform as an IMDCT callback without any interpreter in the loop: the binding hands over the
+ * addresses of mdct_init / mdct_backward (src/mdct.h:99-105) from oracle/_ref; plans are per thread because the
+ * lookup struct (src/mdct.h:87-97: two ints, two table pointers, a float) is built lazily here. */
+typedef void (*ref_mdct_init_fn)(void* lookup, int n);
+typedef void (*ref_mdct_backward_fn)(void* lookup, float* in, float* out);
+static ref_mdct_init_fn g_ref_mdct_init;
+static ref_mdct_backward_fn g_ref_mdct_backward;
+
+void por_bind_reference_mdct(void* init_fn, void* backward_fn) {
+	g_ref_mdct_init = (ref_mdct_init_fn) init_fn;
+	g_ref_mdct_backward = (ref_mdct_backward_fn) backward_fn;
+}
+
+void por_imdct_reference(void* user, uint32_t n, const float* in, float* out) {
+	static __thread struct { uint32_t n; void* lookup[8]; } plans[8];      /* 64 bytes of lookup storage, pointer aligned */
+	static __thread int n_plans;
+	(void) user;
+	int k = 0;
+	while(k < n_plans && plans[k].n != n) ++k;
+	if(k == n_plans) {
+		if(n_plans == 8) k = 0; else ++n_plans;      /* more than 8 block sizes per thread: recycle (tables leak, test code) */
+		memset(&plans[k], 0, sizeof plans[k]);
+		plans[k].n = n;
+		g_ref_mdct_init(plans[k].lookup, (int) n);
+	}
+	g_ref_mdct_backward(plans[k].lookup, (float*) in, out);
+}
+
 void por_window(uint32_t bs0, uint32_t bs1, int blockflag, int prev, int next, float* out) {
 	uint32_t n = blockflag ? bs1 : bs0;
 	if(!blockflag) { prev = 0; next = 0; } /* hpp:876: flags only matter for long blocks */

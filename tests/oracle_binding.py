@@ -124,15 +124,14 @@ def reference_imdct(x):
 
 
 def _ref_imdct_cb():
+    """The reference's mdct_backward as the oracle's IMDCT callback: a C function of the oracle library that calls straight
+    into oracle/_ref (no Python in the loop, so threads of the CPU baseline really run side by side)."""
     ref = reference_lib()
-
-    def cb(user, n, pin, pout):
-        if n not in _ref_plans:
-            l = _MdctLookup()
-            ref.mdct_init(C.byref(l), n)
-            _ref_plans[n] = l
-        ref.mdct_backward(C.byref(_ref_plans[n]), pin, pout)
-    return IMDCT_FN(cb)
+    L = lib()
+    L.por_bind_reference_mdct.argtypes = [C.c_void_p, C.c_void_p]
+    L.por_bind_reference_mdct.restype = None
+    L.por_bind_reference_mdct(C.cast(ref.mdct_init, C.c_void_p), C.cast(ref.mdct_backward, C.c_void_p))
+    return C.cast(L.por_imdct_reference, IMDCT_FN)
 
 
 def synth_batch(setups, batch: abi.Batch, imdct="fast", capture=False):
