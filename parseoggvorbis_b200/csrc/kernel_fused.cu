@@ -70,7 +70,6 @@ struct FusedParams {
 	uint32_t slot_floats;    // floats of one spectra buffer = C_max * blocksize1/2
 	uint32_t curve_bytes;    // size of the curve-block region
 	uint32_t table_float2;   // float2 slots of the shared-memory twiddle/rotation tables
-	uint32_t dbg_skip;       // timing experiments only (POV_DBG_SKIP): 1 floor, 2 spectral, 4 fft, 8 ola, 16 tma
 };
 
 // Compact per-packet descriptor kept in shared memory for the whole run (loaded once in the prologue), so that the
@@ -458,10 +457,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParam
 	fa.pk = s_pk; fa.curves = curves; fa.fscr = fscr;
 	fa.floor_cap[0] = P.floor_cap[0]; fa.floor_cap[1] = P.floor_cap[1]; fa.scratch_cap = P.scratch_cap;
 	fa.bs[0] = bs0; fa.bs[1] = bs1; fa.C = C;
-	auto floor_task = [&](const StepCtx& sx, int f) { if(!(P.dbg_skip & 1)) floor_task_fn(fa, sx.first, sx.flag, sx.mode, f, warp, lane); };
+	auto floor_task = [&](const StepCtx& sx, int f) { floor_task_fn(fa, sx.first, sx.flag, sx.mode, f, warp, lane); };
 
 	StepCtx cur = make_step(0);
-	if(threadIdx.x == 0 && cur.count && !(P.dbg_skip & 16)) issue_loads(cur);
+	if(threadIdx.x == 0 && cur.count) issue_loads(cur);
 	// prologue: curves of the first step (later steps get theirs during the previous step's overlap-add stage)
 	for(int f = warp; f < (int) cur.count * C; f += nwarps) floor_task(cur, f);
 	uint32_t phase = 0;
@@ -488,12 +487,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParam
 
 		// ---- wait for this step's spectra (TMA): one warp polls, the barrier releases everyone; it also publishes the
 		//      curve blocks of this step, which were built during the previous step's stage 4 (or the prologue) ----
-		if(warp == 0 && !(P.dbg_skip & 16)) mbar_wait(&s_bar, phase);
+		if(warp == 0) mbar_wait(&s_bar, phase);
 		phase ^= 1;
 		__syncthreads();
 
 		// ---- stage 2: floor evaluation + coupling + floor multiply + pre-rotation -> T ----
-		if(!(P.dbg_skip & 2)) {
+		{
 			const float2* rot = flag ? s_rot[1] : s_rot[0];
 			const float2 c1 = flag ? rc1[1] : rc1[0], c6 = flag ? rc6[1] : rc6[0];
 			const int lq = log2Q - 2;
@@ -513,10 +512,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParam
 		}
 		__syncthreads();
 		// the spectra buffer is free again: prefetch the next step's spectra behind stages 3-4
-		if(threadIdx.x == 0 && nxt.count && !(P.dbg_skip & 16)) issue_loads(nxt);
+		if(threadIdx.x == 0 && nxt.count) issue_loads(nxt);
 
 		// ---- stage 3: FFT passes + post-rotation -> D (lo / hi halves) ----
-		if(!(P.dbg_skip & 4)) {
+		{
 			const float2* rot = flag ? s_rot[1] : s_rot[0];
 			const float2* tw8 = flag ? s_tw8[1] : s_tw8[0];
 			const float2* TWP = su->fftp[flag];
@@ -558,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_fused_synth(FusedParam
 			const float* cur_lo = Dlo_cur + (size_t) g * C * Q;
 			const float* cur_hi = Dhi + (size_t) g * C * Q;
 			const bool emits = prev_valid && emit > 0 && (run.first_packet + (uint32_t) (first + g)) != st.first_packet;
-			if(emits && ola_n > 0 && !(P.dbg_skip & 8)) {
+			if(emits && ola_n > 0) {
 				OlaGeom G;
 				G.Hp = prev_n / 4; G.H = Q;
 				G.shift = Q - prev_n / 4;
@@ -665,7 +664,6 @@ cudaError_t launch_fused(const DevBatchView& b, const DevRun* runs, uint32_t n_r
 	fused_layout(max_channels, max_blocksize, min_blocksize, floor_cap, table_float2, P, threads, smem);
 	P.b = b;
 	P.runs = runs;
-	{ const char* e = getenv("POV_DBG_SKIP"); P.dbg_skip = e ? (uint32_t) atoi(e) : 0; }
 	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 	cudaError_t e;
 	if(threads == 128) e = only_256_2048 ? launch_variant<128, 5, true>(P, n_runs, smem, st) : launch_variant<128, 5, false>(P, n_runs, smem, st);
