@@ -357,3 +357,30 @@ def test_warp_kernel_block_size_pairs_stereo(ctx, bs):
     assert ctx.kernel_name(bh) == "k_warp_synth"
     bh.free()
     _check_against_oracle(ctx, setup, batch, stages=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [(256, 512), (512, 1024), (1024, 2048)])
+def test_interleaved_layout_block_size_pairs(ctx, bs):
+    """Interleaved PCM is a second instantiation of the warp kernel: it must equal the planar result bit for bit for the
+    grouped small-block geometries too (several long FFTs per warp, strided stores)."""
+    rng = np.random.default_rng(bs[0] + 3 * bs[1])
+    setup = workloads.make_setup(2, bs, 22050, couplings=[(0, 1)])
+    plans = [workloads.plan_stream(workloads.block_sequence(150, rng, p_short=0.2), setup.blocksize, trim_last=int(rng.integers(0, 30)))
+             for _ in range(2)]
+    out = {}
+    for layout in (abi.POV_PCM_PLANAR, abi.POV_PCM_INTERLEAVED):
+        batch = workloads.build_dense_batch(setup, plans, np.random.default_rng(11), pcm_layout=layout)
+        batch.streams["setup_id"] = ctx.register_setup(setup)
+        bh = ctx.upload(batch)
+        assert ctx.kernel_name(bh) == "k_warp_synth"
+        ctx.run(bh)
+        out[layout] = (ctx.fetch_pcm(bh).copy(), batch.streams.copy())
+        bh.free()
+    planar, st = out[abi.POV_PCM_PLANAR]
+    inter, _ = out[abi.POV_PCM_INTERLEAVED]
+    for s in st:
+        base, frames = int(s["pcm_base"]), int(s["pcm_frames"])
+        a = planar[base:base + 2 * frames].reshape(2, frames)
+        b = inter[base:base + 2 * frames].reshape(frames, 2)
+        assert np.array_equal(a, b.T)
