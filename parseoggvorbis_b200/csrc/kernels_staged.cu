@@ -73,8 +73,14 @@ constexpr int kResThreads = 256;
 
 __global__ void __launch_bounds__(kResThreads) k_residue_apply(DevBatchView b, float* __restrict__ spectra_out) {
 	extern __shared__ __align__(16) unsigned char res_smem[];
-	__shared__ uint32_t s_scan[kResThreads];
+	__shared__ uint32_t s_scan[kResThreads / 32];
 	__shared__ uint32_t s_carry;
+	// setup tables the inner loops index for every bin and pass: kept in shared memory so that the dependent chain of a
+	// (bin, pass) is shared-memory lookups plus two global loads (entry number, VQ value)
+	__shared__ const float* s_vq[POV_MAX_CODEBOOKS];
+	__shared__ uint32_t s_nent[POV_MAX_CODEBOOKS];          // 0: no lookup table (lookup_type 0) -> every entry is invalid
+	__shared__ uint16_t s_dim[POV_MAX_CODEBOOKS];
+	__shared__ uint8_t s_books[POV_MAX_CLASSES * 8];
 	const uint32_t p = blockIdx.x;
 	const pov_packet pk = b.packets[p];
 	const DevSetup& su = setup_of(b, pk);
@@ -84,6 +90,13 @@ __global__ void __launch_bounds__(kResThreads) k_residue_apply(DevBatchView b, f
 	float* out = spectra_out + b.spec_off[p];
 	float* acc = reinterpret_cast<float*>(res_smem);                 // [nch*half] working vector of one submap
 	uint32_t* cursor = reinterpret_cast<uint32_t*>(acc + (size_t) C * half);   // [8*parts*nch] exclusive offsets
+	const uint32_t n_books = min(su.n_codebooks, (uint32_t) POV_MAX_CODEBOOKS);
+	for(uint32_t i = threadIdx.x; i < n_books; i += blockDim.x) {
+		const DevCodebook cb = su.codebooks[i];
+		s_vq[i] = cb.vq;
+		s_nent[i] = cb.lookup_type ? cb.n_entries : 0u;
+		s_dim[i] = (uint16_t) min(cb.dim, 0xFFFFu);
+	}
 
 	// nonzero propagate (hpp:1174-1180) decides which channels the residue touches
 	uint32_t used = pk.floor_used;
@@ -98,8 +111,9 @@ __global__ void __launch_bounds__(kResThreads) k_residue_apply(DevBatchView b, f
 		for(uint32_t c = 0; c < C; ++c) if(mp.mux[c] == s) chs[nch++] = c;
 		const DevResidue& rs = su.residues[mp.submap_residue[s]];
 		// type 2 decodes ONE interleaved vector of length nch*half that is always "used" (hpp:685-694)
-		const uint32_t vch = (rs.type == 2) ? 1u : nch;
-		const uint32_t vlen = (rs.type == 2) ? nch * half : half;
+		const uint32_t rtype = rs.type;
+		const uint32_t vch = (rtype == 2) ? 1u : nch;
+		const uint32_t vlen = (rtype == 2) ? nch * half : half;
 		const uint32_t lb = min(rs.begin, vlen), le = min(rs.end, vlen);
 		const uint32_t psize = rs.partition_size;
 		const uint32_t parts = (le - lb) / psize;
@@ -107,36 +121,43 @@ __global__ void __launch_bounds__(kResThreads) k_residue_apply(DevBatchView b, f
 		const uint8_t* cls = pl + 4;
 		const uint32_t cls_bytes = (vch * parts + 3u) & ~3u;
 		const uint8_t* ent = cls + cls_bytes;
+		const bool ent16 = su.entry_bits == 16;
 		const uint32_t ent_bytes = (n_entries * (su.entry_bits / 8) + 3u) & ~3u;
 		pl = ent + ent_bytes;
 
+		__syncthreads();                                     // previous submap done with s_books / acc; book tables visible
+		for(uint32_t i = threadIdx.x; i < rs.n_class * 8u; i += blockDim.x) s_books[i] = rs.books[i];
 		for(uint32_t i = threadIdx.x; i < vch * vlen; i += blockDim.x) acc[i] = 0.f;
-		// vector counts in decode order + block-wide exclusive scan
-		const uint32_t items = 8 * parts * vch;
 		if(threadIdx.x == 0) s_carry = 0;
 		__syncthreads();
+		// vector counts in decode order (pass, partition, channel) + block-wide exclusive scan: warp shuffles, one
+		// shared-memory hop between the warps
+		const uint32_t items = 8 * parts * vch;
+		const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 		for(uint32_t base = 0; base < items; base += blockDim.x) {
 			const uint32_t it = base + threadIdx.x;
 			uint32_t cnt = 0;
 			if(it < items) {
 				const uint32_t j = it % vch, part = (it / vch) % parts, pass = it / (vch * parts);
-				const bool ch_used = (rs.type == 2) ? true : ((used >> chs[j]) & 1);
+				const bool ch_used = (rtype == 2) ? true : ((used >> chs[j]) & 1);
 				if(ch_used) {
-					const uint32_t book = rs.books[cls[j * parts + part] * 8 + pass];
-					if(book != POV_NO_BOOK && book < su.n_codebooks) cnt = psize / su.codebooks[book].dim;
+					const uint32_t book = s_books[cls[j * parts + part] * 8 + pass];
+					if(book != POV_NO_BOOK && book < n_books) cnt = psize / s_dim[book];
 				}
 			}
-			s_scan[threadIdx.x] = cnt;
-			__syncthreads();
-			for(uint32_t d = 1; d < blockDim.x; d <<= 1) {      // Hillis-Steele inclusive scan
-				const uint32_t v = (threadIdx.x >= d) ? s_scan[threadIdx.x - d] : 0;
-				__syncthreads();
-				s_scan[threadIdx.x] += v;
-				__syncthreads();
+			uint32_t incl = cnt;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+				if((int) lane >= o) incl += v;
 			}
-			if(it < items) cursor[it] = s_carry + s_scan[threadIdx.x] - cnt;
+			if(lane == 31) s_scan[warp] = incl;
 			__syncthreads();
-			if(threadIdx.x == blockDim.x - 1) s_carry += s_scan[threadIdx.x];
+			uint32_t before = s_carry;
+			for(uint32_t w = 0; w < warp; ++w) before += s_scan[w];
+			if(it < items) cursor[it] = before + incl - cnt;
+			__syncthreads();
+			if(threadIdx.x == blockDim.x - 1) s_carry = before + incl;
 			__syncthreads();
 		}
 		// apply: one thread per BIN. A bin receives at most one addend per pass (hpp:734-752), so it can gather its own
@@ -145,32 +166,32 @@ __global__ void __launch_bounds__(kResThreads) k_residue_apply(DevBatchView b, f
 		for(uint32_t idx = threadIdx.x; idx < parts * vch * psize; idx += blockDim.x) {
 			const uint32_t o = idx % psize, w = idx / psize;
 			const uint32_t j = w % vch, part = w / vch;
-			const bool ch_used = (rs.type == 2) ? true : ((used >> chs[j]) & 1);
+			const bool ch_used = (rtype == 2) ? true : ((used >> chs[j]) & 1);
 			if(!ch_used) continue;
 			const uint32_t cl = cls[j * parts + part];
 			float sum = 0.f;
+#pragma unroll
 			for(uint32_t pass = 0; pass < 8; ++pass) {
-				const uint32_t book = rs.books[cl * 8 + pass];
+				const uint32_t book = s_books[cl * 8 + pass];
 				if(book == POV_NO_BOOK) continue;
-				if(book >= su.n_codebooks) { bad |= POV_PKT_VQ_ENTRY; continue; }
-				const DevCodebook cb = su.codebooks[book];
-				const uint32_t nvec = psize / cb.dim;
+				if(book >= n_books) { bad |= POV_PKT_VQ_ENTRY; continue; }
+				const uint32_t dim = s_dim[book];
+				const uint32_t nvec = psize / dim;
 				// type 0: v[k + l*nvec] (hpp:734-743); types 1/2: v[k*dim + l] (hpp:744-752)
 				uint32_t k, l;
-				if(rs.type == 0) { l = o / nvec; k = o - l * nvec; if(nvec == 0 || l >= cb.dim) continue; }
-				else { k = o / cb.dim; l = o - k * cb.dim; if(k >= nvec) continue; }
+				if(rtype == 0) { if(nvec == 0) continue; l = o / nvec; k = o - l * nvec; if(l >= dim) continue; }
+				else { k = o / dim; l = o - k * dim; if(k >= nvec) continue; }
 				const uint32_t cur = cursor[(pass * parts + part) * vch + j] + k;
 				if(cur >= n_entries) { bad |= POV_PKT_VQ_ENTRY; continue; }
-				const uint32_t e = (su.entry_bits == 16) ? reinterpret_cast<const uint16_t*>(ent)[cur]
-				                                         : reinterpret_cast<const uint32_t*>(ent)[cur];
-				if(cb.lookup_type == 0 || e >= cb.n_entries) { bad |= POV_PKT_VQ_ENTRY; continue; }
-				sum += __ldg(&cb.vq[(size_t) e * cb.dim + l]);
+				const uint32_t e = ent16 ? reinterpret_cast<const uint16_t*>(ent)[cur] : reinterpret_cast<const uint32_t*>(ent)[cur];
+				if(e >= s_nent[book]) { bad |= POV_PKT_VQ_ENTRY; continue; }
+				sum += __ldg(&s_vq[book][(size_t) e * dim + l]);
 			}
 			acc[(size_t) j * vlen + lb + part * psize + o] = sum;
 		}
 		__syncthreads();
 		// scatter to the channel-major dense layout (de-interleave for type 2, hpp:690-692)
-		if(rs.type == 2) {
+		if(rtype == 2) {
 			for(uint32_t i = threadIdx.x; i < nch * half; i += blockDim.x) {
 				const uint32_t j = i % nch, bin = i / nch;
 				out[(size_t) chs[j] * half + bin] = acc[i];
@@ -181,7 +202,6 @@ __global__ void __launch_bounds__(kResThreads) k_residue_apply(DevBatchView b, f
 				out[(size_t) chs[j] * half + bin] = acc[i];
 			}
 		}
-		__syncthreads();
 	}
 	if(bad) atomicOr(&b.status[p], bad);
 }
