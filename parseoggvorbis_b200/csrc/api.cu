@@ -12,6 +12,9 @@
 #include <string>
 #include <vector>
 
+#include <exception>
+#include <new>
+
 #include "api_internal.h"
 #include "host_tables.h"
 #include "kernels.h"
@@ -29,6 +32,15 @@ int pov_fail(pov_ctx* ctx, int code, const char* fmt, ...) {
 		va_end(ap);
 	}
 	return code;
+}
+
+// Nothing may throw across the C boundary (include/pov_synth.h): every entry point that allocates is a function-try-block
+// ending in this handler (std::bad_alloc from a descriptor that asks for absurd sizes, std::length_error, ...).
+int pov_fail_exception(pov_ctx* ctx) {
+	try { throw; }
+	catch(const std::bad_alloc&) { return pov_fail(ctx, POV_ERR_ARG, "out of host memory (descriptor sizes beyond what this machine can hold)"); }
+	catch(const std::exception& e) { return pov_fail(ctx, POV_ERR_ARG, "internal error: %s", e.what()); }
+	catch(...) { return pov_fail(ctx, POV_ERR_ARG, "internal error: unknown exception"); }
 }
 
 #define CUDA_TRY(ctx, expr)                                                                                       \
@@ -253,7 +265,7 @@ static bool build_fast_tables(const pov_setup* s, const std::vector<DevFloor>& f
 	return warp_kernel_smem_bytes(s->blocksize[0], s->blocksize[1], short_cap, nullptr, nullptr, nullptr) <= 227 * 1024;
 }
 
-extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id_out) {
+extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id_out) try {
 	if(!ctx || !s || !id_out) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	if(s->abi_version != POV_ABI_VERSION) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: abi_version %u != %u", s->abi_version, POV_ABI_VERSION);
@@ -422,7 +434,7 @@ extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	*id_out = (uint32_t) (ctx->setups.size() - 1);
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)
 
 extern "C" int pov_setup_entry_bits(const pov_ctx* ctx, uint32_t id) {
 	if(!ctx || id >= ctx->setups.size()) return -1;
@@ -458,7 +470,7 @@ extern "C" void pov_batch_free(pov_ctx* ctx, pov_batch_handle* h) {
 	delete h;
 }
 
-extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_handle** out) {
+extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_handle** out) try {
 	if(!ctx || !b || !out) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	if(b->input_kind > POV_INPUT_ENTRIES || b->pcm_layout > POV_PCM_INTERLEAVED) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: bad input_kind/pcm_layout");
@@ -513,7 +525,9 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 		expect_first += st.n_packets;
 		const SetupRec& su = ctx->setups[st.setup_id];
 		const uint32_t C = su.channels;
-		if(st.pcm_base + st.pcm_frames * C > b->pcm_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: stream %u: PCM region exceeds pcm_floats", si);
+		// (subtraction form: none of these 64-bit sums may wrap)
+		if(st.pcm_base > b->pcm_floats || st.pcm_frames > (b->pcm_floats - st.pcm_base) / C)
+			return pov_fail(ctx, POV_ERR_ARG, "pov_batch: stream %u: PCM region exceeds pcm_floats", si);
 		maxC = std::max(maxC, C); maxbs = std::max(maxbs, su.blocksize[1]); minbs = std::min(minbs, su.blocksize[0]);
 		maxposts = std::max(maxposts, su.max_posts); res_smem = std::max(res_smem, su.res_smem);
 		if(su.blocksize[0] != 256 || su.blocksize[1] != 2048) only_std = false;
@@ -530,19 +544,19 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 			if(pk.floor_used >> C) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: floor_used has bits beyond %u channels", p, C);
 			const uint32_t max_emit = k ? n_prev / 4 + n / 4 : 0;
 			if(pk.emit_frames > max_emit) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: emit_frames %u > %u (hpp:1026)", p, pk.emit_frames, max_emit);
-			if(pk.pcm_off + pk.emit_frames > st.pcm_frames) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: PCM chunk outside the stream's %llu frames", p, (unsigned long long) st.pcm_frames);
+			if(pk.pcm_off > st.pcm_frames || pk.emit_frames > st.pcm_frames - pk.pcm_off) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: PCM chunk outside the stream's %llu frames", p, (unsigned long long) st.pcm_frames);
 			// Y lists
 			const DevMapping& mp = su.maps_host[su.mode_mapping[pk.mode]];
 			uint64_t ny = 0;
 			for(uint32_t c = 0; c < C; ++c)
 				if((pk.floor_used >> c) & 1) ny += su.floors_host[mp.floor_of_ch[c]].n_posts;
-			if(pk.ys_off + ny > b->n_ys) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: Y lists outside the Y arena", p);
+			if(pk.ys_off > b->n_ys || ny > b->n_ys - pk.ys_off) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: Y lists outside the Y arena", p);
 			if(b->input_kind == POV_INPUT_DENSE) {
 				if(pk.spec_off & 3) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: spec_off must be a multiple of 4 floats (16-byte TMA source)", p);
-				if(pk.spec_off + (uint64_t) C * (n / 2) > payload_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: spectra outside the payload arena", p);
+				if(pk.spec_off > payload_floats || (uint64_t) C * (n / 2) > payload_floats - pk.spec_off) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: spectra outside the payload arena", p);
 				h->spec_off[p] = pk.spec_off;
 			} else {
-				if((pk.spec_off & 3) || pk.spec_off + 4 > b->payload_bytes) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload offset invalid", p);
+				if((pk.spec_off & 3) || b->payload_bytes < 4 || pk.spec_off > b->payload_bytes - 4) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload offset invalid", p);
 				if(su.residues_host.empty()) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: setup has no residues", p);
 				h->spec_off[p] = dense_floats;
 				dense_floats += (uint64_t) C * (n / 2);
@@ -612,11 +626,17 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 				const uint32_t vch = rs.type == 2 ? 1 : nch, vlen = rs.type == 2 ? nch * half : half;
 				const uint32_t lb = std::min(rs.begin, vlen), le = std::min(rs.end, vlen);
 				const uint32_t parts = (le - lb) / rs.partition_size;
-				if(off + 4 > b->payload_bytes) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload truncated", p);
+				if(b->payload_bytes < 4 || off > b->payload_bytes - 4) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload truncated", p);
 				uint32_t ne;
 				memcpy(&ne, (const uint8_t*) b->payload + off, 4);
-				off += 4 + (((uint64_t) vch * parts + 3) & ~3ull) + (((uint64_t) ne * (su.entry_bits / 8) + 3) & ~3ull);
-				if(off > b->payload_bytes) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload truncated", p);
+				// sizes are < 2^37 each, off <= payload_bytes: the sum cannot wrap
+				const uint64_t cls_bytes = ((uint64_t) vch * parts + 3) & ~3ull, ent_bytes = ((uint64_t) ne * (su.entry_bits / 8) + 3) & ~3ull;
+				if(cls_bytes + ent_bytes > b->payload_bytes - off - 4) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue payload truncated", p);
+				// classification numbers index the (class, pass) book table: hpp:715-722 produces values < n_class by construction
+				const uint8_t* cls = (const uint8_t*) b->payload + off + 4;
+				for(uint64_t i = 0; i < (uint64_t) vch * parts; ++i)
+					if(cls[i] >= rs.n_class) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: residue classification %u >= %u classes", p, cls[i], rs.n_class);
+				off += 4 + cls_bytes + ent_bytes;
 			}
 		}
 	}
@@ -664,7 +684,7 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	if(b->input_kind == POV_INPUT_ENTRIES) CUDA_TRY(ctx, h->d_spectra.reserve(std::max<size_t>(sizeof(float) * dense_floats, 16)));
 	if(fresh) *out = fresh.release();
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)
 
 static DevBatchView make_view(pov_ctx* ctx, pov_batch_handle* h) {
 	DevBatchView v;
@@ -710,7 +730,7 @@ static int prepare_stage_buffers(pov_ctx* ctx, pov_batch_handle* h, DevStageBuff
 	return POV_OK;
 }
 
-extern "C" int pov_batch_run_staged(pov_ctx* ctx, pov_batch_handle* h) {
+extern "C" int pov_batch_run_staged(pov_ctx* ctx, pov_batch_handle* h) try {
 	if(!ctx || !h) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	DevBatchView v = make_view(ctx, h);
@@ -721,9 +741,9 @@ extern "C" int pov_batch_run_staged(pov_ctx* ctx, pov_batch_handle* h) {
 	CUDA_TRY(ctx, launch_staged(v, sb, h->max_channels, ctx->stream, &ctx->launches));
 	h->staged_ready = true;
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)
 
-extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
+extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) try {
 	if(!ctx || !h) return POV_ERR_ARG;
 	if(ctx->kernel_choice == 2 && !h->warp_ok) return pov_fail(ctx, POV_ERR_UNSUPPORTED, "POV_KERNEL=warp: this batch is outside what the warp kernel supports");
 	if(!h->warp_ok && !h->fused_ok) return pov_batch_run_staged(ctx, h);   // working set beyond one SM's shared memory: staged kernels
@@ -743,7 +763,7 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) {
 	CUDA_TRY(ctx, launch_fused(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), h->max_channels, h->max_blocksize,
 	                           h->min_blocksize, h->floor_cap_cls, h->table_float2, h->only_256_2048, ctx->stream, &ctx->launches));
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)
 
 extern "C" const char* pov_batch_kernel_name(const pov_ctx* ctx, const pov_batch_handle* h) {
 	if(!ctx || !h) return "none";
@@ -758,18 +778,18 @@ extern "C" int pov_batch_sync(pov_ctx* ctx, pov_batch_handle* h) {
 	return POV_OK;
 }
 
-extern "C" int pov_batch_fetch_pcm(pov_ctx* ctx, pov_batch_handle* h, float* out, uint64_t n_floats, int sync) {
+extern "C" int pov_batch_fetch_pcm(pov_ctx* ctx, pov_batch_handle* h, float* out, uint64_t n_floats, int sync) try {
 	if(!ctx || !h || (!out && n_floats)) return POV_ERR_ARG;
 	if(n_floats > h->pcm_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_pcm: %llu floats requested, arena holds %llu", (unsigned long long) n_floats, (unsigned long long) h->pcm_floats);
 	cudaSetDevice(ctx->device);
 	if(n_floats) CUDA_TRY(ctx, cudaMemcpyAsync(out, h->d_pcm.ptr, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	if(sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)
 
 extern "C" void* pov_batch_pcm_dev(pov_batch_handle* h) { return h ? h->d_pcm.ptr : nullptr; }
 
-extern "C" int pov_batch_status(pov_ctx* ctx, pov_batch_handle* h, uint32_t* out, uint32_t n) {
+extern "C" int pov_batch_status(pov_ctx* ctx, pov_batch_handle* h, uint32_t* out, uint32_t n) try {
 	if(!ctx || !h) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	std::vector<uint32_t> tmp(h->n_packets);
@@ -784,10 +804,10 @@ extern "C" int pov_batch_status(pov_ctx* ctx, pov_batch_handle* h, uint32_t* out
 		return pov_fail(ctx, POV_ERR_STREAM, "audio packet %u: check failed: %s", p, what);
 	}
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)
 
 extern "C" int pov_batch_fetch_stage(pov_ctx* ctx, pov_batch_handle* h, uint32_t packet, uint32_t channel, int stage,
-                                     void* out, uint64_t out_bytes) {
+                                     void* out, uint64_t out_bytes) try {
 	if(!ctx || !h || !out) return POV_ERR_ARG;
 	if(packet >= h->n_packets) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_stage: packet out of range");
 	const SetupRec& su = ctx->setups[h->pk_setup[packet]];
@@ -824,7 +844,7 @@ extern "C" int pov_batch_fetch_stage(pov_ctx* ctx, pov_batch_handle* h, uint32_t
 	CUDA_TRY(ctx, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)
 
 // bulk access for the dump writer: whole stage arrays in one copy
 int pov_batch_fetch_stage_all(pov_ctx* ctx, pov_batch_handle* h, StageHost& out) {
@@ -854,7 +874,7 @@ int pov_batch_fetch_stage_all(pov_ctx* ctx, pov_batch_handle* h, StageHost& out)
 // ---------------------------------------------------------------------------------------------------------------
 // drop-in for mdct_backward (src/mdct.h:105)
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int pov_mdct_backward_batch(pov_ctx* ctx, uint32_t n, uint64_t count, const float* in, float* out) {
+extern "C" int pov_mdct_backward_batch(pov_ctx* ctx, uint32_t n, uint64_t count, const float* in, float* out) try {
 	if(!ctx || (count && (!in || !out))) return POV_ERR_ARG;
 	if(!is_pow2_in(n, 64, 8192)) return pov_fail(ctx, POV_ERR_ARG, "pov_mdct_backward_batch: n = %u is not a power of two in 64..8192 (hpp:1295)", n);
 	if(count > 0x7fffffffull) return pov_fail(ctx, POV_ERR_ARG, "pov_mdct_backward_batch: count too large for one call");
@@ -870,4 +890,4 @@ extern "C" int pov_mdct_backward_batch(pov_ctx* ctx, uint32_t n, uint64_t count,
 	CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->mdct_out.ptr, count * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)

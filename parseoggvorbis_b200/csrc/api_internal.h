@@ -104,6 +104,9 @@ struct StageHost {                // whole stage arrays on the host (debug dump 
 };
 
 int pov_fail(pov_ctx* ctx, int code, const char* fmt, ...);
+// Entry points are function-try-blocks that end in POV_NOTHROW_END: no exception crosses the C boundary.
+int pov_fail_exception(pov_ctx* ctx);
+#define POV_NOTHROW_END(ctx) catch(...) { return pov_fail_exception(ctx); }
 int pov_batch_fetch_stage_all(pov_ctx* ctx, pov_batch_handle* h, StageHost& out);
 
 #endif

@@ -58,6 +58,7 @@ extern "C" int pov_ogg_parse_memory(const uint8_t* data, size_t len, pov_parsed*
 	static thread_local char errbuf[512];
 	if(!out || (!data && len)) return POV_ERR_ARG;
 	*out = nullptr;
+	try {
 	std::unique_ptr<pov_parsed> P(new pov_parsed());
 	ParseError err;
 	if(!parse_ogg_file(data, len, P->streams, err)) {
@@ -73,6 +74,11 @@ extern "C" int pov_ogg_parse_memory(const uint8_t* data, size_t len, pov_parsed*
 	}
 	*out = P.release();
 	return POV_OK;
+	} catch(...) {
+		snprintf(errbuf, sizeof errbuf, "out of memory or internal error while building the descriptors");
+		if(error_out) *error_out = errbuf;
+		return POV_ERR_ARG;
+	}
 }
 
 extern "C" uint32_t pov_parsed_stream_count(const pov_parsed* p) { return p ? (uint32_t) p->streams.size() : 0; }
@@ -152,7 +158,7 @@ static int register_stream_setup_slow(pov_ctx* ctx, const StreamWork& st, uint32
 	return pov_setup_register(ctx, &a.s, id);
 }
 
-extern "C" int pov_ogg_vorbis_decode_memory(pov_ctx* ctx, const uint8_t* data, size_t len, const char* debug_out, pov_decoded* out) {
+extern "C" int pov_ogg_vorbis_decode_memory(pov_ctx* ctx, const uint8_t* data, size_t len, const char* debug_out, pov_decoded* out) try {
 	if(!ctx || !out || (!data && len)) return POV_ERR_ARG;
 	memset(out, 0, sizeof *out);
 	std::vector<StreamWork> streams;
@@ -209,7 +215,7 @@ extern "C" int pov_ogg_vorbis_decode_memory(pov_ctx* ctx, const uint8_t* data, s
 	}
 	out->pcm = pcm;
 	return POV_OK;
-}
+} POV_NOTHROW_END(ctx)
 
 extern "C" void pov_decoded_free(pov_decoded* d) {
 	if(!d) return;
@@ -311,7 +317,7 @@ inline size_t align16(size_t x) { return (x + 15) & ~(size_t) 15; }
 }  // namespace
 
 extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* data, const size_t* len,
-                                 uint32_t host_threads, uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out) {
+                                 uint32_t host_threads, uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out) try {
 	if(!ctx || (n_files && (!data || !len))) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	// automatic: every core but one — the calling thread validates, queues and retires chunks and must not be time-sliced
@@ -363,6 +369,7 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 			ck->n_files = std::min(files_per_chunk, n_files - ck->first_file);
 			ck->frames.assign(ck->n_files, 0);
 			hb.clear();
+			try {                  // a worker never lets an exception escape its thread: the chunk carries the error instead
 			for(uint32_t i = 0; i < ck->n_files && ck->error.empty(); ++i) {
 				ParseError err;
 				file.clear();
@@ -405,6 +412,9 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 					b.pcm_floats = hb.pcm_floats;
 				}
 			}
+			} catch(...) {
+				if(ck->error.empty()) ck->error = "chunk at file " + std::to_string(ck->first_file) + ": out of memory or internal error while assembling the batch";
+			}
 			// Back-pressure by chunk INDEX, not by count: the chunk the consumer is waiting for always passes, however many
 			// later chunks the other workers have finished in the meantime (a count limit can fill the queue with later chunks
 			// and then block the one worker that holds the chunk everybody is waiting for).
@@ -414,7 +424,18 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 			cv_ready.notify_all();
 		}
 	};
-	std::vector<std::thread> pool;
+	// the pool is joined on every way out of this function (an exception on the calling thread included)
+	struct PoolJoiner {
+		std::vector<std::thread> pool;
+		std::atomic<bool>& stop; std::mutex& mu; std::condition_variable& cv_space; CorpusState& cs;
+		~PoolJoiner() {
+			stop.store(true);
+			{ std::lock_guard<std::mutex> lk(mu); cv_space.notify_all(); }
+			{ std::lock_guard<std::mutex> lk(cs.pmu); cs.pcv.notify_all(); }
+			for(auto& t : pool) if(t.joinable()) t.join();
+		}
+	} joiner{{}, stop, mu, cv_space, cs};
+	std::vector<std::thread>& pool = joiner.pool;
 	for(uint32_t t = 0; t < host_threads; ++t) pool.emplace_back(worker);
 
 	uint64_t total = 0;
@@ -542,7 +563,7 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 	if(total_values_out) *total_values_out = total;
 	if(checksum_out) *checksum_out = h_sum;
 	return rc;
-}
+} POV_NOTHROW_END(ctx)
 
 // ---------------------------------------------------------------------------------------------------------------
 // same shape as the reference's C entry point (hpp:1493): decode, discard the PCM, report errors as a string

@@ -39,6 +39,9 @@ constexpr int kRegionF2 = 576;          // float2 slots of one FFT work region (
 constexpr int kSlotF2 = kRegionF2 / 2;  // the work area of a warp is three half regions A | B | C: even steps transform in
                                         // A+B and leave their overlap half (D lo) in A, odd steps use B+C and leave it in C;
                                         // the other half (D hi, consumed by the same step's overlap-add) always lands in B
+#ifndef POV_WARP_TMEM
+#define POV_WARP_TMEM 1        // per-lane factor tables of the 512-point FFT in tensor memory (0: shared memory, the round-1 layout)
+#endif
 #ifndef POV_WARP_PKT_CAP
 #define POV_WARP_PKT_CAP 32
 #endif
@@ -81,7 +84,7 @@ template <int Q0, int Q1> struct Map {
 	static constexpr int kOffFp1    = kOffRot0 + Q0 * 8;
 	static constexpr int kOffFp0    = kOffFp1 + fp_count(Q1) * 8;
 	static constexpr int kOffRecip  = kOffFp0 + fp_count(Q0) * 8;           // ceil(2^32 / d), d <= POV_FAST_MAX_X
-	static constexpr int kOffBar    = kOffRecip + (POV_FAST_MAX_X + 4) * 4;
+	static constexpr int kOffBar    = kOffRecip + (POV_FAST_MAX_X + 4) * 4;      // mbarrier (8 bytes) | tensor-memory base address (4 bytes)
 	static constexpr int kOffWarps  = kOffBar + 16;
 	static_assert(kOffWarps % 16 == 0, "warp areas must stay 16-byte aligned");
 };
@@ -121,6 +124,44 @@ template <class T> __device__ __forceinline__ T* sptr(uint32_t a) { return reint
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {   // TMA bulk prefetch (size multiple of 16)
 	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// ---- tensor memory (TMEM) as a second table store --------------------------------------------------------------------
+// The rotation, twiddle and window factors a lane needs are the same for every packet (they depend on the lane's
+// fixed place in the FFT only), so each lane keeps its own copy in ITS row of tensor memory (tcgen05.ld/st .32x32b:
+// thread t <-> TMEM lane t of the warp's 32-lane quarter, registers <-> consecutive columns). tcgen05.ld does not go
+// through the LSU / shared-memory data pipe that bounds this kernel: measured on B200 (tools/probes/tmem_probe.cu), 20
+// warps read 268 B/clk/SM from TMEM alone and 122 B/clk/SM from TMEM *while* shared memory delivers its full
+// 122-128 B/clk/SM. Column map of a quarter (floats), whole-warp FFT (Q = 512) only:
+constexpr uint32_t kTmSpec = 0;     // 4 x [w[j] pair of quad q = lane + 32 m | pair of quad Q/2-1-q]      spectral stage
+constexpr uint32_t kTmTw1  = 32;    // [W^j, W^2j, W^3j, W^4j] of butterflies lane and 63 - lane             pass over j2
+constexpr uint32_t kTmTw2  = 48;    // [W^j, W^2j, W^3j, W^4j] of j0 = lane % 8                              pass over j1
+constexpr uint32_t kTmRot  = 56;    // w[lane + 64 k], k < 8 | w[63 - lane + 64 k]                           post-rotation
+constexpr uint32_t kTmWin  = 88;    // 4 x [slope[4 lane + 128 i ..+3] | slope[2Q - 4 - (4 lane + 128 i) ..+3]]  overlap-add
+constexpr uint32_t kTmCols = 128;   // allocation (power of two >= 32)
+__device__ __forceinline__ void tm_alloc(uint32_t* slot_smem) {      // one warp; the base address lands in shared memory
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "n"(kTmCols) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_dealloc(uint32_t base) {
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kTmCols) : "memory");
+}
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const float (&v)[8]) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+	             ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Issue / complete split: the load is started early and its registers are only touched after tm_wait8, which carries the
+// eight values as in-out operands so that no use can be scheduled above the wait.
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, float (&v)[8]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tm_wait8(float (&v)[8]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+	             : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
 }
 
 __device__ __forceinline__ void uncouple_f(float& m, float& a) {   // hpp:1220-1239, branch-free
@@ -335,10 +376,12 @@ __device__ __forceinline__ float4 curve_quad(const uint2* __restrict__ rec, cons
 // Every access of a pass is either contiguous over the lanes or hits 16 distinct 8-byte bank pairs per half warp.
 // Every pass has one call site per block class and is inlined (no call ABI, strides become immediates); the hot loop of
 // the 20 independently running warps is ~1700 instructions, just inside the 32 KB L1.5 instruction cache.
+__device__ __forceinline__ void twiddle8w(float2* a, float2 w1, float2 w2, float2 w3, float2 w4);
 __device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ tw, int half) {   // tw: (W^j, W^2j); tw + half: (W^3j, W^4j)
 	const float4 w12 = *reinterpret_cast<const float4*>(tw), w34 = *reinterpret_cast<const float4*>(tw + half);
-	const float2 w1 = make_float2(w12.x, w12.y), w2 = make_float2(w12.z, w12.w);
-	const float2 w3 = make_float2(w34.x, w34.y), w4 = make_float2(w34.z, w34.w);
+	twiddle8w(a, make_float2(w12.x, w12.y), make_float2(w12.z, w12.w), make_float2(w34.x, w34.y), make_float2(w34.z, w34.w));
+}
+__device__ __forceinline__ void twiddle8w(float2* a, float2 w1, float2 w2, float2 w3, float2 w4) {
 	a[1] = cmul(a[1], w1);
 	a[2] = cmul(a[2], w2);
 	a[3] = cmul(a[3], w3);
@@ -351,17 +394,29 @@ __device__ __forceinline__ void twiddle8(float2* a, const float2* __restrict__ t
 // Radix-8 DIF pass of two butterflies per lane: inputs in*[m*sin], outputs out*[k*sout] (twiddled by tw*).
 // All addresses are shared-window byte addresses, strides are in float2 units. Twiddles of butterfly j: (W^j, W^2j) at
 // tw, (W^3j, W^4j) at tw + twhalf (the table keeps the two halves apart so that lanes read consecutive 16-byte words).
-__device__ __forceinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t twA_, uint32_t twB_, int twhalf, uint32_t outA_, uint32_t outB_, int sout) {
+template <int kTm = 0>
+__device__ __forceinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t twA_, uint32_t twB_, int twhalf, uint32_t outA_, uint32_t outB_, int sout, uint32_t tm = 0) {
 	const float2* inA = sptr<const float2>(inA_); const float2* inB = sptr<const float2>(inB_);
 	float2* outA = sptr<float2>(outA_); float2* outB = sptr<float2>(outB_);
 	float2 a[8], b[8];
+	float wa[8], wb[8];               // kTm: twiddles from this lane's tensor-memory row (1: a and b differ, 2: shared by both)
 #pragma unroll
 	for(int m = 0; m < 8; ++m) { a[m] = inA[m * sin]; b[m] = inB[m * sin]; }
 	__syncwarp();
 	dft8(a);
-	twiddle8(a, sptr<const float2>(twA_), twhalf);
+	if constexpr(kTm != 0) {
+		tm_ld8(tm, wa);
+		tm_wait8(wa);
+		twiddle8w(a, make_float2(wa[0], wa[1]), make_float2(wa[2], wa[3]), make_float2(wa[4], wa[5]), make_float2(wa[6], wa[7]));
+	} else twiddle8(a, sptr<const float2>(twA_), twhalf);
 	dft8(b);
-	twiddle8(b, sptr<const float2>(twB_), twhalf);
+	if constexpr(kTm == 1) {
+		tm_ld8(tm + 8, wb);
+		tm_wait8(wb);
+		twiddle8w(b, make_float2(wb[0], wb[1]), make_float2(wb[2], wb[3]), make_float2(wb[4], wb[5]), make_float2(wb[6], wb[7]));
+	} else if constexpr(kTm == 2) {
+		twiddle8w(b, make_float2(wa[0], wa[1]), make_float2(wa[2], wa[3]), make_float2(wa[4], wa[5]), make_float2(wa[6], wa[7]));
+	} else twiddle8(b, sptr<const float2>(twB_), twhalf);
 #pragma unroll
 	for(int k = 0; k < 8; ++k) { outA[k * sout] = a[k]; outB[k * sout] = b[k]; }
 	__syncwarp();
@@ -369,8 +424,9 @@ __device__ __forceinline__ void r8_pass(uint32_t inA_, uint32_t inB_, int sin, u
 
 // Last pass + post-rotation of butterflies kkA and kkB = J-1-kkA (rotA = rot + kkA, rotB = rot + kkB):
 //   c[k] = X[k] * w[k];  D2[k] = (D[2k], D[2k+1]) = (Re c[k], -Im c[Q-1-k]);  Q-1-(kkA + J k2) = kkB + J (7-k2)
+template <bool kTm = false>
 __device__ __forceinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin, uint32_t rotA_, uint32_t rotB_, int J,
-                                       uint32_t loA_, uint32_t loB_, uint32_t hiA_, uint32_t hiB_) {
+                                       uint32_t loA_, uint32_t loB_, uint32_t hiA_, uint32_t hiB_, uint32_t tm = 0) {
 	const float2* inA = sptr<const float2>(inA_); const float2* inB = sptr<const float2>(inB_);
 	const float2* rotA = sptr<const float2>(rotA_); const float2* rotB = sptr<const float2>(rotB_);
 	float2* loA = sptr<float2>(loA_); float2* loB = sptr<float2>(loB_);      // D2[kk + J k2], k2 < 4  (D lo half: next packet's overlap)
@@ -379,12 +435,31 @@ __device__ __forceinline__ void last_pass(uint32_t inA_, uint32_t inB_, int sin,
 #pragma unroll
 	for(int m = 0; m < 8; ++m) { a[m] = inA[m * sin]; b[m] = inB[m * sin]; }
 	__syncwarp();
-	dft8(a);
-	dft8(b);
+	if constexpr(kTm) {
+		// rotation factors from this lane's tensor-memory row: [w[kkA + J k], k < 8 | w[kkB + J k], k < 8], 8 floats at a time
+		float r0[8], r1[8];
+		dft8(a);
+		tm_ld8(tm, r0);
+		tm_ld8(tm + 8, r1);
+		tm_wait8(r0);
+		tm_wait8(r1);
 #pragma unroll
-	for(int k = 0; k < 8; ++k) {
-		a[k] = cmul(a[k], rotA[J * k]);
-		b[k] = cmul(b[k], rotB[J * k]);
+		for(int k = 0; k < 4; ++k) { a[k] = cmul(a[k], make_float2(r0[2 * k], r0[2 * k + 1])); a[k + 4] = cmul(a[k + 4], make_float2(r1[2 * k], r1[2 * k + 1])); }
+		dft8(b);
+		tm_ld8(tm + 16, r0);
+		tm_ld8(tm + 24, r1);
+		tm_wait8(r0);
+		tm_wait8(r1);
+#pragma unroll
+		for(int k = 0; k < 4; ++k) { b[k] = cmul(b[k], make_float2(r0[2 * k], r0[2 * k + 1])); b[k + 4] = cmul(b[k + 4], make_float2(r1[2 * k], r1[2 * k + 1])); }
+	} else {
+		dft8(a);
+		dft8(b);
+#pragma unroll
+		for(int k = 0; k < 8; ++k) {
+			a[k] = cmul(a[k], rotA[J * k]);
+			b[k] = cmul(b[k], rotB[J * k]);
+		}
 	}
 #pragma unroll
 	for(int k = 0; k < 4; ++k) {
@@ -435,8 +510,9 @@ __device__ __forceinline__ void first_pass_small(uint32_t Tf_, uint32_t fp_, int
 //                      r8 over j1 inside each        -> A2[j0*(J+2) + r' + R k1]   -> last pass (J = 8R)
 //   Q = 512:           r8 over j2 (R = 8)            -> A1[k0*72 + j], then as above
 // f = FFT index inside the warp (0 for Q = 512), u = lane inside the FFT, tw / fp / rot = shared-window table addresses.
-template <int Q>
-__device__ __forceinline__ void fft_passes(uint32_t Tfs, int u, uint32_t tws, uint32_t fps, uint32_t rots, uint32_t lo, uint32_t hi) {
+template <int Q, bool kTm = false>
+__device__ __forceinline__ void fft_passes(uint32_t Tfs, int u, uint32_t tws, uint32_t fps, uint32_t rots, uint32_t lo, uint32_t hi, uint32_t tm = 0) {
+	static_assert(!kTm || Q == 512, "tensor-memory tables are laid out for the whole-warp FFT");
 	constexpr int R = Q / 64, J = Q / 8;
 	const uint32_t uu = (uint32_t) u, u2 = (uint32_t) J - 1u - uu;
 	if constexpr(R == 1) {
@@ -444,14 +520,14 @@ __device__ __forceinline__ void fft_passes(uint32_t Tfs, int u, uint32_t tws, ui
 		last_pass(Tfs + uu * 72, Tfs + u2 * 72, 1, rots + uu * 8, rots + u2 * 8, J, lo + uu * 8, lo + u2 * 8, hi + uu * 8, hi + u2 * 8);
 	} else {
 		constexpr int S2 = J + 2;
-		if constexpr(R == 8) r8_pass(Tfs + uu * 8, Tfs + u2 * 8, 64, tws + uu * 16, tws + u2 * 16, 128, Tfs + uu * 8, Tfs + u2 * 8, 72);
+		if constexpr(R == 8) r8_pass<kTm ? 1 : 0>(Tfs + uu * 8, Tfs + u2 * 8, 64, tws + uu * 16, tws + u2 * 16, 128, Tfs + uu * 8, Tfs + u2 * 8, 72, tm + kTmTw1);
 		else first_pass_small<R>(Tfs, fps, u);
 		// pass over j1 inside the sub-FFTs: lane owns (r' = u/8, j0 = u%8) and (r' + R/2, j0); its twiddles are the L = 64 pass
 		constexpr uint32_t kTw64 = (R == 8) ? 256u : 0u;
 		const uint32_t j0 = uu & 7u, rp = uu >> 3;
-		r8_pass(Tfs + (rp * 72 + j0) * 8, Tfs + ((rp + R / 2) * 72 + j0) * 8, 8, tws + (kTw64 + j0 * 2) * 8, tws + (kTw64 + j0 * 2) * 8, 16,
-		        Tfs + (j0 * S2 + rp) * 8, Tfs + (j0 * S2 + rp + R / 2) * 8, R);
-		last_pass(Tfs + uu * 8, Tfs + u2 * 8, S2, rots + uu * 8, rots + u2 * 8, J, lo + uu * 8, lo + u2 * 8, hi + uu * 8, hi + u2 * 8);
+		r8_pass<kTm ? 2 : 0>(Tfs + (rp * 72 + j0) * 8, Tfs + ((rp + R / 2) * 72 + j0) * 8, 8, tws + (kTw64 + j0 * 2) * 8, tws + (kTw64 + j0 * 2) * 8, 16,
+		                     Tfs + (j0 * S2 + rp) * 8, Tfs + (j0 * S2 + rp + R / 2) * 8, R, tm + kTmTw2);
+		last_pass<kTm>(Tfs + uu * 8, Tfs + u2 * 8, S2, rots + uu * 8, rots + u2 * 8, J, lo + uu * 8, lo + u2 * 8, hi + uu * 8, hi + u2 * 8, tm + kTmRot);
 	}
 }
 
@@ -462,7 +538,7 @@ __device__ __forceinline__ void fft_passes(uint32_t Tfs, int u, uint32_t tws, ui
 // fmode: 0 evaluate the curve, 1 multiply by 1 (hpp:1247 skipped), 2 multiply by 0.
 template <int NL, bool GEN>
 __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, int o0, int o1, int o2, int o3, uint32_t curve_, uint32_t rec_cap,
-                                               uint32_t rot_, int Q, uint32_t Tf_, int u, uint32_t cp_) {
+                                               uint32_t rot_, int Q, uint32_t Tf_, int u, uint32_t cp_, uint32_t tm) {
 	// Lane u handles the quads q = u + (Q/16) m, m = 0..3: bins 4q..4q+3 and M-4-4q..M-1-4q arrive with two 128-bit loads
 	// per channel and yield the points 2q, 2q+1 and their mirrors Q-2-2q, Q-1-2q (two 128-bit stores, natural order).
 	const int LPF = Q >> 4, M = 2 * Q;
@@ -525,7 +601,13 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 		const float l0 = __fmul_rn(lo[0].x, fl.x), l1 = __fmul_rn(lo[0].y, fl.y), l2 = __fmul_rn(lo[0].z, fl.z), l3 = __fmul_rn(lo[0].w, fl.w);
 		const float h0 = __fmul_rn(hi[0].x, fh.x), h1 = __fmul_rn(hi[0].y, fh.y), h2 = __fmul_rn(hi[0].z, fh.z), h3 = __fmul_rn(hi[0].w, fh.w);
 		// t[j] = (X[2j] + i X[M-1-2j]) * w[j] for j = 2q, 2q+1 and Q-2-2q, Q-1-2q
-		const float4 wl = rot4[q], wh = rot4[(Q >> 1) - 1 - q];
+		float4 wl, wh;
+		if(tm) {                      // tm != 0: whole-warp FFT, rotation factors from this lane's tensor-memory row (warp uniform)
+			float wr[8];
+			tm_ld8(tm + kTmSpec + 8u * (uint32_t) m, wr);
+			tm_wait8(wr);
+			wl = make_float4(wr[0], wr[1], wr[2], wr[3]); wh = make_float4(wr[4], wr[5], wr[6], wr[7]);
+		} else { wl = rot4[q]; wh = rot4[(Q >> 1) - 1 - q]; }
 		const float2 t0 = cmul(make_float2(l0, h3), make_float2(wl.x, wl.y));
 		const float2 t1 = cmul(make_float2(l2, h1), make_float2(wl.z, wl.w));
 		const float2 t2 = cmul(make_float2(h0, l3), make_float2(wh.x, wh.y));
@@ -539,15 +621,15 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 // the largest channel set any coupling program of the setup needs: variants beyond it are not even compiled in.
 template <int kMaxNL>
 __device__ __forceinline__ void spectral_dispatch(const FastCouple* cp, const float* base, int half, uint32_t curve_, uint32_t rec_cap,
-                                                  uint32_t rot_, int Q, uint32_t Tf_, int u) {
+                                                  uint32_t rot_, int Q, uint32_t Tf_, int u, uint32_t tm) {
 	const int o0 = (int) cp->ch[0] * half, o1 = (int) cp->ch[1] * half, o2 = (int) cp->ch[2] * half, o3 = (int) cp->ch[3] * half;
 	const uint32_t cps = smem_u32(cp);
 	const int nl = cp->nl;
-	if(kMaxNL == 1 || nl == 1) spectral_stage<1, false>(base, o0, o0, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
-	else if(kMaxNL >= 2 && nl == 2 && cp->nsteps == 1) spectral_stage<2, false>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
-	else if(kMaxNL >= 2 && nl == 2) spectral_stage<2, true>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
-	else if(kMaxNL >= 3 && nl == 3) spectral_stage<3, true>(base, o0, o1, o2, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps);
-	else if(kMaxNL >= 3) spectral_stage<4, true>(base, o0, o1, o2, o3, curve_, rec_cap, rot_, Q, Tf_, u, cps);
+	if(kMaxNL == 1 || nl == 1) spectral_stage<1, false>(base, o0, o0, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps, tm);
+	else if(kMaxNL >= 2 && nl == 2 && cp->nsteps == 1) spectral_stage<2, false>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps, tm);
+	else if(kMaxNL >= 2 && nl == 2) spectral_stage<2, true>(base, o0, o1, o0, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps, tm);
+	else if(kMaxNL >= 3 && nl == 3) spectral_stage<3, true>(base, o0, o1, o2, o0, curve_, rec_cap, rot_, Q, Tf_, u, cps, tm);
+	else if(kMaxNL >= 3) spectral_stage<4, true>(base, o0, o1, o2, o3, curve_, rec_cap, rot_, Q, Tf_, u, cps, tm);
 }
 
 // ---- overlap-add ---------------------------------------------------------------------------------------------------
@@ -580,17 +662,25 @@ __device__ __forceinline__ float ola_one(const OlaGeom& G, const float* __restri
 
 // Long block after a long block, both slopes long: every sample has both terms and both windows. Lane produces
 // out[j..j+3] and out[1020-j..1023-j] (j < 512) from the same four vectors (TDAC symmetry of both frames and windows).
-template <int Q, bool kStrided>
+template <int Q, bool kStrided, bool kTm>
 __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, const float* __restrict__ chi, const float* __restrict__ sl,
-                                              float* __restrict__ dst, int stride, int lane) {
+                                              float* __restrict__ dst, int stride, int lane, uint32_t tm) {
 	// n = 4Q: the chunk has 2Q samples, half of them (Q) below the centre; 8 samples per lane and iteration
 #pragma unroll
 	for(int i = 0; i < Q / 128; ++i) {
 		const int j = 4 * lane + 128 * i;
+		float ww[8];
 		const float4 p = *reinterpret_cast<const float4*>(plo + (Q - 4) - j);
 		const float4 c = *reinterpret_cast<const float4*>(chi + j);
-		const float4 wa = *reinterpret_cast<const float4*>(sl + j);
-		const float4 wb = *reinterpret_cast<const float4*>(sl + (2 * Q - 4) - j);
+		float4 wa, wb;
+		if constexpr(kTm) {           // window slopes from this lane's tensor-memory row
+			tm_ld8(tm + kTmWin + 8u * (uint32_t) i, ww);
+			tm_wait8(ww);
+			wa = make_float4(ww[0], ww[1], ww[2], ww[3]); wb = make_float4(ww[4], ww[5], ww[6], ww[7]);
+		} else {
+			wa = *reinterpret_cast<const float4*>(sl + j);
+			wb = *reinterpret_cast<const float4*>(sl + (2 * Q - 4) - j);
+		}
 		float4 o1, o2;
 		o1.x = __fadd_rn(__fmul_rn(-p.w, wb.w), __fmul_rn(c.x, wa.x));
 		o1.y = __fadd_rn(__fmul_rn(-p.z, wb.z), __fmul_rn(c.y, wa.y));
@@ -665,8 +755,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	if(threadIdx.x < 4) reinterpret_cast<float*>(smem + M::kOffInvDb + 1024)[threadIdx.x] = 0.f;
 	for(uint32_t d = threadIdx.x; d <= POV_FAST_MAX_X; d += kThreads)
 		s_recip[d] = (d < 2) ? 0xFFFFFFFFu : (uint32_t) ((0x100000000ull + d - 1) / d);
+	// tensor memory holds the per-lane factor tables of the whole-warp (512-point) FFT; one CTA per SM, so the allocation never waits
+	constexpr bool kTm = (Q1 == 512) && (POV_WARP_TMEM != 0);
+	uint32_t* s_tmbase = reinterpret_cast<uint32_t*>(smem + M::kOffBar + 8);
+	if constexpr(kTm) { if(warp == kWarps - 1) tm_alloc(s_tmbase); tm_fence_before(); }
 	__syncthreads();
 	mbar_wait(s_bar, 0);
+	uint32_t tmw = 0;                    // this warp's window into tensor memory: lanes 32 (warp % 4) .. +31
+	if constexpr(kTm) {
+		tm_fence_after();
+		tmw = *s_tmbase + ((uint32_t) ((warp & 3) * 32) << 16);
+		if(warp < 4) {                   // one warp per lane quarter writes the rows (thread t <-> TMEM lane t)
+			const float4* rot4 = reinterpret_cast<const float4*>(s_rot1);
+			const float4* tw4 = reinterpret_cast<const float4*>(s_tw1);
+			const float4* sl4 = reinterpret_cast<const float4*>(s_slope1);
+			auto put2 = [&](uint32_t col, float4 x, float4 y) {
+				const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+				tm_st8(tmw + col, v);
+			};
+			const int l2 = 63 - lane, j0 = lane & 7;
+			for(int m = 0; m < 4; ++m) put2(kTmSpec + 8u * m, rot4[lane + 32 * m], rot4[(Q1 >> 1) - 1 - (lane + 32 * m)]);
+			put2(kTmTw1, tw4[lane], tw4[lane + 64]);
+			put2(kTmTw1 + 8, tw4[l2], tw4[l2 + 64]);
+			put2(kTmTw2, tw4[128 + j0], tw4[136 + j0]);
+			for(int h = 0; h < 2; ++h) {
+				const int kk = h ? l2 : lane;
+				for(int g = 0; g < 2; ++g) {
+					const float2 r0 = s_rot1[kk + 64 * (4 * g)], r1 = s_rot1[kk + 64 * (4 * g + 1)], r2 = s_rot1[kk + 64 * (4 * g + 2)], r3 = s_rot1[kk + 64 * (4 * g + 3)];
+					put2(kTmRot + 16u * h + 8u * g, make_float4(r0.x, r0.y, r1.x, r1.y), make_float4(r2.x, r2.y, r3.x, r3.y));
+				}
+			}
+			for(int i = 0; i < 4; ++i) put2(kTmWin + 8u * i, sl4[lane + 32 * i], sl4[(Q1 >> 1) - 1 - (lane + 32 * i)]);
+			tm_wait_st();
+		}
+		tm_fence_before();
+		__syncthreads();
+		tm_fence_after();
+	}
 
 	// ---- warp-private areas ----
 	const uint32_t warp_bytes = (uint32_t) kWarpFixedBytes + P.curve_bytes;
@@ -759,11 +884,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			// FFT buffer of FFT f: Q/64 sub-FFT rows of 72 slots (one row for Q = 64)
 			const uint32_t Ts = smem_u32(T), Tfs = Ts + (uint32_t) f * (uint32_t) ((Qs >> 6) * 72 * 8);
 			const uint32_t rots = smem_u32(flag ? s_rot1 : s_rot0), tws = smem_u32(flag ? s_tw1 : s_tw0);
+			// (a whole-warp FFT has f = 0 in every lane: the call below is warp uniform there, which the tensor-memory loads need)
 			if(f < count)
-				spectral_dispatch<kMaxNL>(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u);
+				spectral_dispatch<kMaxNL>(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u,
+				                          (kTm && flag) ? tmw : 0u);
 			__syncwarp();
 			// last pass output: long: lo half -> survivor slot, hi half -> slot B; short: D of FFT f packed at T + Q0 f (lo | hi)
-			if(flag && !kLongGrouped) fft_passes<Q1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB));
+			if(flag && !kLongGrouped) fft_passes<Q1, kTm>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB), tmw);
 			else if(flag) {
 				const uint32_t lo = Ts + (uint32_t) f * (uint32_t) (Q1 * 8);
 				fft_passes<Q1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, lo, lo + (uint32_t) (Q1 / 2 * 8));
@@ -788,8 +915,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				if(emits) {
 					const uint64_t chan_base = chan0 + w.pcm_rel;
 					if(flag && prev_n == N1 && lc == N1 / 2 && prev_right == N1 / 2 && emit == (uint32_t) (N1 / 2) && (!planar || (chan_base & 3ull) == 0)) {
-						if constexpr(planar) ola_long_long<Q1, false>(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, 1, lane);
-						else ola_long_long<Q1, true>(prev_lo, cur_hi, s_slope1, b.pcm + st.pcm_base + (frame0 + w.pcm_rel) * (uint64_t) C + (uint64_t) ch, C, lane);
+						if constexpr(planar) ola_long_long<Q1, false, kTm>(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, 1, lane, tmw);
+						else ola_long_long<Q1, true, kTm>(prev_lo, cur_hi, s_slope1, b.pcm + st.pcm_base + (frame0 + w.pcm_rel) * (uint64_t) C + (uint64_t) ch, C, lane, tmw);
 					} else {
 						OlaGeom G;
 						G.Hp = prev_n / 4; G.H = Q;
@@ -827,6 +954,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			first += count;
 			par ^= 1;
 		}
+	}
+	if constexpr(kTm) {
+		tm_fence_before();
+		__syncthreads();
+		if(warp == kWarps - 1) tm_dealloc(*s_tmbase);
 	}
 }
 

@@ -7,7 +7,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
 #include <map>
+#include <new>
 
 namespace pov {
 
@@ -175,11 +177,15 @@ static bool parse_codebook(BitCursor& br, HuffBook& book, const Fail& fail) {
 	const bool ordered = br.get(1);
 	if(!ordered) {
 		const bool sparse = br.get(1);
+		// every entry costs at least one bit (sparse flag) or five (length): a packet too short for them is truncated,
+		// whatever the 24-bit entry count claims
+		REQUIRE((uint64_t) book.n_entries * (sparse ? 1u : 5u) <= br.nbits - std::min(br.nbits, br.pos), "codebook: truncated (hpp:327)");
 		for(uint32_t i = 0; i < book.n_entries; ++i) {
 			if(sparse && !br.get(1)) continue;
 			lens.push_back((uint8_t) (br.get(5) + 1));
 			nums.push_back(i);
 		}
+		REQUIRE(!br.overrun, "codebook: truncated (hpp:327)");
 	} else {
 		uint32_t len = br.get(5) + 1, cur = 0;
 		while(cur < book.n_entries) {
@@ -200,29 +206,37 @@ static bool parse_codebook(BitCursor& br, HuffBook& book, const Fail& fail) {
 		const double delta = float32_unpack(br.get(32));
 		const int value_bits = (int) br.get(4) + 1;
 		const bool sequence_p = br.get(1);
-		uint32_t n_values;
+		// The expanded table holds n_entries * dim floats. The reference computes that product (and, for lookup type 2, the
+		// multiplicand count) in 32 bits; here both are 64-bit, and a table beyond kMaxVqValues floats is refused as
+		// unsupported instead of being allocated (a crafted 117-byte header can ask for 275 GB).
+		constexpr uint64_t kMaxVqValues = 1ull << 24;
+		const uint64_t table_values = (uint64_t) book.n_entries * book.dim;
+		REQUIRE(table_values <= kMaxVqValues, "codebook: VQ table of %llu values exceeds this build's limit of %llu",
+		        (unsigned long long) table_values, (unsigned long long) kMaxVqValues);
+		uint64_t n_values;
 		if(book.lookup_type == 1) {          // lookup1_values (hpp:314-316), 32-bit wrap-around included
-			n_values = 0;
-			while(pow_u32(n_values + 1, book.dim) <= book.n_entries) ++n_values;
+			uint32_t nv = 0;
+			while(pow_u32(nv + 1, book.dim) <= book.n_entries) ++nv;
+			n_values = nv;
 		} else {
-			n_values = book.n_entries * book.dim;
+			n_values = table_values;
 		}
-		REQUIRE((uint64_t) n_values * value_bits <= br.nbits, "codebook: truncated multiplicands (hpp:327)");
-		std::vector<uint32_t> mult(n_values);
-		for(uint32_t i = 0; i < n_values; ++i) mult[i] = br.get(value_bits);
+		REQUIRE(n_values * (uint64_t) value_bits <= br.nbits - std::min(br.nbits, br.pos), "codebook: truncated multiplicands (hpp:327)");
+		std::vector<uint32_t> mult((size_t) n_values);
+		for(size_t i = 0; i < (size_t) n_values; ++i) mult[i] = br.get(value_bits);
 		// hpp:212-245: double arithmetic, each element rounded to float; `last` re-reads the rounded value
-		book.vq.assign((size_t) book.n_entries * book.dim, 0.f);
+		book.vq.assign((size_t) table_values, 0.f);
 		if(book.lookup_type == 1) {
 			REQUIRE(n_values > 0, "codebook: no lookup values");
 			for(uint32_t e = 0; e < book.n_entries; ++e) {
 				double last = 0;
 				uint32_t div = 1;
 				for(uint32_t d = 0; d < book.dim; ++d) {
-					const uint32_t off = (div ? e / div : 0) % n_values;
+					const uint32_t off = (div ? e / div : 0) % (uint32_t) n_values;
 					const float v = (float) (mult[off] * delta + minimum + last);
 					book.vq[(size_t) e * book.dim + d] = v;
 					if(sequence_p) last = v;
-					div *= n_values;
+					div *= (uint32_t) n_values;
 				}
 			}
 		} else {
@@ -368,6 +382,21 @@ static bool parse_setup_packet(const uint8_t* p, size_t len, VorbisSetup& s, con
 	uint32_t maxe = 0;
 	for(auto& b : s.books) maxe = std::max(maxe, b.n_entries);
 	s.entry_bits = maxe > 65536 ? 32 : 16;
+	// What the residue walk below relies on, checked once per setup instead of once per packet. The reference checks the
+	// classbook at decode time (hpp:700) and indexes the VQ books unchecked (hpp:727); for a VQ dimension that does not
+	// divide the partition size its type-1 loop (hpp:744-752) writes past the partition, its type-0 loop (hpp:736-742) leaves
+	// bins untouched: neither is decodable audio, so such a setup is refused here.
+	for(size_t ri = 0; ri < s.residues.size(); ++ri) {
+		const ResidueSetup& r = s.residues[ri];
+		REQUIRE(r.classbook < nbooks, "residue %zu: classbook %u out of range (hpp:700)", ri, r.classbook);
+		for(uint32_t i = 0; i < r.n_class * 8; ++i) {
+			const uint32_t bk = r.books[i];
+			if(bk == POV_NO_BOOK) continue;
+			REQUIRE(bk < nbooks, "residue %zu: VQ book %u out of range (hpp:727)", ri, bk);
+			REQUIRE(r.partition_size % s.books[bk].dim == 0, "residue %zu: VQ dimension %u does not divide the partition size %u (unsupported)",
+			        ri, s.books[bk].dim, r.partition_size);
+		}
+	}
 	return true;
 }
 
@@ -375,8 +404,12 @@ static bool parse_setup_packet(const uint8_t* p, size_t len, VorbisSetup& s, con
 // audio packet -> descriptors: hpp:1128-1211 (mode/window, floor Y reads, residue classification + cascade walk)
 // and the emit bookkeeping of VorbisStreamDecodeState (hpp:1019-1059, 1061-1067)
 // ---------------------------------------------------------------------------------------------------------------
-// The walk is the reference's (hpp:697-760): 8 passes over the partitions, a classification word every cb.dim partitions
-// in pass 0, then per partition and channel the vectors of the (class, pass) book. The hot loop keeps the bit position in
+// The walk is Vorbis I 8.6.2 as the reference implements it (hpp:697-760): 8 passes over the partitions, a classification
+// word every cb.dim partitions in pass 0, then per partition and channel the vectors of the (class, pass) book.
+// One deliberate difference: the reference advances `partition_count` INSIDE its channel loop (hpp:755), which is the
+// spec's order only when a submap has one channel (always true for residue type 2, and for mono streams); with several
+// channels of type 0/1 it skips partitions and can index past the vector. Here — and in the device kernels — the count
+// advances once per partition, as the spec says (DESIGN.md "Deliberate divergences"). The hot loop keeps the bit position in
 // a register, decodes through the 10-bit first-level tables in place and writes the entry numbers straight into a
 // per-thread scratch array sized for the worst case (every partition coded in every pass with one-dimensional vectors).
 static bool decode_residue_submap(BitCursor& br, const VorbisSetup& s, const ResidueSetup& r, uint32_t nch, const uint8_t* used,
@@ -607,7 +640,22 @@ static bool check_comment_packet(const uint8_t* p, size_t len, const Fail& fail)
 	return true;
 }
 
+static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err);
+// Never throws: an allocation failure (or any other exception) while parsing hostile input is a parse error like the rest.
 bool parse_ogg_file(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err) {
+	try {
+		return parse_ogg_file_checked(data, len, streams, err);
+	} catch(const std::bad_alloc&) {
+		err.failed = true; err.msg = "out of memory while parsing (sizes in the stream beyond what this machine can hold)";
+	} catch(const std::exception& e) {
+		err.failed = true; err.msg = std::string("internal error while parsing: ") + e.what();
+	} catch(...) {
+		err.failed = true; err.msg = "internal error while parsing";
+	}
+	return false;
+}
+
+static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err) {
 	Fail fail{err};
 	std::map<uint32_t, size_t> live;                     // serial -> index into streams (erased at EOS, hpp:1480)
 	size_t pos = 0;
