@@ -189,6 +189,10 @@ uint64_t    pov_ctx_launch_count(const pov_ctx* ctx);
 
 /* The 256-entry floor1_inverse_dB_table this library uses (reference: src/inverse_db_table.h:13-78). Host only. */
 void        pov_inverse_db_table(float out[256]);
+/* The window of a block (hpp:837-862: VorbisModeNumber::precalc / getWindow) as the kernels' slope tables define it:
+ * n = blocksize[blockflag] floats. Host-only (no context, no device): the overlap-add stage multiplies by exactly
+ * these values. Returns POV_ERR_ARG for block sizes outside 64..8192 / not powers of two / bs0 > bs1 / n mismatch. */
+int         pov_window(uint32_t blocksize0, uint32_t blocksize1, int blockflag, int prev, int next, float* out, uint32_t n);
 
 /* Validate + upload one stream setup; derived tables (neighbours, sort order, windows, twiddles) are built here. */
 int         pov_setup_register(pov_ctx* ctx, const pov_setup* setup, uint32_t* setup_id_out);

@@ -161,6 +161,11 @@ static int get_block_tables(pov_ctx* ctx, uint32_t n, BlockTables** out) {
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_fftp, fftp.data(), fftp.size(), ctx->stream));
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_fft8, fft8.data(), fft8.size(), ctx->stream));
 	CUDA_TRY(ctx, dev_upload((float**) &t.d_slope, slope.data(), slope.size(), ctx->stream));
+	std::vector<float> tm;
+	if(n == 2048) {
+		make_tm_lane_tables(n, rot, slope, tm);
+		CUDA_TRY(ctx, dev_upload((float**) &t.d_tm, tm.data(), tm.size(), ctx->stream));
+	}
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	auto ins = ctx->blk_tables.emplace(n, std::move(t));
 	*out = &ins.first->second;
@@ -440,6 +445,15 @@ extern "C" int pov_setup_entry_bits(const pov_ctx* ctx, uint32_t id) {
 	if(!ctx || id >= ctx->setups.size()) return -1;
 	return (int) ctx->setups[id].entry_bits;
 }
+
+extern "C" int pov_window(uint32_t bs0, uint32_t bs1, int blockflag, int prev, int next, float* out, uint32_t n) try {
+	if(!out || !is_pow2_in(bs0, 64, 8192) || !is_pow2_in(bs1, 64, 8192) || bs0 > bs1) return POV_ERR_ARG;
+	std::vector<float> w;
+	make_window(bs0, bs1, blockflag, prev, next, w);
+	if(w.size() != n) return POV_ERR_ARG;
+	memcpy(out, w.data(), n * sizeof(float));
+	return POV_OK;
+} catch(...) { return POV_ERR_ARG; }
 
 extern "C" int pov_setup_get_window(const pov_ctx* ctx, uint32_t id, int blockflag, int prev, int next, float* out, uint32_t n) {
 	if(!ctx || id >= ctx->setups.size() || !out) return POV_ERR_ARG;
@@ -755,7 +769,8 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) try {
 		for(const WarpGroup& g : h->warp_groups) {      // one persistent launch per setup (its tables live in shared memory)
 			const SetupRec& su = ctx->setups[g.setup];
 			CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr + g.first_run, g.n_runs, su.channels, su.d_fast, su.blocksize[0], su.blocksize[1],
-			                          su.fast_short_cap, su.fast_max_nl, su.dev.slope, su.dev.rot, su.dev.fft8, su.dev.fftp, ctx->d_counter, ctx->sm_count, ctx->stream,
+			                          su.fast_short_cap, su.fast_max_nl, su.dev.slope, su.dev.rot, su.dev.fft8, su.dev.fftp,
+			                          ctx->blk_tables.count(2048) ? ctx->blk_tables[2048].d_tm : nullptr, ctx->d_counter, ctx->sm_count, ctx->stream,
 			                          &ctx->launches));
 		}
 		return POV_OK;

@@ -27,6 +27,7 @@ struct BlockTables {              // per blocksize n: DCT-IV rotation, FFT twidd
 	float c1[2] = {1, 0}, c6[2] = {1, 0};
 	const float*  d_slope = nullptr;
 	std::vector<float> h_slope;
+	const float*  d_tm = nullptr;     // n == 2048: lane rows of the tensor-memory FFT (make_tm_lane_tables)
 };
 
 struct SetupRec {

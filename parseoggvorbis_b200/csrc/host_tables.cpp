@@ -122,6 +122,55 @@ void make_rotation_consts(uint32_t n, float c1[2], float c6[2]) {
 	c6[0] = (float) cos(M_PI * 6.0 / (8.0 * M)); c6[1] = (float) sin(M_PI * 6.0 / (8.0 * M));
 }
 
+// ---- tensor-memory lane tables of the 512-point FFT -------------------------------------------------------------------
+// The FFT (kernel_warp.cu fft512_tm; executable model with the measured tcgen05 shape maps: tools/model/tmem_fft_model.py):
+//   pass 1  radix 8 over j8 j7 j6, lane = (j5 j4 j3 j2 j1), registers 2 k0 + j0
+//   pass 2  radix 4 over j5 j4,    lane = (j3 j2 j1 | k0_1^r k0_0^r), r = k0_2
+//   pass 3  radix 4 over j3 j2,    lane = (j1 . . | k1_1^r k1_0^r)
+//   pass 4  radix 4 over j1 j0,    lane t = (k0_1^r k1_1^r k1_0^r k2_1^r k2_0^r), register R = 8 k3_1 + 4 r + 2 k3_0 + (k0_0 ^ r)
+// output frequency k = k0 + 8 k1 + 32 k2 + 128 k3.
+uint32_t tm_fft_freq_of(uint32_t lane, uint32_t reg) {
+	const uint32_t k3 = ((reg >> 3) << 1) | ((reg >> 1) & 1), r = (reg >> 2) & 1, h = reg & 1, x = r ? 1u : 0u;
+	const uint32_t k0_0 = h ^ x, k0_1 = ((lane >> 4) & 1) ^ x, k0_2 = r;
+	const uint32_t k1 = ((lane >> 2) & 3) ^ (x * 3), k2 = (lane & 3) ^ (x * 3);
+	return k0_0 | (k0_1 << 1) | (k0_2 << 2) | (k1 << 3) | (k2 << 5) | (k3 << 7);
+}
+
+void make_tm_lane_tables(uint32_t n, const std::vector<float>& rot, const std::vector<float>& slope, std::vector<float>& out) {
+	const uint32_t Q = n / 4;                 // 512
+	out.assign(32 * (size_t) kTmTableCols, 0.f);
+	auto W = [](double e, double N, float* dst) { const double a = -2.0 * M_PI * e / N; dst[0] = (float) cos(a); dst[1] = (float) sin(a); };
+	for(uint32_t l = 0; l < 32; ++l) {
+		float* row = &out[(size_t) l * kTmTableCols];
+		// [0,32): spectral stage, quads q = l + 32 m and Q/2 - 1 - q: rotation pairs (w[2q], w[2q+1])
+		for(uint32_t m = 0; m < 4; ++m) {
+			const uint32_t q = l + 32 * m, q2 = Q / 2 - 1 - q;
+			for(uint32_t i = 0; i < 4; ++i) { row[8 * m + i] = rot[4 * q + i]; row[8 * m + 4 + i] = rot[4 * q2 + i]; }
+		}
+		// [32,48): pass 1 twiddles W_512^(e c), c = 1..4, e = 2 l + j0
+		for(uint32_t j0 = 0; j0 < 2; ++j0)
+			for(uint32_t c = 1; c <= 4; ++c) W((double) ((2 * l + j0) * c), 512.0, row + 32 + 8 * j0 + 2 * (c - 1));
+		// [48,64): pass 2 twiddles W_64^(e c), c = 1..3, e = (j3 j2 j1 j0) = 2 (l >> 2) + j0
+		for(uint32_t j0 = 0; j0 < 2; ++j0)
+			for(uint32_t c = 1; c <= 3; ++c) W((double) ((2 * (l >> 2) + j0) * c), 64.0, row + 48 + 8 * j0 + 2 * (c - 1));
+		// [64,80): pass 3 twiddles W_16^(e c), c = 1..3, e = (j1 j0) = 2 (l >> 4) + j0
+		for(uint32_t j0 = 0; j0 < 2; ++j0)
+			for(uint32_t c = 1; c <= 3; ++c) W((double) ((2 * (l >> 4) + j0) * c), 16.0, row + 64 + 8 * j0 + 2 * (c - 1));
+		// [80,112): post-rotation w[k] of the 16 outputs in register order
+		for(uint32_t R = 0; R < 16; ++R) {
+			const uint32_t k = tm_fft_freq_of(l, R);
+			row[80 + 2 * R] = rot[2 * k]; row[80 + 2 * R + 1] = rot[2 * k + 1];
+		}
+		// [112,144): overlap-add, iteration i: rising slope at j..j+3 and at 2Q-4-j..2Q-1-j, j = 4 * (true quad of storage quad 32 i + l)
+		for(uint32_t i = 0; i < 4; ++i) {
+			const uint32_t sq = 32 * i + l;
+			const uint32_t tq = (sq & 0x44u) | ((sq & 3u) << 4) | ((sq & 0x20u) >> 2) | ((sq & 0x18u) >> 3);
+			const uint32_t j = 4 * tq;
+			for(uint32_t e = 0; e < 4; ++e) { row[112 + 8 * i + e] = slope[j + e]; row[112 + 8 * i + 4 + e] = slope[2 * Q - 4 - j + e]; }
+		}
+	}
+}
+
 // Neighbours (src/Utils.hpp:60-118) depend on the X list only, so they are found once here instead of once per
 // packet and post as in the reference (hpp:532-533). level[] orders the posts so that a post's two neighbours
 // are final before it is unwrapped; sorted_idx is the ascending-x order of hpp:458-469.

@@ -23,6 +23,12 @@ void make_fft_pass_tables(uint32_t n, std::vector<float>& out_re_im);
 // compact radix-8 pass tables (layout: fft_core.cuh Tw8Tables<Q>) and the rotation helper constants
 void make_fft_r8_tables(uint32_t n, std::vector<float>& out_re_im);
 void make_rotation_consts(uint32_t n, float c1[2], float c6[2]);
+// Per-lane factor rows of the 512-point register FFT whose lane <-> register exchanges go through tensor memory
+// (kernel_warp.cu "fft512_tm"): [32 lanes][kTmTableCols] floats, block size n = 2048 only. Column map in kernel_warp.cu.
+constexpr uint32_t kTmTableCols = 144;
+void make_tm_lane_tables(uint32_t n, const std::vector<float>& rot_re_im, const std::vector<float>& slope, std::vector<float>& out);
+// index maps of that FFT (shared by the table generator and the tests' model): output frequency held by (lane, register)
+uint32_t tm_fft_freq_of(uint32_t lane, uint32_t reg);
 // floor1 derived tables. Returns false (with msg) when the X list is not usable.
 bool make_floor_tables(const pov_floor1& in, DevFloor& out, std::string& msg);
 

