@@ -40,7 +40,13 @@ constexpr int kSlotF2 = kRegionF2 / 2;  // the work area of a warp is three half
                                         // A+B and leave their overlap half (D lo) in A, odd steps use B+C and leave it in C;
                                         // the other half (D hi, consumed by the same step's overlap-add) always lands in B
 #ifndef POV_WARP_TMEM
-#define POV_WARP_TMEM 2        // tensor memory: 0 = unused (round-1 layout), 1 = per-lane factor tables, 2 = tables + the FFT exchanges (fft512_tm)
+#define POV_WARP_TMEM 1        // tensor memory: 0 = unused (round-1 layout), 1 = per-lane factor tables (default), 2 = tables + the FFT exchanges (fft512_tm; measured slower)
+#endif
+#ifndef POV_TM_SPLIT_LD
+#define POV_TM_SPLIT_LD 1
+#endif
+#ifndef POV_TM_SPLIT_ST
+#define POV_TM_SPLIT_ST 0
 #endif
 #ifndef POV_WARP_PKT_CAP
 #define POV_WARP_PKT_CAP 32
@@ -523,6 +529,14 @@ __device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&r)[16]) {
 	asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
 	             : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]) : "r"(taddr));
 }
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const float* c) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+	             :: "r"(taddr), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]), "f"(c[4]), "f"(c[5]), "f"(c[6]), "f"(c[7]), "f"(c[8]), "f"(c[9]), "f"(c[10]), "f"(c[11]), "f"(c[12]), "f"(c[13]), "f"(c[14]), "f"(c[15]) : "memory");
+}
+__device__ __forceinline__ void tm_ld16h(uint32_t taddr, float (&r)[8]) {        // 16 lanes x 16 columns
+	asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "r"(taddr));
+}
 __device__ __forceinline__ void tm_wait32(float (&a)[16], float (&b)[16]) {
 	asm volatile("tcgen05.wait::ld.sync.aligned;"
 	             : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(a[8]), "+f"(a[9]), "+f"(a[10]), "+f"(a[11]), "+f"(a[12]), "+f"(a[13]), "+f"(a[14]), "+f"(a[15]), "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]), "+f"(b[8]), "+f"(b[9]), "+f"(b[10]), "+f"(b[11]), "+f"(b[12]), "+f"(b[13]), "+f"(b[14]), "+f"(b[15]));
@@ -543,15 +557,37 @@ __device__ __forceinline__ void tm_exchange(uint32_t xa, float2 (&v)[16]) {
 	float c[32];
 #pragma unroll
 	for(int reg = 0; reg < 16; ++reg) { c[2 * tm_colmap<kX>(reg)] = v[reg].x; c[2 * tm_colmap<kX>(reg) + 1] = v[reg].y; }
+#if POV_TM_SPLIT_ST
+	tm_st16(xa, c);
+	tm_st16(xa + 16u, c + 16);
+#else
 	tm_st32(xa, c);
+#endif
+#ifndef POV_TM_NOFENCE
 	tm_wait_st();
+#endif
 	__syncwarp();
+#if POV_TM_SPLIT_LD
+	// four loads of 16 lanes x 16 columns: complex register 8 I + 4 cg + 2 k + h <- column group cg (two 256-bit atoms each)
+	float q0[8], q1[8], q2[8], q3[8];
+	tm_ld16h(xa, q0);
+	tm_ld16h(xa + 16u, q1);
+	tm_ld16h(xa + (16u << 16), q2);
+	tm_ld16h(xa + (16u << 16) + 16u, q3);
+	tm_wait8(q0); tm_wait8(q1); tm_wait8(q2); tm_wait8(q3);
+#pragma unroll
+	for(int i = 0; i < 4; ++i) {
+		v[i] = make_float2(q0[2 * i], q0[2 * i + 1]); v[4 + i] = make_float2(q1[2 * i], q1[2 * i + 1]);
+		v[8 + i] = make_float2(q2[2 * i], q2[2 * i + 1]); v[12 + i] = make_float2(q3[2 * i], q3[2 * i + 1]);
+	}
+#else
 	float r0[16], r1[16];
 	tm_ld16(xa, r0);
 	tm_ld16(xa + (16u << 16), r1);
 	tm_wait32(r0, r1);
 #pragma unroll
 	for(int i = 0; i < 8; ++i) { v[i] = make_float2(r0[2 * i], r0[2 * i + 1]); v[8 + i] = make_float2(r1[2 * i], r1[2 * i + 1]); }
+#endif
 }
 
 // Column map of a lane's table row for the exchange variant (host_tables.cpp: make_tm_lane_tables):
@@ -986,18 +1022,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			w.spec_rel = (int32_t) (int64_t) (b.spec_off[run.first_packet + lane] - spec0);
 			wp[lane] = w;
 		}
-		const pov_stream st = b.streams[pk0->stream];
 		const float* spec_base = b.spectra + spec0;
-		const uint64_t frame0 = pcm0;           // stream frame index of the run's first packet chunk
+		// where this run's first chunk starts in the PCM arena, for this channel (one pointer instead of the stream record):
+		//   planar:      pcm_base + ch * pcm_frames + frame,  + 1 per frame;   interleaved: pcm_base + frame * C + ch,  + C per frame
+		float* out0;
+		bool first_of_stream;                   // the run starts at its stream's first packet, which only primes the overlap (hpp:1021)
+		{
+			const pov_stream st = b.streams[pk0->stream];
+			out0 = b.pcm + (planar ? st.pcm_base + (uint64_t) ch * st.pcm_frames + pcm0 : st.pcm_base + pcm0 * (uint64_t) C + (uint64_t) ch);
+			first_of_stream = run.first_packet == st.first_packet;
+		}
 		__syncwarp();
 		unwrap_run(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, (uint32_t) N0, (uint32_t) N1, lane);
 
-		int prev_valid = 0, prev_n = 0, prev_right = 0;
-		bool prev_perm = false;                  // the previous frame's D lo half is in fft512_tm's storage order
-		const float* prev_lo = nullptr;
-		int par = 0;                             // step parity: which half regions this step uses
-		int first = 0;
-		while(first < run_n) {
+		// State carried from step to step, packed into one register (the FFT in between needs every register it can get):
+		//   bit 0 step parity (which half regions the step uses) | bit 1 a previous frame exists | bit 2 it was a long block |
+		//   bit 3 its right slope is long | bit 4 its D lo half is in fft512_tm's storage order | bit 5 the run starts at its
+		//   stream's first packet | bits 8.. index of the step's first packet in the run.
+		// The previous frame's D lo half always sits in the survivor slot of the previous step (slot A or C by its parity).
+		uint32_t stt = first_of_stream ? 32u : 0u;
+		while((int) (stt >> 8) < run_n) {
+			const int first = (int) (stt >> 8);
+			const int par = (int) (stt & 1u);
 			const uint32_t meta0 = wp[first].meta;
 			const uint32_t mode = meta0 & 0xffu;
 			const int flag = tb->mode_flag[mode];
@@ -1067,7 +1113,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			// ================= window + overlap-add + emit (hpp:1008-1059 in gather form) =================
 			const int n = flag ? N1 : N0, Q = n / 4;
 			const float* Dstep = reinterpret_cast<const float*>(T);
-			const uint64_t chan0 = st.pcm_base + (uint64_t) ch * st.pcm_frames + frame0;
+			int prev_valid = (int) ((stt >> 1) & 1u), prev_n = (stt & 4u) ? N1 : N0, prev_right = (stt & 8u) ? N1 / 2 : N0 / 2;
+			bool prev_perm = (stt & 16u) != 0;
+			const float* prev_lo = reinterpret_cast<const float*>(slotA + (par ^ 1) * (2 * kSlotF2));
 			for(int g = 0; g < count; ++g) {
 				const WPkt& w = wp[first + g];
 				const uint32_t wflags = (w.meta >> 8) & 0xffu, emit = w.emit;
@@ -1076,12 +1124,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				const int rc = (flag && (wflags & 2u)) ? N1 / 2 : N0 / 2;
 				const float* cur_lo = !grouped ? reinterpret_cast<const float*>(surv) : Dstep + (size_t) g * 2 * Q;
 				const float* cur_hi = !grouped ? reinterpret_cast<const float*>(slotB) : cur_lo + Q;
-				const bool emits = prev_valid && emit > 0 && (run.first_packet + (uint32_t) (first + g)) != st.first_packet;
+				const bool emits = prev_valid && emit > 0 && !((stt & 32u) && first + g == 0);
 				if(emits) {
-					const uint64_t chan_base = chan0 + w.pcm_rel;
-					if(flag && prev_n == N1 && lc == N1 / 2 && prev_right == N1 / 2 && emit == (uint32_t) (N1 / 2) && (!planar || (chan_base & 3ull) == 0)) {
-						if constexpr(planar) ola_long_long<Q1, false, kTm>(prev_lo, cur_hi, s_slope1, b.pcm + chan_base, 1, lane, tmw);
-						else ola_long_long<Q1, true, kTm>(prev_lo, cur_hi, s_slope1, b.pcm + st.pcm_base + (frame0 + w.pcm_rel) * (uint64_t) C + (uint64_t) ch, C, lane, tmw);
+					float* const dst = out0 + (planar ? (size_t) w.pcm_rel : (size_t) w.pcm_rel * (size_t) C);
+					if(flag && prev_n == N1 && lc == N1 / 2 && prev_right == N1 / 2 && emit == (uint32_t) (N1 / 2) && (!planar || ((size_t) dst & 15) == 0)) {
+						if constexpr(planar) ola_long_long<Q1, false, kTm>(prev_lo, cur_hi, s_slope1, dst, 1, lane, tmw);
+						else ola_long_long<Q1, true, kTm>(prev_lo, cur_hi, s_slope1, dst, C, lane, tmw);
 					} else {
 						OlaGeom G;
 						G.Hp = prev_n / 4; G.H = Q;
@@ -1093,9 +1141,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 						G.pperm = prev_perm; G.cperm = (kTm == 2) && flag && !kLongGrouped;
 						for(uint32_t j = (uint32_t) lane; j < emit; j += 32u) {
 							const float v = ola_one(G, prev_lo, cur_hi, (int) j);
-							const uint64_t fidx = frame0 + w.pcm_rel + j;
-							const uint64_t o = planar ? st.pcm_base + (uint64_t) ch * st.pcm_frames + fidx : st.pcm_base + fidx * (uint64_t) C + (uint64_t) ch;
-							b.pcm[o] = v;
+							dst[planar ? (size_t) j : (size_t) j * (size_t) C] = v;
 						}
 					}
 				}
@@ -1118,8 +1164,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				__syncwarp();
 				prev_lo = reinterpret_cast<const float*>(surv);
 			}
-			first += count;
-			par ^= 1;
+			stt = ((uint32_t) (first + count) << 8) | (stt & 32u) | (prev_perm ? 16u : 0u) | (prev_right == N1 / 2 ? 8u : 0u) | (prev_n == N1 ? 4u : 0u) | 2u |
+			      (uint32_t) (par ^ 1);
 		}
 	}
 	if constexpr(kTm != 0) {

@@ -125,6 +125,55 @@ __global__ void __launch_bounds__(640, 1) k_bw(uint32_t* out, int iters, long lo
 	if(warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(s_base) : "memory");
 }
 
+// exchange trip as in k_warp_synth: STTM.x32 -> (wait::st) -> 2 x LDTM.16dp256bit.x4 -> wait::ld, 20 warps, with FILL dependent FFMAs per trip
+template <int FENCE, int FILL>
+__global__ void __launch_bounds__(640, 1) k_trip(uint32_t* out, int iters, long long* cycles) {
+	__shared__ uint32_t s_base;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if(warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_base)) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t xa = s_base + ((uint32_t) ((warp & 3) * 32) << 16) + 32u * (uint32_t) (warp >> 2);
+	float v[32];
+	for(int i = 0; i < 32; ++i) v[i] = (float) (lane * 32 + i);
+	const long long t0 = clock64();
+	for(int it = 0; it < iters; ++it) {
+		asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+		             :: "r"(xa), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+		                "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31]) : "memory");
+		if(FENCE) wait_st();
+		__syncwarp();
+		asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		             : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "r"(xa));
+		asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		             : "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31]) : "r"(xa + (16u << 16)));
+		asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+		             "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]));
+#pragma unroll
+		for(int f = 0; f < FILL; ++f)
+#pragma unroll
+			for(int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0000001f, 0.5f);
+	}
+	const long long t1 = clock64();
+	float acc = 0; for(int i = 0; i < 32; ++i) acc += v[i];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = __float_as_uint(acc);
+	if(threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if(warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(s_base) : "memory");
+}
+template <int FENCE, int FILL> static void run_trip(uint32_t* o2, long long* cyc, int warps) {
+	const int iters = 20000;
+	for(int rep = 0; rep < 2; ++rep) { k_trip<FENCE, FILL><<<148, warps * 32>>>(o2, iters, cyc); cudaDeviceSynchronize(); }
+	long long c0; cudaMemcpy(&c0, cyc, 8, cudaMemcpyDeviceToHost);
+	printf("trip warps=%2d fence=%d fill=%2d FFMA/value: %s, %.1f cycles per trip and SM (all warps), %.1f per warp-trip\n", warps, FENCE, FILL,
+	       cudaGetErrorString(cudaGetLastError()), (double) c0 / iters / warps, (double) c0 / iters);
+}
+
 int main() {
 	uint32_t* d; cudaMalloc(&d, 12 * 4 * 32 * 8 * 4);
 	cudaMemset(d, 0xff, 12 * 4 * 32 * 8 * 4);
@@ -163,6 +212,10 @@ int main() {
 			printf("bw warps=%2d mode=%d (%s): %s %.3f ms, %lld cycles, %.1f B/clk/SM per memory kind\n", warps, mode, mode == 1 ? "tmem" : mode == 2 ? "smem" : "both",
 			       cudaGetErrorString(e), ms, c0, bytes / (double) c0);
 		}
+	}
+	for(int warps : {1, 4, 20}) {
+		run_trip<1, 0>(o2, cyc, warps); run_trip<0, 0>(o2, cyc, warps);
+		run_trip<1, 8>(o2, cyc, warps); run_trip<0, 8>(o2, cyc, warps);
 	}
 	return 0;
 }
