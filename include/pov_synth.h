@@ -256,6 +256,15 @@ int  pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* dat
                        uint32_t host_threads, uint64_t* frames_out, uint64_t* total_values_out,
                        double* checksum_out);
 
+/* The same decode with an output edge: `sink` receives the PCM of every logical stream, in file order, from the calling
+ * thread, as the chunk that holds it retires — the batch form of ParseCallbacks::gotPcmData (hpp:966-973, 1047-1053).
+ * `planar` is [channels][frames] (channel c at planar + c * frames) and is valid during the call only. A non-zero return
+ * stops the decode, which then fails with POV_ERR_STREAM like the reference's CHECK(callbacks.gotPcmData(...)). */
+typedef int (*pov_pcm_sink)(uint32_t file_index, uint32_t channels, uint64_t frames, const float* planar, void* user);
+int  pov_decode_corpus_pcm(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* data, const size_t* len,
+                           uint32_t host_threads, pov_pcm_sink sink, void* user,
+                           uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out);
+
 /* Host-only front-end (no GPU needed): parse a whole Ogg/Vorbis file into descriptor batches, one per logical stream
  * (Ogg framing hpp:51-102,1433-1484; headers hpp:1283-1373; per-packet entropy decode hpp:498-517, 711-757). The
  * setup/batch returned by pov_parsed_get point into memory owned by the handle (POV_INPUT_ENTRIES, setup_id 0). */

@@ -241,6 +241,7 @@ struct Chunk {
 	pov_stream* streams = nullptr;             // writable alias of view.streams
 	std::vector<StreamWork> setups;            // one representative stream (headers only) per distinct setup
 	std::vector<uint64_t> frames;              // per file
+	std::vector<uint32_t> stream_file, stream_channels;   // per stream of the batch: file index (corpus-wide), channel count
 	std::string error;
 };
 
@@ -316,8 +317,22 @@ void corpus_state_free(void* p) { delete (CorpusState*) p; }
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t) 15; }
 }  // namespace
 
+static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* data, const size_t* len, uint32_t host_threads,
+                         pov_pcm_sink sink, void* sink_user, uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out);
+
 extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* data, const size_t* len,
                                  uint32_t host_threads, uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out) try {
+	return decode_corpus(ctx, n_files, data, len, host_threads, nullptr, nullptr, frames_out, total_values_out, checksum_out);
+} POV_NOTHROW_END(ctx)
+
+extern "C" int pov_decode_corpus_pcm(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* data, const size_t* len, uint32_t host_threads,
+                                     pov_pcm_sink sink, void* user, uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out) try {
+	if(!sink) return pov_fail(ctx, POV_ERR_ARG, "pov_decode_corpus_pcm: null sink");
+	return decode_corpus(ctx, n_files, data, len, host_threads, sink, user, frames_out, total_values_out, checksum_out);
+} POV_NOTHROW_END(ctx)
+
+static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* data, const size_t* len, uint32_t host_threads,
+                         pov_pcm_sink sink, void* sink_user, uint64_t* frames_out, uint64_t* total_values_out, double* checksum_out) {
 	if(!ctx || (n_files && (!data || !len))) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	// automatic: every core but one — the calling thread validates, queues and retires chunks and must not be time-sliced
@@ -383,6 +398,8 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 					while(k < ck->setups.size() && ck->setups[k].setup_key != st.setup_key) ++k;
 					hb.append(st, k);
 					ck->frames[i] += st.frames;
+					ck->stream_file.push_back(ck->first_file + i);
+					ck->stream_channels.push_back(st.setup.channels);
 					if(k == ck->setups.size()) {
 						st.packets.clear(); st.ys.clear(); st.payload.clear();
 						ck->setups.push_back(std::move(st));
@@ -454,16 +471,28 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 			float a = 0, b = 0;
 			if(cudaEventElapsedTime(&a, sl.t_begin, sl.t_kernels) == cudaSuccess && cudaEventElapsedTime(&b, sl.t_kernels, sl.t_end) == cudaSuccess) { g_copy_in_kernels += a; g_copy_out += b; }
 		}
-		if(sl.in_flight) { cs.release(sl.in_flight->buf); sl.in_flight.reset(); }
-		if(!ok) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: chunk failed on the device");
-		for(uint32_t p = 0; p < sl.n_packets; ++p)
+		int out = POV_OK;
+		if(!ok) out = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: chunk failed on the device");
+		for(uint32_t p = 0; p < sl.n_packets && out == POV_OK; ++p)
 			if(sl.status[p]) {
 				const char* what = (sl.status[p] & POV_PKT_FLOOR_PREDICTED) ? "predicted <= range (hpp:536)"
 				                 : (sl.status[p] & POV_PKT_FLOOR_RANGE)     ? "floor[i] < 256 (hpp:587)"
 				                                                            : "temp.size() > 0 (hpp:739,748: VQ entry out of range)";
-				return pov_fail(ctx, POV_ERR_STREAM, "chunk at file %u, audio packet %u: check failed: %s", sl.first_file, p, what);
+				out = pov_fail(ctx, POV_ERR_STREAM, "chunk at file %u, audio packet %u: check failed: %s", sl.first_file, p, what);
 			}
-		return POV_OK;
+		// the output edge (hpp:966-973 gotPcmData, hpp:1047-1053): every logical stream of the chunk, in file order, from the
+		// calling thread; the samples stay valid during the callback only (they live in this slot's pinned buffer)
+		if(out == POV_OK && sink && sl.in_flight && sl.n_packets) {
+			const Chunk& ck = *sl.in_flight;
+			for(uint32_t i = 0; i < ck.view.n_streams && out == POV_OK; ++i) {
+				const pov_stream& rec = ck.streams[i];
+				if(rec.pcm_frames == 0) continue;                  // hpp:1045: nothing is delivered for an empty chunk
+				if(sink(ck.stream_file[i], ck.stream_channels[i], rec.pcm_frames, sl.pinned + rec.pcm_base, sink_user) != 0)
+					out = pov_fail(ctx, POV_ERR_STREAM, "file %u: check failed: callbacks.gotPcmData(channelPcms) (hpp:1052: the sink asked to stop)", ck.stream_file[i]);
+			}
+		}
+		if(sl.in_flight) { cs.release(sl.in_flight->buf); sl.in_flight.reset(); }
+		return out;
 	};
 
 	// POV_CORPUS_TIMING=1: where the calling thread's time goes (stderr), to tell a starved consumer from a slow one
@@ -538,7 +567,10 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 		total += pcm_floats;
 		t_fetch += now() - t0;
 	}
-	for(auto& sl : cs.slot) { const int r2 = retire(sl); if(rc == POV_OK) rc = r2; }
+	for(uint32_t k = 0; k < 2; ++k) {          // oldest chunk first: chunk n-2 sits in slot n & 1 (file order at the output edge)
+		const int r2 = retire(cs.slot[(n_chunks + k) & 1]);
+		if(rc == POV_OK) rc = r2;
+	}
 	if(timing)
 		fprintf(stderr, "pov_decode_corpus: %u chunks in %.3f s on the calling thread: wait for parsed chunks %.3f, "
 		        "setup ids + wait for the slot %.3f, validate+queue upload %.3f, launch %.3f, fetch/issue %.3f; on the streams (sum over chunks): "
@@ -563,7 +595,7 @@ extern "C" int pov_decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* 
 	if(total_values_out) *total_values_out = total;
 	if(checksum_out) *checksum_out = h_sum;
 	return rc;
-} POV_NOTHROW_END(ctx)
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // same shape as the reference's C entry point (hpp:1493): decode, discard the PCM, report errors as a string

@@ -23,9 +23,12 @@ SYMBOLS = [
     "pov_ctx_launch_count", "pov_setup_register", "pov_setup_entry_bits", "pov_setup_get_window",
     "pov_batch_upload", "pov_batch_run", "pov_batch_kernel_name", "pov_batch_run_staged", "pov_batch_fetch_pcm", "pov_batch_pcm_dev",
     "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_mdct_backward_batch",
-    "pov_ogg_vorbis_decode_memory", "pov_decoded_free", "pov_decode_corpus", "pov_ogg_vorbis_full_read_from_memory",
+    "pov_ogg_vorbis_decode_memory", "pov_decoded_free", "pov_decode_corpus", "pov_decode_corpus_pcm", "pov_ogg_vorbis_full_read_from_memory",
     "pov_ogg_parse_memory", "pov_parsed_stream_count", "pov_parsed_get", "pov_parsed_free",
 ]
+
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_float), C.c_void_p)
 
 
 class PovError(RuntimeError):
@@ -82,6 +85,8 @@ def load() -> C.CDLL:
     L.pov_decoded_free.restype = None
     L.pov_decode_corpus.argtypes = [vp, u32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), u32,
                                     C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
+    L.pov_decode_corpus_pcm.argtypes = [vp, u32, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), u32, SINK_FN, vp,
+                                        C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
     L.pov_ogg_vorbis_full_read_from_memory.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p)]
     L.pov_ogg_parse_memory.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_char_p)]
     L.pov_parsed_stream_count.argtypes = [vp]
@@ -274,4 +279,23 @@ class SynthContext:
         chk = C.c_double(0)
         self._check(self.L.pov_decode_corpus(self.ctx, n, arr, lens, host_threads,
                                              frames.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(total), C.byref(chk)))
+        return frames, int(total.value), float(chk.value)
+
+    def decode_corpus_pcm(self, files, sink, host_threads: int = 0):
+        """The corpus decode with its output edge (pov_decode_corpus_pcm): `sink(file_index, pcm)` is called from this thread
+        for every logical stream, in file order, with a (channels, frames) float32 array that is only valid during the call;
+        a true return value stops the decode (PovError, like the reference's CHECK(callbacks.gotPcmData(...)))."""
+        n = len(files)
+        arr = (C.c_char_p * n)(*files)
+        lens = (C.c_size_t * n)(*[len(f) for f in files])
+        frames = np.zeros(n, np.uint64)
+        total = C.c_uint64(0)
+        chk = C.c_double(0)
+
+        @SINK_FN
+        def _sink(file_index, channels, nframes, planar, user):
+            pcm = np.ctypeslib.as_array(planar, shape=(int(channels), int(nframes)))
+            return 1 if sink(int(file_index), pcm) else 0
+        self._check(self.L.pov_decode_corpus_pcm(self.ctx, n, arr, lens, host_threads, _sink, None,
+                                                 frames.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(total), C.byref(chk)))
         return frames, int(total.value), float(chk.value)

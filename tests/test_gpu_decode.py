@@ -153,3 +153,38 @@ def test_entries_batch_staged_equals_fused(ctx):
     st.setup_id = 0
     ctx.L.pov_batch_free(ctx.ctx, h)
     po.close()
+
+
+def test_corpus_output_edge_delivers_every_sample_in_file_order(ctx, golden):
+    """pov_decode_corpus_pcm: the sink sees the PCM of 150 mixed files (bundled + synthetic streams, several chunks), in
+    file order, sample for sample what the reference decodes (hpp:966-973, 1047-1053)."""
+    names = ["stereo44khz", "mono44khz", "synth_res0_mono", "synth_two_submaps", "synth_surround51"]
+    files = [_load(names[i % len(names)]) for i in range(150)]
+    seen = []
+
+    bad = []
+
+    def sink(file_index, pcm):          # (an exception inside a ctypes callback would be swallowed: record, assert afterwards)
+        ref = golden[names[file_index % len(names)]]["pcm"]
+        if pcm.shape != ref.shape or float(np.abs(pcm - ref).max()) > 1e-5:
+            bad.append(file_index)
+        seen.append(file_index)
+        return False
+    frames, total, chk = ctx.decode_corpus_pcm(files, sink, host_threads=4)
+    assert seen == list(range(150)) and not bad, bad
+    assert list(frames) == [golden[names[i % len(names)]]["pcm"].shape[1] for i in range(150)]
+    assert total == sum(golden[names[i % len(names)]]["pcm"].size for i in range(150))
+
+
+def test_corpus_output_edge_stops_when_the_sink_says_so(ctx):
+    files = [_load("mono44khz")] * 200
+    calls = []
+
+    def sink(file_index, pcm):
+        calls.append(file_index)
+        return file_index == 70
+    with pytest.raises(RuntimeError) as ei:
+        ctx.decode_corpus_pcm(files, sink, host_threads=3)
+    assert "gotPcmData" in str(ei.value) and calls[-1] == 70 and calls == list(range(71))
+    f, t, _ = ctx.decode_corpus(files, host_threads=3)           # the context keeps working
+    assert len(f) == 200 and t > 0
