@@ -10,9 +10,13 @@ packets per stream, mixed 256/2048 blocks, one coupling step), replicated to --s
 that one step reads and writes far more than the 126 MB L2.
 
 `value`: inputs already resident in HBM, CUDA-event time on the library's stream, max over ranks.
-`e2e`:   the same step through the public API with HOST buffers: descriptor validation + H2D of every arena from
-         pinned memory + kernel + D2H of the PCM into pinned memory, all inside the timed region.
-Multi-GPU: streams are independent, so every rank decodes its own shard; no collective on the data path.
+`e2e`:   the metric through the reference-facing call with HOST buffers (BASELINE.json configs[4], the sharded corpus
+         decode): Ogg/Vorbis files in host memory -> pov_decode_corpus (host front end, H2D of the packet data, entropy
+         decode + synthesis kernels, D2H of the PCM into pinned host memory) -> PCM in host memory. This is the work the
+         reference arm does (OggReader::full_read_from_memory on every file), on the same files, so the two are like for like.
+`e2e_dense`: the config-2 step itself through pov_batch_upload/run/fetch_pcm with pinned host arenas (dense f32 spectra in,
+         PCM out): bounded by PCIe, kept to explain the copy cost of the synthesis stage alone.
+Multi-GPU: streams / files are independent, so every rank decodes its own shard; no collective on the data path.
 """
 import argparse
 import json
@@ -164,19 +168,34 @@ def cpu_baseline_port(setup, batch, n_streams_sample):
                                                          if kind == "reference" else "IMDCT = oracle FFT", dt)}
 
 
+CORPUS_FILE = os.path.join(ROOT, "tests", "golden", "test.stereo44khz.ogg")
+
+
+def workload_config(args):
+    """The `config` object: identical for both arms (it depends on the command line only)."""
+    return {"workload": "value/roofline: config2, synthetic 44.1 kHz stereo, %d packets/stream, mixed 256/2048 blocks, 1 coupling "
+                        "step, %d streams per GPU (%d distinct, seed=rank), spectra resident in HBM; e2e (and the reference arm): "
+                        "config5, the bundled 44.1 kHz stereo fixture x %d files per GPU, bytes in host memory -> PCM in host memory" %
+                        (args.packets, args.streams, min(args.distinct, args.streams), args.corpus_files),
+            "corpus_files_per_gpu": args.corpus_files,
+            "l2_policy": "inputs+outputs of a step (7 GB for config2, 7.5 GB for the corpus) far exceed the 126 MB L2; no flush needed",
+            "parallelism": "independent streams / files sharded across ranks, no collective"}
+
+
 def run_reference_arm(args):
     """The reference's own CPU decoder (oracle/_ref/ref_decode_bench around OggReader::full_read_from_memory,
-    src/ParseOggVorbis.hpp:1428) on all host cores. Rank 0 only."""
+    src/ParseOggVorbis.hpp:1428) on all host cores, on the corpus of the e2e leg. Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_decode_bench")
-    ogg = os.path.join(ROOT, "tests", "golden", "test.stereo44khz.ogg")
+    ogg = CORPUS_FILE
     cores = os.cpu_count() or 1
     if not os.path.exists(exe):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_decode_bench not built (make -C oracle ref)"}))
         return 0
-    per_thread = max(1, args.ref_decodes)
+    # one step = the per-GPU corpus of the e2e leg (a bounded sample of the N-GPU job: the files are identical)
+    per_thread = max(1, (args.corpus_files + cores - 1) // cores) if args.ref_decodes <= 0 else args.ref_decodes
     times, samples = [], 0
     for i in range(args.warmup + args.steps):
         out = subprocess.check_output([exe, ogg, str(cores), str(per_thread)], text=True)
@@ -185,13 +204,13 @@ def run_reference_arm(args):
             times.append(r["seconds"]); samples = r["samples"]
     total_t = sum(times)
     value = samples * len(times) / total_t
-    sample = ("full reference decode (Ogg framing + Huffman + synthesis; the reference cannot run synthesis alone) of "
+    sample = ("the corpus of the e2e leg: full reference decode (Ogg framing + Huffman + synthesis) of "
               "tests/audio/test.stereo44khz.ogg (44.1 kHz stereo, 256/2048 blocks, 182272 samples) x %d decodes on %d "
-              "threads per step" % (cores * per_thread, cores))
+              "threads per step (one GPU's share of the job; at N GPUs the job is N such shares)" % (cores * per_thread, cores))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "bundled fixture replicated",
-            "config": {"workload": "config1-stream x%d (CPU reference arm)" % (cores * per_thread)},
+            "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -208,10 +227,14 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="independent config-2 streams per GPU per step")
     ap.add_argument("--packets", type=int, default=4096, help="packets per stream")
     ap.add_argument("--distinct", type=int, default=4, help="independently generated streams (rest are replicas)")
-    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-depth", type=int, default=2, help="contexts (= streams) the end-to-end steps are pipelined over")
     ap.add_argument("--cpu-streams", type=int, default=0, help="streams of the CPU-baseline sample (0 = one per core)")
-    ap.add_argument("--ref-decodes", type=int, default=40, help="reference arm: decodes per thread per step")
+    ap.add_argument("--ref-decodes", type=int, default=0, help="reference arm: decodes per thread per step (0 = corpus_files / cores)")
+    ap.add_argument("--corpus-files", type=int, default=10000, help="files per GPU per step of the corpus (e2e) leg")
+    ap.add_argument("--corpus-steps", type=int, default=3)
+    ap.add_argument("--corpus-threads", type=int, default=0, help="front-end threads per rank (0 = cores / ranks - 1)")
+    ap.add_argument("--no-e2e-dense", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -301,14 +324,52 @@ def main():
                  "snr_db": float(ob.snr_db(got, ref)),
                  "packets_with_status": status_bad}
 
-    # ---- end-to-end leg: host buffers in, host PCM out, every step ----
+    # ---- end-to-end leg (the headline): config 5, files in host memory -> PCM in host memory through pov_decode_corpus ----
+    e2e = None
+    if not args.no_e2e:
+        with open(CORPUS_FILE, "rb") as f:
+            one = f.read()
+        files = [bytes(bytearray(one)) for _ in range(args.corpus_files)]       # distinct host copies (255 MB for 10 000)
+        cores = os.cpu_count() or 1
+        threads = args.corpus_threads or max(1, cores // world - 1)
+        cctx = SynthContext(local)
+        frames, total, chk = cctx.decode_corpus(files, host_threads=threads)    # warm-up: tables, pinned pools and arenas at full size
+        b0 = cctx.io_bytes()
+        barrier()
+        t0 = time.perf_counter()
+        vals = 0
+        for _ in range(args.corpus_steps):
+            frames, total, chk = cctx.decode_corpus(files, host_threads=threads)
+            vals += total
+        barrier()
+        wall = time.perf_counter() - t0
+        b1 = cctx.io_bytes()
+        tt = torch.tensor([wall * 1e3], dtype=torch.float64, device="cuda")
+        tv = torch.tensor([float(vals)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tv, op=dist.ReduceOp.SUM)
+        expect = 182272 * args.corpus_files                         # 2 channels x 91136 frames per file
+        e2e = {"value": float(tv.item()) / (float(tt.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int((b1[0] - b0[0]) // args.corpus_steps), "d2h_bytes_per_step": int((b1[1] - b0[1]) // args.corpus_steps),
+               "steps": args.corpus_steps, "ms_per_step": float(tt.item()) / args.corpus_steps,
+               "files_per_step_per_gpu": args.corpus_files, "ogg_bytes_per_step_per_gpu": len(one) * args.corpus_files,
+               "host_threads_per_rank": threads, "host_cores": cores,
+               "per_rank_gb_per_s": {"h2d": (b1[0] - b0[0]) / wall / 1e9, "d2h": (b1[1] - b0[1]) / wall / 1e9},
+               "pcm_values_per_step_ok": bool(total == expect), "checksum": chk,
+               "timing": "host clock around pov_decode_corpus (parse + H2D + kernels + D2H into pinned host memory), barrier + "
+                         "synchronize on both sides, max over ranks"}
+        cctx.close()
+        del files
+
+    # ---- the config-2 step through the batch API with host buffers (dense spectra in, PCM out): PCIe-bound ----
     # Every step validates the descriptors, copies all input arenas from pinned host memory to the device, runs the
     # kernel and copies the whole PCM arena back into pinned host memory. Steps are issued as a pipeline over --e2e-depth
     # contexts (= CUDA streams), so that the H2D copy of step k+1 overlaps the D2H copy of step k on the two copy
     # engines — the way a corpus decode streams batches through the device. Timed with the host clock around the whole
     # pipeline (barrier + synchronize on both sides), which includes every copy and every launch.
-    e2e = None
-    if not args.no_e2e:
+    e2e_dense = None
+    if not args.no_e2e and not args.no_e2e_dense:
         depth = max(1, args.e2e_depth)
         pb, keep = pin_batch(batch)
         ctxs = [ctx] + [SynthContext(local) for _ in range(depth - 1)]
@@ -349,7 +410,7 @@ def main():
         tt = torch.tensor([wall * 1e3], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * samples_per_step * args.e2e_steps / (float(tt.item()) * 1e-3), "unit": UNIT,
+        e2e_dense = {"value": world * samples_per_step * args.e2e_steps / (float(tt.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                "ms_per_step": float(tt.item()) / args.e2e_steps, "pipeline_depth": depth,
                "timing": "host clock around the pipelined steps (upload+run+fetch each), max over ranks",
@@ -364,7 +425,7 @@ def main():
         # DRAM traffic of one launch from the committed ncu --set full capture of this very workload (per launch, GB)
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tj = json.load(f)
             if tj["kernel"] == kernel_name and int(tj["samples_per_launch"]) == samples_per_step:
                 traffic = tj["traffic_bytes_per_launch"] / 1e9
@@ -374,15 +435,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config2: synthetic 44.1 kHz stereo, %d packets/stream, mixed 256/2048 blocks, "
-                                   "1 coupling step, %d streams per GPU (%d distinct, seed=rank)" %
-                                   (args.packets, args.streams, min(args.distinct, args.streams)),
-                       "samples_per_step_per_gpu": samples_per_step,
-                       "l2_policy": "inputs+outputs per step (%.2f GB) far exceed the 126 MB L2; no flush needed" %
-                                    (samples_per_step * BYTES_PER_SAMPLE / 1e9),
-                       "parallelism": "independent streams sharded across ranks, no collective"},
+            "config": workload_config(args), "samples_per_step_per_gpu": samples_per_step,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_unit": "GB per launch (dram read+write of the committed ncu --set full capture of this workload, "
+                                         "profiles/r02_traffic.json; not re-measured in this run)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": samples_per_step * BYTES_PER_SAMPLE,
                          "kernel_ms": kernel_ms},
@@ -390,6 +447,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if e2e_dense:
+            line["e2e_dense"] = e2e_dense
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(setup, batch, args.cpu_streams or (os.cpu_count() or 1))
         print(json.dumps(line))

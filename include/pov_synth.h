@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define POV_ABI_VERSION      1u
+#define POV_ABI_VERSION      2u
 #define POV_MAX_CHANNELS     8u    /* reference: uint8_t audio_channels (hpp:107); this build: <= 8 */
 #define POV_MAX_POSTS        256u  /* floor1 syntax bound 2 + 31*8 = 250 (hpp:426,437) */
 #define POV_MAX_COUPLINGS    256u  /* hpp:783 */
@@ -65,7 +65,22 @@ typedef struct pov_codebook {
 	uint32_t lookup_type;  /* hpp:142; 0 = scalar-only book, no VQ table */
 	uint32_t reserved;
 	const float* vq;       /* hpp:149 lookup_table_ [n_entries * dim]; NULL iff lookup_type == 0 */
+	const uint8_t* lengths;/* hpp:126 Entry::len_ per entry, 0 = unused entry (hpp:270-272); only read for POV_INPUT_PACKETS
+	                          batches (device-side entropy decode), may be NULL otherwise */
 } pov_codebook;
+
+/* How a floor1's coded Y list is laid out in the packet (hpp:425-447, read by hpp:498-517): needed only for
+ * POV_INPUT_PACKETS batches, where the device walks the packet bits itself. */
+typedef struct pov_floor1_syntax {
+	uint8_t n_partitions;             /* hpp:426 (<= 31) */
+	uint8_t n_classes;                /* hpp:429 maximum class + 1 (<= 16) */
+	uint8_t reserved[2];
+	uint8_t partition_class[32];      /* hpp:428 */
+	uint8_t class_dim[16];            /* hpp:433, 1..8 */
+	uint8_t class_subclass_bits[16];  /* hpp:434, 0..3 */
+	uint8_t class_masterbook[16];     /* hpp:436 (only if subclass_bits > 0) */
+	int16_t class_books[16][8];       /* hpp:441 subclass book number, -1 = none (the Y is 0) */
+} pov_floor1_syntax;
 
 typedef struct pov_floor1 {
 	uint16_t n_posts;      /* == xs.size(), >= 2 */
@@ -108,6 +123,7 @@ typedef struct pov_setup {
 	uint32_t n_residues;   const pov_residue*  residues;
 	uint32_t n_mappings;   const pov_mapping*  mappings;
 	uint32_t n_modes;      const pov_mode*     modes;
+	const pov_floor1_syntax* floor_syntax; /* [n_floors], or NULL (then POV_INPUT_PACKETS batches are refused for this setup) */
 } pov_setup;
 
 /* ---- batch description ----------------------------------------------------------------------------------- */
@@ -131,13 +147,16 @@ typedef struct pov_packet {
 	uint16_t floor_used;      /* bit c: channel c decoded a floor curve (hpp:478-482), BEFORE nonzero propagate */
 	uint32_t emit_frames;     /* frames released by this packet: 0 for a stream's first packet, else
 	                             prev/4 + cur/4 (hpp:1026), shortened at a page end by the granule rule (hpp:1028-1033) */
-	uint32_t reserved;
+	uint32_t packet_bytes;    /* POV_INPUT_PACKETS: length of the raw audio packet; otherwise unused (0) */
 	uint64_t pcm_off;         /* frame index inside the stream's PCM where this packet's chunk starts */
 	uint64_t ys_off;          /* index (uint16 units) into the Y arena: for every channel WITH floor_used set, in
-	                             channel order, that channel's coded Y list "floor1 ys" (hpp:498-518), n_posts each */
+	                             channel order, that channel's coded Y list "floor1 ys" (hpp:498-518), n_posts each.
+	                             POV_INPUT_PACKETS: ignored (floor_used and the Y lists are decoded on the device) */
 	uint64_t spec_off;        /* POV_INPUT_DENSE:   float index into the spectra arena of this packet's
 	                                                 "after_residue" vectors, [channels][blocksize/2] (hpp:1211)
-	                             POV_INPUT_ENTRIES: byte offset into the residue payload arena (layout below) */
+	                             POV_INPUT_ENTRIES: byte offset into the residue payload arena (layout below)
+	                             POV_INPUT_PACKETS: byte offset (multiple of 4) of the raw audio packet in the payload arena;
+	                                                the bytes after it up to the next multiple of 4 must be zero */
 } pov_packet;
 
 /* Residue payload of ONE packet in POV_INPUT_ENTRIES mode (everything little-endian, 4-byte aligned):
@@ -150,7 +169,12 @@ typedef struct pov_packet {
  *                                        hpp:711-757), padded to 4 bytes. E = 16 bits if every codebook of the
  *                                        setup has <= 65536 entries, else 32 (pov_setup_entry_bits()).
  */
-enum { POV_INPUT_DENSE = 0, POV_INPUT_ENTRIES = 1 };
+/* POV_INPUT_PACKETS: the payload arena holds the raw Vorbis audio packets (what hpp:1375-1381 hands to parse_audio).
+ * mode, window_flags, emit_frames and pcm_off come from the host (they need the first bits of the packet and the page
+ * granule only); the device reads everything else from the bits: floor flags and coded Ys (hpp:478-518), residue
+ * classifications and VQ entry numbers (hpp:696-760) — the entropy decode of SURVEY.md §8(f)-2. Reading past the end of a
+ * packet yields zero bits, as in the reference (Utils.hpp:389-392). The setup must carry codebook lengths and floor syntax. */
+enum { POV_INPUT_DENSE = 0, POV_INPUT_ENTRIES = 1, POV_INPUT_PACKETS = 2 };
 enum { POV_PCM_PLANAR = 0, POV_PCM_INTERLEAVED = 1 };
 
 typedef struct pov_batch {
@@ -186,6 +210,11 @@ const char* pov_last_error(const pov_ctx* ctx);
 void*       pov_ctx_stream(pov_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench accounting). */
 uint64_t    pov_ctx_launch_count(const pov_ctx* ctx);
+/* Whole-file and corpus decode hand the audio packets to the device as they are (entropy decode in k_packet_decode) when
+ * `on` is non-zero — the default; environment POV_DEVICE_ENTROPY=0 turns it off — and walk them on the host otherwise. */
+void        pov_ctx_set_device_entropy(pov_ctx* ctx, int on);
+/* Bytes this context has copied host -> device and device -> host so far (descriptor/payload arenas, PCM, status words). */
+void        pov_ctx_io_bytes(const pov_ctx* ctx, uint64_t* h2d_out, uint64_t* d2h_out);
 
 /* The 256-entry floor1_inverse_dB_table this library uses (reference: src/inverse_db_table.h:13-78). Host only. */
 void        pov_inverse_db_table(float out[256]);
@@ -270,6 +299,10 @@ int  pov_decode_corpus_pcm(pov_ctx* ctx, uint32_t n_files, const uint8_t* const*
  * setup/batch returned by pov_parsed_get point into memory owned by the handle (POV_INPUT_ENTRIES, setup_id 0). */
 typedef struct pov_parsed pov_parsed;
 int      pov_ogg_parse_memory(const uint8_t* data, size_t len, pov_parsed** out, const char** error_out);
+/* flags: POV_PARSE_RAW_PACKETS — do not entropy-decode the audio packets; the batches are POV_INPUT_PACKETS (a stream whose
+ * setup cannot be walked on the device — floor0, a submap without channels — still comes back as POV_INPUT_ENTRIES). */
+#define POV_PARSE_RAW_PACKETS 1u
+int      pov_ogg_parse_memory_ex(const uint8_t* data, size_t len, uint32_t flags, pov_parsed** out, const char** error_out);
 uint32_t pov_parsed_stream_count(const pov_parsed* p);
 int      pov_parsed_get(const pov_parsed* p, uint32_t stream, pov_setup* setup_out, pov_batch* batch_out);
 void     pov_parsed_free(pov_parsed* p);

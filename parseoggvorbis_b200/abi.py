@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-POV_ABI_VERSION = 1
+POV_ABI_VERSION = 2
 POV_MAX_CHANNELS = 8
 POV_MAX_POSTS = 256
 POV_MAX_COUPLINGS = 256
@@ -22,7 +22,7 @@ POV_NO_BOOK = 255
 
 POV_OK, POV_ERR_ARG, POV_ERR_CUDA, POV_ERR_STREAM, POV_ERR_UNSUPPORTED = range(5)
 POV_PKT_OK, POV_PKT_FLOOR_PREDICTED, POV_PKT_FLOOR_RANGE, POV_PKT_VQ_ENTRY = 0, 1, 2, 4
-POV_INPUT_DENSE, POV_INPUT_ENTRIES = 0, 1
+POV_INPUT_DENSE, POV_INPUT_ENTRIES, POV_INPUT_PACKETS = 0, 1, 2
 POV_PCM_PLANAR, POV_PCM_INTERLEAVED = 0, 1
 
 (POV_STAGE_FINAL_YS, POV_STAGE_STEP2_FLAG, POV_STAGE_FLOOR, POV_STAGE_FLOOR_OUTPUTS,
@@ -31,7 +31,14 @@ POV_PCM_PLANAR, POV_PCM_INTERLEAVED = 0, 1
 
 class pov_codebook(C.Structure):
     _fields_ = [("dim", C.c_uint32), ("n_entries", C.c_uint32), ("lookup_type", C.c_uint32),
-                ("reserved", C.c_uint32), ("vq", C.POINTER(C.c_float))]
+                ("reserved", C.c_uint32), ("vq", C.POINTER(C.c_float)), ("lengths", C.POINTER(C.c_uint8))]
+
+
+class pov_floor1_syntax(C.Structure):
+    _fields_ = [("n_partitions", C.c_uint8), ("n_classes", C.c_uint8), ("reserved", C.c_uint8 * 2),
+                ("partition_class", C.c_uint8 * 32), ("class_dim", C.c_uint8 * 16),
+                ("class_subclass_bits", C.c_uint8 * 16), ("class_masterbook", C.c_uint8 * 16),
+                ("class_books", (C.c_int16 * 8) * 16)]
 
 
 class pov_floor1(C.Structure):
@@ -65,7 +72,8 @@ class pov_setup(C.Structure):
                 ("n_floors", C.c_uint32), ("floors", C.POINTER(pov_floor1)),
                 ("n_residues", C.c_uint32), ("residues", C.POINTER(pov_residue)),
                 ("n_mappings", C.c_uint32), ("mappings", C.POINTER(pov_mapping)),
-                ("n_modes", C.c_uint32), ("modes", C.POINTER(pov_mode))]
+                ("n_modes", C.c_uint32), ("modes", C.POINTER(pov_mode)),
+                ("floor_syntax", C.POINTER(pov_floor1_syntax))]
 
 
 class pov_stream(C.Structure):
@@ -75,7 +83,7 @@ class pov_stream(C.Structure):
 
 class pov_packet(C.Structure):
     _fields_ = [("stream", C.c_uint32), ("mode", C.c_uint8), ("window_flags", C.c_uint8),
-                ("floor_used", C.c_uint16), ("emit_frames", C.c_uint32), ("reserved", C.c_uint32),
+                ("floor_used", C.c_uint16), ("emit_frames", C.c_uint32), ("packet_bytes", C.c_uint32),
                 ("pcm_off", C.c_uint64), ("ys_off", C.c_uint64), ("spec_off", C.c_uint64)]
 
 
@@ -97,7 +105,7 @@ class pov_decoded(C.Structure):
 STREAM_DTYPE = np.dtype([("setup_id", "<u4"), ("first_packet", "<u4"), ("n_packets", "<u4"),
                          ("reserved", "<u4"), ("pcm_frames", "<u8"), ("pcm_base", "<u8")], align=True)
 PACKET_DTYPE = np.dtype([("stream", "<u4"), ("mode", "u1"), ("window_flags", "u1"), ("floor_used", "<u2"),
-                         ("emit_frames", "<u4"), ("reserved", "<u4"), ("pcm_off", "<u8"), ("ys_off", "<u8"),
+                         ("emit_frames", "<u4"), ("packet_bytes", "<u4"), ("pcm_off", "<u8"), ("ys_off", "<u8"),
                          ("spec_off", "<u8")], align=True)
 assert STREAM_DTYPE.itemsize == C.sizeof(pov_stream)
 assert PACKET_DTYPE.itemsize == C.sizeof(pov_packet)

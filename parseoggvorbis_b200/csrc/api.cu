@@ -18,6 +18,7 @@
 #include "api_internal.h"
 #include "host_tables.h"
 #include "kernels.h"
+#include "vorbis_parse.h"
 
 using namespace pov;
 
@@ -111,6 +112,7 @@ extern "C" int pov_ctx_create(int device, pov_ctx** out, const char** error_out)
 	if((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail("sync", e);
 	if((e = cudaMalloc((void**) &ctx->d_counter, 256)) != cudaSuccess) return fail("cudaMalloc work counter", e);
 	if(const char* k = getenv("POV_KERNEL")) ctx->kernel_choice = !strcmp(k, "fused") ? 1 : !strcmp(k, "warp") ? 2 : 0;
+	if(const char* de = getenv("POV_DEVICE_ENTROPY")) ctx->device_entropy = atoi(de) != 0;
 	const char* rl = getenv("POV_RUN_LEN");
 	ctx->run_len = rl ? (uint32_t) std::min(64, std::max(2, atoi(rl))) : 0;   // the fused kernel keeps <= 65 descriptors per run
 	ctx->err[0] = 0;
@@ -119,6 +121,7 @@ extern "C" int pov_ctx_create(int device, pov_ctx** out, const char** error_out)
 }
 
 static void free_setup(SetupRec& s) {
+	cudaFree((void*) s.d_huff); cudaFree((void*) s.d_hbooks); cudaFree((void*) s.d_fsyntax);
 	cudaFree((void*) s.d_floors); cudaFree((void*) s.d_mappings); cudaFree((void*) s.d_residues);
 	cudaFree((void*) s.d_codebooks); cudaFree((void*) s.d_vq); cudaFree((void*) s.d_fast);
 }
@@ -141,6 +144,11 @@ extern "C" void pov_ctx_destroy(pov_ctx* ctx) {
 extern "C" const char* pov_last_error(const pov_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" void* pov_ctx_stream(pov_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
 extern "C" uint64_t pov_ctx_launch_count(const pov_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void pov_ctx_set_device_entropy(pov_ctx* ctx, int on) { if(ctx) ctx->device_entropy = on != 0; }
+extern "C" void pov_ctx_io_bytes(const pov_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
+	if(h2d) *h2d = ctx ? ctx->h2d_bytes : 0;
+	if(d2h) *d2h = ctx ? ctx->d2h_bytes : 0;
+}
 
 // per-blocksize tables shared by all setups of a context
 static int get_block_tables(pov_ctx* ctx, uint32_t n, BlockTables** out) {
@@ -181,6 +189,15 @@ static void serialize_setup(const pov_setup* s, std::string& out) {
 		const pov_codebook& c = s->codebooks[i];
 		put(&c.dim, 4); put(&c.n_entries, 4); put(&c.lookup_type, 4);
 		if(c.lookup_type != 0 && c.vq) put(c.vq, sizeof(float) * (size_t) c.dim * c.n_entries);
+		const uint8_t has_len = c.lengths != nullptr;
+		put(&has_len, 1);
+		if(c.lengths) put(c.lengths, c.n_entries);
+	}
+	{
+		const uint8_t has_syntax = s->floor_syntax != nullptr;
+		put(&has_syntax, 1);
+		if(s->floor_syntax) put(s->floor_syntax, sizeof(pov_floor1_syntax) * (size_t) s->n_floors);
+		for(uint32_t i = 0; i < s->n_residues; ++i) put(&s->residues[i].classbook, 4);
 	}
 	for(uint32_t i = 0; i < s->n_floors; ++i) {
 		const pov_floor1& f = s->floors[i];
@@ -427,6 +444,109 @@ extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id
 		if(rec.fast_ok) CUDA_TRY(ctx, dev_upload((FastTables**) &rec.d_fast, &ft, 1, ctx->stream));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // ft lives on this stack frame
 	}
+	// ---- device entropy decode (POV_INPUT_PACKETS): Huffman tables, floor syntax, per-mode worst-case arena sizes ----
+	{
+		bool ok = s->floor_syntax != nullptr && s->n_residues > 0 && s->n_residues <= 64 && s->n_codebooks <= 255;
+		for(uint32_t i = 0; i < s->n_codebooks && ok; ++i) ok = s->codebooks[i].lengths != nullptr;
+		std::vector<uint32_t> arena;
+		std::vector<DevHuffBook> hb(s->n_codebooks);
+		for(uint32_t i = 0; i < s->n_codebooks && ok; ++i) {
+			HuffTables t;
+			std::string why;
+			if(!build_huff_tables(s->codebooks[i].lengths, s->codebooks[i].n_entries, POV_HUFF_LUT_BITS, t, why))
+				return pov_fail(ctx, POV_ERR_ARG, "pov_setup: codebook %u: %s", i, why.c_str());
+			memset(&hb[i], 0, sizeof hb[i]);
+			hb[i].lut_off = (uint32_t) arena.size();
+			arena.insert(arena.end(), t.lut.begin(), t.lut.end());
+			hb[i].sorted_off = (uint32_t) arena.size();
+			hb[i].n_sorted = (uint32_t) t.sorted_code.size();
+			arena.insert(arena.end(), t.sorted_code.begin(), t.sorted_code.end());
+			for(size_t k = 0; k < t.sorted_entry.size(); ++k) arena.push_back((t.sorted_entry[k] << 6) | t.sorted_len[k]);
+			hb[i].n_entries = s->codebooks[i].n_entries; hb[i].dim = s->codebooks[i].dim; hb[i].lookup_type = s->codebooks[i].lookup_type;
+			if(s->codebooks[i].n_entries >= (1u << 26)) ok = false;           // entry numbers share a word with the length
+		}
+		std::vector<DevFloorSyntax> fsx(s->n_floors);
+		for(uint32_t i = 0; i < s->n_floors && ok; ++i) {
+			const pov_floor1_syntax& in = s->floor_syntax[i];
+			DevFloorSyntax& o = fsx[i];
+			memset(&o, 0, sizeof o);
+			if(in.n_partitions > 31 || in.n_classes > 16) { ok = false; break; }
+			o.n_partitions = in.n_partitions; o.n_classes = in.n_classes;
+			uint32_t rb = 0, rg = floors[i].range - 1;
+			while(rg) { ++rb; rg >>= 1; }
+			o.ybits = (uint8_t) rb;                                           // ilog(range - 1), hpp:494-497
+			uint32_t count = 2;
+			for(uint32_t k = 0; k < in.n_partitions; ++k) {
+				if(in.partition_class[k] >= in.n_classes) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: floor %u: partition class out of range (hpp:429)", i);
+				o.partition_class[k] = in.partition_class[k];
+				count += in.class_dim[in.partition_class[k]];
+			}
+			if(count != s->floors[i].n_posts) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: floor %u: syntax describes %u posts, the floor has %u (hpp:519)", i, count, s->floors[i].n_posts);
+			for(uint32_t k = 0; k < in.n_classes; ++k) {
+				if(in.class_dim[k] < 1 || in.class_dim[k] > 8 || in.class_subclass_bits[k] > 3) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: floor %u: class %u out of range (hpp:433-434)", i, k);
+				o.class_dim[k] = in.class_dim[k]; o.class_subclass_bits[k] = in.class_subclass_bits[k]; o.class_masterbook[k] = in.class_masterbook[k];
+				if(in.class_subclass_bits[k] && in.class_masterbook[k] >= s->n_codebooks) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: floor %u: masterbook out of range", i);
+				for(uint32_t b = 0; b < 8; ++b) {
+					const int bk = (b < (1u << in.class_subclass_bits[k])) ? in.class_books[k][b] : -1;
+					if(bk >= (int) s->n_codebooks) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: floor %u: subclass book out of range", i);
+					o.class_books[k][b] = (int16_t) bk;
+				}
+			}
+		}
+		for(uint32_t i = 0; i < s->n_residues && ok; ++i) {
+			if(s->residues[i].classbook >= s->n_codebooks) return pov_fail(ctx, POV_ERR_ARG, "pov_setup: residue %u: classbook out of range (hpp:700)", i);
+			d.classbook[i] = s->residues[i].classbook;
+		}
+		// a submap without channels is fatal for every packet of its mapping in the reference (hpp:680): refuse the mode of decode
+		for(uint32_t m = 0; m < s->n_mappings && ok; ++m)
+			for(uint32_t sm = 0; sm < maps[m].n_submaps; ++sm) {
+				bool any = false;
+				for(uint32_t c = 0; c < s->channels; ++c) any |= (maps[m].mux[c] == sm);
+				if(!any) ok = false;
+			}
+		if(ok) {
+			// worst-case arena sizes of one packet per mode: Y slots of every channel; entries payload = per submap the header,
+			// the classification bytes and, per pass, the largest vector count any class can code in a partition
+			for(uint32_t mo = 0; mo < s->n_modes; ++mo) {
+				const DevMapping& mp = maps[s->modes[mo].mapping];
+				const uint32_t half = s->blocksize[s->modes[mo].blockflag ? 1 : 0] / 2;
+				uint32_t ycap = 0;
+				uint64_t ecap = 0;
+				for(uint32_t c = 0; c < s->channels; ++c) ycap += floors[mp.floor_of_ch[c]].n_posts;
+				for(uint32_t sm = 0; sm < mp.n_submaps; ++sm) {
+					uint32_t nch = 0;
+					for(uint32_t c = 0; c < s->channels; ++c) nch += (mp.mux[c] == sm);
+					const DevResidue& r = residues[mp.submap_residue[sm]];
+					const uint32_t vch = r.type == 2 ? 1 : nch, vlen = r.type == 2 ? nch * half : half;
+					const uint32_t lb = std::min(r.begin, vlen), le = std::min(r.end, vlen), parts = (le - lb) / r.partition_size;
+					uint64_t per_part = 0;
+					for(uint32_t pass = 0; pass < 8; ++pass) {
+						uint32_t mx = 0;
+						for(uint32_t cl = 0; cl < r.n_class; ++cl) {
+							const uint32_t bk = r.books[cl * 8 + pass];
+							if(bk != POV_NO_BOOK && bk < s->n_codebooks) mx = std::max(mx, r.partition_size / s->codebooks[bk].dim);
+						}
+						per_part += mx;
+					}
+					ecap += 4 + (((uint64_t) vch * parts + 3) & ~3ull) + ((per_part * parts * vch * (d.entry_bits / 8) + 3) & ~3ull);
+				}
+				if(ecap > 0xFFFFFFF0ull) { ok = false; break; }
+				rec.mode_ys_cap[mo] = ycap;
+				rec.mode_ent_cap[mo] = (uint32_t) ecap;
+			}
+		}
+		if(ok) {
+			uint32_t mb = 0, v = s->n_modes - 1;
+			while(v) { ++mb; v >>= 1; }
+			d.mode_bits = mb;
+			CUDA_TRY(ctx, dev_upload((uint32_t**) &rec.d_huff, arena.data(), arena.size(), ctx->stream));
+			CUDA_TRY(ctx, dev_upload((DevHuffBook**) &rec.d_hbooks, hb.data(), hb.size(), ctx->stream));
+			CUDA_TRY(ctx, dev_upload((DevFloorSyntax**) &rec.d_fsyntax, fsx.data(), fsx.size(), ctx->stream));
+			CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+			d.huff = rec.d_huff; d.hbooks = rec.d_hbooks; d.fsyntax = rec.d_fsyntax;
+		}
+		rec.entropy_ok = ok;
+	}
 	rec.image.swap(image);
 	ctx->setups.push_back(std::move(rec));
 
@@ -471,6 +591,7 @@ extern "C" int pov_setup_get_window(const pov_ctx* ctx, uint32_t id, int blockfl
 static void release_batch(pov_batch_handle* h) {
 	h->d_streams.release(); h->d_packets.release(); h->d_ys.release(); h->d_payload.release(); h->d_spec_off.release();
 	h->d_stage_off.release(); h->d_runs.release(); h->d_pcm.release(); h->d_status.release(); h->d_spectra.release();
+	h->d_entries.release(); h->d_pk_off.release();
 	h->st_final_ys.release(); h->st_flag.release(); h->st_floor.release(); h->st_floor_out.release();
 	h->st_env.release(); h->st_mdct.release();
 	if(h->h_derived) { cudaFreeHost(h->h_derived); h->h_derived = nullptr; h->h_derived_cap = 0; }
@@ -487,7 +608,7 @@ extern "C" void pov_batch_free(pov_ctx* ctx, pov_batch_handle* h) {
 extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_handle** out) try {
 	if(!ctx || !b || !out) return POV_ERR_ARG;
 	cudaSetDevice(ctx->device);
-	if(b->input_kind > POV_INPUT_ENTRIES || b->pcm_layout > POV_PCM_INTERLEAVED) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: bad input_kind/pcm_layout");
+	if(b->input_kind > POV_INPUT_PACKETS || b->pcm_layout > POV_PCM_INTERLEAVED) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: bad input_kind/pcm_layout");
 	if((b->n_streams && !b->streams) || (b->n_packets && !b->packets)) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: null arrays");
 	if(b->input_kind == POV_INPUT_DENSE && ((uintptr_t) b->payload & 3)) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: dense payload must be 4-byte aligned");
 
@@ -501,6 +622,9 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	// ---- validation + derived arrays (one pass over the packets) ----
 	const uint32_t P = b->n_packets;
 	h->spec_off.resize(P); h->stage_off.resize(P); h->pk_n.resize(P); h->pk_setup.resize(P);
+	const bool raw_packets = b->input_kind == POV_INPUT_PACKETS;
+	h->pk_ys_off.resize(raw_packets ? P : 0); h->pk_ent_off.resize(raw_packets ? P : 0); h->pk_raw_off.resize(raw_packets ? P : 0);
+	h->ys_cap = h->ent_cap = 0;
 	h->runs.clear();
 	uint32_t maxC = 1, maxbs = 64, minbs = 8192, maxposts = 2, res_smem = 0, posts_cls[2] = {2, 2};
 	bool only_std = true;
@@ -539,6 +663,9 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 		expect_first += st.n_packets;
 		const SetupRec& su = ctx->setups[st.setup_id];
 		const uint32_t C = su.channels;
+		if(raw_packets && !su.entropy_ok)
+			return pov_fail(ctx, POV_ERR_UNSUPPORTED, "pov_batch: stream %u: setup %u cannot be entropy-decoded on the device (no codebook lengths / floor "
+			                "syntax, floor0, or a submap without channels)", si, st.setup_id);
 		// (subtraction form: none of these 64-bit sums may wrap)
 		if(st.pcm_base > b->pcm_floats || st.pcm_frames > (b->pcm_floats - st.pcm_base) / C)
 			return pov_fail(ctx, POV_ERR_ARG, "pov_batch: stream %u: PCM region exceeds pcm_floats", si);
@@ -564,8 +691,17 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 			uint64_t ny = 0;
 			for(uint32_t c = 0; c < C; ++c)
 				if((pk.floor_used >> c) & 1) ny += su.floors_host[mp.floor_of_ch[c]].n_posts;
-			if(pk.ys_off > b->n_ys || ny > b->n_ys - pk.ys_off) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: Y lists outside the Y arena", p);
-			if(b->input_kind == POV_INPUT_DENSE) {
+			if(!raw_packets && (pk.ys_off > b->n_ys || ny > b->n_ys - pk.ys_off)) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: Y lists outside the Y arena", p);
+			if(raw_packets) {
+				const uint64_t padded = ((uint64_t) pk.packet_bytes + 3) & ~3ull;
+				if((pk.spec_off & 3) || pk.spec_off > b->payload_bytes || padded > b->payload_bytes - pk.spec_off)
+					return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: raw packet outside the payload arena", p);
+				h->pk_ys_off[p] = h->ys_cap; h->ys_cap += su.mode_ys_cap[pk.mode];
+				h->pk_ent_off[p] = h->ent_cap; h->ent_cap += su.mode_ent_cap[pk.mode];
+				h->pk_raw_off[p] = pk.spec_off;
+				h->spec_off[p] = dense_floats;
+				dense_floats += (uint64_t) C * (n / 2);
+			} else if(b->input_kind == POV_INPUT_DENSE) {
 				if(pk.spec_off & 3) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: spec_off must be a multiple of 4 floats (16-byte TMA source)", p);
 				if(pk.spec_off > payload_floats || (uint64_t) C * (n / 2) > payload_floats - pk.spec_off) return pov_fail(ctx, POV_ERR_ARG, "pov_batch: packet %u: spectra outside the payload arena", p);
 				h->spec_off[p] = pk.spec_off;
@@ -669,15 +805,20 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	auto up = [&](DevBuf& buf, const void* src, size_t bytes) -> cudaError_t {
 		cudaError_t e = buf.reserve(std::max<size_t>(bytes, 16));
 		if(e != cudaSuccess || bytes == 0) return e;
+		ctx->h2d_bytes += bytes;
 		return cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, st);
 	};
 	CUDA_TRY(ctx, up(h->d_streams, b->streams, sizeof(pov_stream) * b->n_streams));
 	CUDA_TRY(ctx, up(h->d_packets, b->packets, sizeof(pov_packet) * P));
-	CUDA_TRY(ctx, up(h->d_ys, b->ys, sizeof(uint16_t) * b->n_ys));
+	if(raw_packets) {
+		CUDA_TRY(ctx, h->d_ys.reserve(std::max<size_t>(sizeof(uint16_t) * h->ys_cap, 16)));
+		CUDA_TRY(ctx, h->d_entries.reserve(std::max<size_t>(h->ent_cap, 16)));
+	} else CUDA_TRY(ctx, up(h->d_ys, b->ys, sizeof(uint16_t) * b->n_ys));
 	CUDA_TRY(ctx, up(h->d_payload, b->payload, b->payload_bytes));
 	{
 		const size_t b_spec = sizeof(uint64_t) * P, o_runs = (b_spec + 15) & ~(size_t) 15, b_runs = sizeof(DevRun) * h->runs.size();
-		const size_t need = std::max<size_t>(o_runs + b_runs, 16);
+		const size_t o_pk = (o_runs + b_runs + 15) & ~(size_t) 15, b_pk = raw_packets ? 3 * sizeof(uint64_t) * P : 0;
+		const size_t need = std::max<size_t>(o_pk + b_pk, 16);
 		if(h->derived_copied) CUDA_TRY(ctx, cudaEventSynchronize(h->derived_copied));     // the previous upload through this handle has read them
 		else CUDA_TRY(ctx, cudaEventCreateWithFlags(&h->derived_copied, cudaEventDisableTiming));
 		if(need > h->h_derived_cap) {
@@ -688,6 +829,12 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 		}
 		if(b_spec) memcpy(h->h_derived, h->spec_off.data(), b_spec);
 		if(b_runs) memcpy((uint8_t*) h->h_derived + o_runs, h->runs.data(), b_runs);
+		if(b_pk) {
+			memcpy((uint8_t*) h->h_derived + o_pk, h->pk_ys_off.data(), b_pk / 3);
+			memcpy((uint8_t*) h->h_derived + o_pk + b_pk / 3, h->pk_ent_off.data(), b_pk / 3);
+			memcpy((uint8_t*) h->h_derived + o_pk + 2 * (b_pk / 3), h->pk_raw_off.data(), b_pk / 3);
+			CUDA_TRY(ctx, up(h->d_pk_off, (uint8_t*) h->h_derived + o_pk, b_pk));
+		}
 		CUDA_TRY(ctx, up(h->d_spec_off, h->h_derived, b_spec));
 		CUDA_TRY(ctx, up(h->d_runs, (uint8_t*) h->h_derived + o_runs, b_runs));
 		CUDA_TRY(ctx, cudaEventRecord(h->derived_copied, st));
@@ -695,7 +842,7 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	CUDA_TRY(ctx, h->d_pcm.reserve(std::max<size_t>(sizeof(float) * b->pcm_floats, 16)));
 	CUDA_TRY(ctx, h->d_status.reserve(std::max<size_t>(sizeof(uint32_t) * P, 16)));
 	CUDA_TRY(ctx, cudaMemsetAsync(h->d_status.ptr, 0, sizeof(uint32_t) * P, st));
-	if(b->input_kind == POV_INPUT_ENTRIES) CUDA_TRY(ctx, h->d_spectra.reserve(std::max<size_t>(sizeof(float) * dense_floats, 16)));
+	if(b->input_kind != POV_INPUT_DENSE) CUDA_TRY(ctx, h->d_spectra.reserve(std::max<size_t>(sizeof(float) * dense_floats, 16)));
 	if(fresh) *out = fresh.release();
 	return POV_OK;
 } POV_NOTHROW_END(ctx)
@@ -708,7 +855,8 @@ static DevBatchView make_view(pov_ctx* ctx, pov_batch_handle* h) {
 	v.ys = (const uint16_t*) h->d_ys.ptr;
 	v.spec_off = (const uint64_t*) h->d_spec_off.ptr;
 	if(h->input_kind == POV_INPUT_DENSE) { v.spectra = (const float*) h->d_payload.ptr; v.payload = nullptr; }
-	else { v.spectra = (const float*) h->d_spectra.ptr; v.payload = (const uint8_t*) h->d_payload.ptr; }
+	else if(h->input_kind == POV_INPUT_ENTRIES) { v.spectra = (const float*) h->d_spectra.ptr; v.payload = (const uint8_t*) h->d_payload.ptr; }
+	else { v.spectra = (const float*) h->d_spectra.ptr; v.payload = (const uint8_t*) h->d_entries.ptr; }   // (what k_packet_decode writes)
 	v.inv_db = ctx->d_inv_db;
 	v.pcm = (float*) h->d_pcm.ptr;
 	v.status = (uint32_t*) h->d_status.ptr;
@@ -717,7 +865,15 @@ static DevBatchView make_view(pov_ctx* ctx, pov_batch_handle* h) {
 }
 
 static int run_residue_if_needed(pov_ctx* ctx, pov_batch_handle* h, const DevBatchView& v) {
-	if(h->input_kind != POV_INPUT_ENTRIES) return POV_OK;
+	if(h->input_kind == POV_INPUT_DENSE) return POV_OK;
+	if(h->input_kind == POV_INPUT_PACKETS) {
+		// entropy decode on the device: raw packet bytes -> floor_used + Y lists + entries payload (then as POV_INPUT_ENTRIES)
+		DevBatchView raw = v;
+		raw.payload = (const uint8_t*) h->d_payload.ptr;
+		const uint64_t* off = (const uint64_t*) h->d_pk_off.ptr;
+		CUDA_TRY(ctx, launch_packet_decode(raw, (pov_packet*) h->d_packets.ptr, (uint16_t*) h->d_ys.ptr, (uint8_t*) h->d_entries.ptr, off, off + h->n_packets,
+		                                   off + 2 * (size_t) h->n_packets, h->n_packets, ctx->stream, &ctx->launches));
+	}
 	CUDA_TRY(ctx, launch_residue_apply(v, (float*) h->d_spectra.ptr, h->res_smem, ctx->stream, &ctx->launches));
 	return POV_OK;
 }
@@ -798,6 +954,7 @@ extern "C" int pov_batch_fetch_pcm(pov_ctx* ctx, pov_batch_handle* h, float* out
 	if(n_floats > h->pcm_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_pcm: %llu floats requested, arena holds %llu", (unsigned long long) n_floats, (unsigned long long) h->pcm_floats);
 	cudaSetDevice(ctx->device);
 	if(n_floats) CUDA_TRY(ctx, cudaMemcpyAsync(out, h->d_pcm.ptr, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	ctx->d2h_bytes += n_floats * sizeof(float);
 	if(sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return POV_OK;
 } POV_NOTHROW_END(ctx)
@@ -809,6 +966,7 @@ extern "C" int pov_batch_status(pov_ctx* ctx, pov_batch_handle* h, uint32_t* out
 	cudaSetDevice(ctx->device);
 	std::vector<uint32_t> tmp(h->n_packets);
 	CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), h->d_status.ptr, sizeof(uint32_t) * h->n_packets, cudaMemcpyDeviceToHost, ctx->stream));
+	ctx->d2h_bytes += sizeof(uint32_t) * h->n_packets;
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	if(out) memcpy(out, tmp.data(), sizeof(uint32_t) * std::min<uint32_t>(n, h->n_packets));
 	for(uint32_t p = 0; p < h->n_packets; ++p) {

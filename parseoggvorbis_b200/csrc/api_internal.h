@@ -52,6 +52,13 @@ struct SetupRec {
 	uint32_t fast_short_cap = 4;
 	uint32_t fast_max_nl = 1;         // largest channel set a coupling program of this setup needs
 	const FastTables* d_fast = nullptr;
+	// device entropy decode (POV_INPUT_PACKETS): tables + per-mode arena capacities of one packet
+	bool entropy_ok = false;
+	const uint32_t* d_huff = nullptr;
+	const DevHuffBook* d_hbooks = nullptr;
+	const DevFloorSyntax* d_fsyntax = nullptr;
+	uint32_t mode_ys_cap[POV_MAX_MODES] = {0};       // uint16 slots: every channel's Y list
+	uint32_t mode_ent_cap[POV_MAX_MODES] = {0};      // bytes of the entries payload in the worst case (multiple of 4)
 	std::string image;            // canonical bytes, for de-duplication
 };
 
@@ -60,8 +67,10 @@ struct pov_ctx {
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
 	uint64_t launches = 0;
+	uint64_t h2d_bytes = 0, d2h_bytes = 0;   // what this context copied between host and device (pov_ctx_io_bytes)
 	uint32_t run_len = 0;         // 0 = automatic
 	int kernel_choice = 0;        // POV_KERNEL: 0 automatic, 1 force the CTA-per-run fused kernel, 2 require the warp kernel
+	bool device_entropy = true;   // whole-file / corpus decode: audio packets are entropy-decoded on the device (POV_DEVICE_ENTROPY=0: on the host)
 	uint32_t* d_counter = nullptr; // work counter of the persistent kernel
 	const float* d_inv_db = nullptr;
 	const DevSetup* d_setups = nullptr;
@@ -87,9 +96,12 @@ struct pov_batch_handle {
 	uint32_t warp_setup = 0;
 	std::vector<WarpGroup> warp_groups;
 	std::vector<uint64_t> spec_off, stage_off;
+	std::vector<uint64_t> pk_ys_off, pk_ent_off, pk_raw_off;     // POV_INPUT_PACKETS: capacity-based places of a packet's Y lists / entries payload
+	uint64_t ys_cap = 0, ent_cap = 0;
 	std::vector<uint32_t> pk_n, pk_setup;
 	std::vector<DevRun> runs;
 	DevBuf d_streams, d_packets, d_ys, d_payload, d_spec_off, d_stage_off, d_runs, d_pcm, d_status, d_spectra;
+	DevBuf d_entries, d_pk_off;                      // POV_INPUT_PACKETS: entries payload written by k_packet_decode; ys_off | ent_off
 	DevBuf st_final_ys, st_flag, st_floor, st_floor_out, st_env, st_mdct;
 	// pinned copy of the derived arrays (spec_off | runs): sources of asynchronous copies, so they must not be pageable
 	// (a pageable source makes the "async" copy wait for the stream) and must outlive the copy (derived_copied)

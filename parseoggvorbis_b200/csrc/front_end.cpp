@@ -55,13 +55,19 @@ static bool finish_stream_tables(pov_parsed& P, std::string& why) {
 }
 
 extern "C" int pov_ogg_parse_memory(const uint8_t* data, size_t len, pov_parsed** out, const char** error_out) {
+	return pov_ogg_parse_memory_ex(data, len, 0, out, error_out);
+}
+
+extern "C" int pov_ogg_parse_memory_ex(const uint8_t* data, size_t len, uint32_t flags, pov_parsed** out, const char** error_out) {
 	static thread_local char errbuf[512];
 	if(!out || (!data && len)) return POV_ERR_ARG;
 	*out = nullptr;
 	try {
 	std::unique_ptr<pov_parsed> P(new pov_parsed());
 	ParseError err;
-	if(!parse_ogg_file(data, len, P->streams, err)) {
+	ParseOptions opt;
+	opt.raw_packets = (flags & POV_PARSE_RAW_PACKETS) != 0;
+	if(!parse_ogg_file(data, len, P->streams, err, opt)) {
 		snprintf(errbuf, sizeof errbuf, "check failed: %s", err.msg.c_str());
 		if(error_out) *error_out = errbuf;
 		return POV_ERR_STREAM;
@@ -89,7 +95,7 @@ extern "C" int pov_parsed_get(const pov_parsed* p, uint32_t stream, pov_setup* s
 	if(setup_out) *setup_out = p->abi[stream]->s;
 	if(batch_out) {
 		memset(batch_out, 0, sizeof *batch_out);
-		batch_out->input_kind = POV_INPUT_ENTRIES;
+		batch_out->input_kind = st.raw ? POV_INPUT_PACKETS : POV_INPUT_ENTRIES;
 		batch_out->pcm_layout = POV_PCM_PLANAR;
 		batch_out->n_streams = 1; batch_out->streams = &p->stream_rec[stream];
 		batch_out->n_packets = (uint32_t) st.packets.size(); batch_out->packets = st.packets.data();
@@ -111,10 +117,11 @@ struct HostBatch {
 	std::vector<uint16_t> ys;
 	std::vector<uint8_t> payload;
 	uint64_t pcm_floats = 0;
+	bool raw = false;                          // the payload holds raw audio packets (POV_INPUT_PACKETS)
 	pov_batch view() const {
 		pov_batch b;
 		memset(&b, 0, sizeof b);
-		b.input_kind = POV_INPUT_ENTRIES; b.pcm_layout = POV_PCM_PLANAR;
+		b.input_kind = raw ? POV_INPUT_PACKETS : POV_INPUT_ENTRIES; b.pcm_layout = POV_PCM_PLANAR;
 		b.n_streams = (uint32_t) streams.size(); b.streams = streams.data();
 		b.n_packets = (uint32_t) packets.size(); b.packets = packets.data();
 		b.ys = ys.data(); b.n_ys = ys.size();
@@ -163,7 +170,19 @@ extern "C" int pov_ogg_vorbis_decode_memory(pov_ctx* ctx, const uint8_t* data, s
 	memset(out, 0, sizeof *out);
 	std::vector<StreamWork> streams;
 	ParseError err;
-	if(!parse_ogg_file(data, len, streams, err)) return pov_fail(ctx, POV_ERR_STREAM, "check failed: %s", err.msg.c_str());
+	// without a dump the audio packets go to the device as they are (entropy decode there); the dump writer needs the
+	// host-side Y lists, so that path keeps the host walk. A file whose streams cannot all be walked on the device is parsed again.
+	ParseOptions opt;
+	opt.raw_packets = ctx->device_entropy && !debug_out;
+	for(int attempt = 0; attempt < 2; ++attempt) {
+		streams.clear();
+		err = ParseError();
+		if(!parse_ogg_file(data, len, streams, err, opt)) return pov_fail(ctx, POV_ERR_STREAM, "check failed: %s", err.msg.c_str());
+		bool mixed = false;
+		for(const StreamWork& st : streams) if(st.have_setup && st.raw != opt.raw_packets) mixed = true;
+		if(!mixed) break;
+		opt.raw_packets = false;
+	}
 	// keep the streams that reached their setup header; all must agree on the channel layout to share one PCM array
 	std::vector<const StreamWork*> use;
 	for(const StreamWork& st : streams) if(st.have_setup) use.push_back(&st);
@@ -173,6 +192,7 @@ extern "C" int pov_ogg_vorbis_decode_memory(pov_ctx* ctx, const uint8_t* data, s
 			return pov_fail(ctx, POV_ERR_UNSUPPORTED, "logical streams with different channel layouts in one file");
 	if(debug_out && use.size() != 1) return pov_fail(ctx, POV_ERR_UNSUPPORTED, "debug dump needs exactly one logical stream");
 	HostBatch hb;
+	hb.raw = opt.raw_packets;
 	for(const StreamWork* st : use) {
 		uint32_t id = 0;
 		int rc = register_stream_setup(ctx, *st, &id);
@@ -338,7 +358,10 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 	// automatic: every core but one — the calling thread validates, queues and retires chunks and must not be time-sliced
 	// against the parsers (measured on 16 cores: 15 workers 6.8e9 samples/s and stable, 16 workers 2.6-3.7e9)
 	if(host_threads == 0) { const uint32_t hc = std::thread::hardware_concurrency(); host_threads = hc > 1 ? hc - 1 : 1; }
-	uint32_t files_per_chunk = 64;
+	// Files per chunk: with the entropy decode on the device a chunk's kernels are latency bound (one thread walks one packet),
+	// so more packets per launch cost nothing and the PCM copy-out — the PCIe bound of the whole decode — runs in long
+	// transfers; with the host walk smaller chunks keep the parser threads and the device overlapped.
+	uint32_t files_per_chunk = ctx->device_entropy ? 256 : 64;
 	if(const char* e = getenv("POV_CORPUS_CHUNK")) files_per_chunk = std::max(1, atoi(e));
 	const uint32_t n_chunks = (n_files + files_per_chunk - 1) / files_per_chunk;
 	const uint32_t max_ready = std::max<uint32_t>(4, 2 * host_threads);
@@ -362,7 +385,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 	cs.max_bufs = std::max(cs.max_bufs, max_ready + host_threads + 3);       // queued + being filled + two in flight + one spare
 	for(auto& sl : cs.slot)
 		if(cudaMemsetAsync(sl.d_sum, 0, sizeof(double), sl.ctx->stream) != cudaSuccess) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaMemset failed");
-	const uint64_t sibling_launches0 = cs.sibling->launches;
+	const uint64_t sibling_launches0 = cs.sibling->launches, sibling_h2d0 = cs.sibling->h2d_bytes, sibling_d2h0 = cs.sibling->d2h_bytes;
 
 	std::atomic<uint32_t> next_chunk(0);
 	std::mutex mu;
@@ -384,16 +407,23 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 			ck->n_files = std::min(files_per_chunk, n_files - ck->first_file);
 			ck->frames.assign(ck->n_files, 0);
 			hb.clear();
+			ParseOptions opt;
+			opt.raw_packets = ctx->device_entropy;
 			try {                  // a worker never lets an exception escape its thread: the chunk carries the error instead
+			for(int attempt = 0; attempt < 2; ++attempt) {       // (second round only if a stream cannot be walked on the device)
+			bool mixed = false;
+			hb.clear(); hb.raw = opt.raw_packets;
+			ck->setups.clear(); ck->stream_file.clear(); ck->stream_channels.clear(); ck->frames.assign(ck->n_files, 0);
 			for(uint32_t i = 0; i < ck->n_files && ck->error.empty(); ++i) {
 				ParseError err;
 				file.clear();
-				if(!parse_ogg_file(data[ck->first_file + i], len[ck->first_file + i], file, err)) {
+				if(!parse_ogg_file(data[ck->first_file + i], len[ck->first_file + i], file, err, opt)) {
 					ck->error = "file " + std::to_string(ck->first_file + i) + ": check failed: " + err.msg;
 					break;
 				}
 				for(StreamWork& st : file) {
 					if(!st.have_setup) continue;
+					if(st.raw != opt.raw_packets) mixed = true;
 					uint32_t k = 0;
 					while(k < ck->setups.size() && ck->setups[k].setup_key != st.setup_key) ++k;
 					hb.append(st, k);
@@ -405,6 +435,9 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 						ck->setups.push_back(std::move(st));
 					}
 				}
+			}
+			if(!mixed || !ck->error.empty()) break;
+			opt.raw_packets = false;
 			}
 			if(ck->error.empty() && !hb.packets.empty()) {
 				// pageable vectors -> one pinned buffer (this copy runs on the worker, the DMA later needs no staging)
@@ -420,7 +453,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 					memcpy(q + o_ys, hb.ys.data(), hb.ys.size() * sizeof(uint16_t));
 					memcpy(q + o_pl, hb.payload.data(), hb.payload.size());
 					pov_batch& b = ck->view;
-					b.input_kind = POV_INPUT_ENTRIES; b.pcm_layout = POV_PCM_PLANAR;
+					b.input_kind = hb.raw ? POV_INPUT_PACKETS : POV_INPUT_ENTRIES; b.pcm_layout = POV_PCM_PLANAR;
 					ck->streams = (pov_stream*) (q + o_st);
 					b.n_streams = (uint32_t) hb.streams.size(); b.streams = ck->streams;
 					b.n_packets = (uint32_t) hb.packets.size(); b.packets = (const pov_packet*) (q + o_pk);
@@ -463,6 +496,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 	const bool timing = getenv("POV_CORPUS_TIMING") != nullptr;
 	double g_copy_in_kernels = 0, g_copy_out = 0;
 	if(timing) for(auto& sl : cs.slot) if(!sl.t_begin) { cudaEventCreate(&sl.t_begin); cudaEventCreate(&sl.t_kernels); cudaEventCreate(&sl.t_end); }
+	bool stopped = false;
 	auto retire = [&](Slot& sl) -> int {           // wait for a slot's chunk and turn its status words into the reference's error
 		if(!sl.busy) return POV_OK;
 		sl.busy = false;
@@ -482,7 +516,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 			}
 		// the output edge (hpp:966-973 gotPcmData, hpp:1047-1053): every logical stream of the chunk, in file order, from the
 		// calling thread; the samples stay valid during the callback only (they live in this slot's pinned buffer)
-		if(out == POV_OK && sink && sl.in_flight && sl.n_packets) {
+		if(out == POV_OK && sink && !stopped && sl.in_flight && sl.n_packets) {
 			const Chunk& ck = *sl.in_flight;
 			for(uint32_t i = 0; i < ck.view.n_streams && out == POV_OK; ++i) {
 				const pov_stream& rec = ck.streams[i];
@@ -491,6 +525,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 					out = pov_fail(ctx, POV_ERR_STREAM, "file %u: check failed: callbacks.gotPcmData(channelPcms) (hpp:1052: the sink asked to stop)", ck.stream_file[i]);
 			}
 		}
+		if(out != POV_OK) stopped = true;          // after the first failure nothing more is delivered (chunks in flight are only drained)
 		if(sl.in_flight) { cs.release(sl.in_flight->buf); sl.in_flight.reset(); }
 		return out;
 	};
@@ -560,6 +595,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 			rc = pov_batch_fetch_pcm(cx, sl.h, sl.pinned, pcm_floats, 0);       // delivery of the PCM to the host (asynchronous)
 			if(!rc && cudaMemcpyAsync(sl.status, sl.h->d_status.ptr, sneed, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess)
 				rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: status copy failed");
+			cx->d2h_bytes += sneed;
 			if(timing) cudaEventRecord(sl.t_end, cx->stream);
 			if(!rc && cudaEventRecord(sl.done, cx->stream) != cudaSuccess) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventRecord failed");
 			if(!rc) { sl.n_packets = n_packets; sl.first_file = sl.in_flight->first_file; }
@@ -592,6 +628,8 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 		cudaStreamSynchronize(sl.ctx->stream);
 	}
 	ctx->launches += cs.sibling->launches - sibling_launches0;
+	ctx->h2d_bytes += cs.sibling->h2d_bytes - sibling_h2d0;
+	ctx->d2h_bytes += cs.sibling->d2h_bytes - sibling_d2h0;
 	if(total_values_out) *total_values_out = total;
 	if(checksum_out) *checksum_out = h_sum;
 	return rc;

@@ -45,6 +45,27 @@ struct DevCodebook {
 	const float* vq;                   // device pointer
 };
 
+// ---- device-side entropy decode (POV_INPUT_PACKETS, kernel_entropy.cu) ------------------------------------------------
+// Huffman tables of one codebook inside the setup's uint32 arena: a first-level table indexed by the next kHuffLutBits
+// stream bits ((entry << 6) | length; 0 = the codeword is longer) and, for those, the codewords sorted by left-aligned value
+// (sorted_code[i], then (entry << 6 | length)[i]).
+#define POV_HUFF_LUT_BITS 9
+struct DevHuffBook {
+	uint32_t lut_off;       // uint32 index into the arena
+	uint32_t sorted_off;    // n_sorted codes, then n_sorted (entry << 6 | length)
+	uint32_t n_sorted;
+	uint32_t n_entries;
+	uint32_t dim;
+	uint32_t lookup_type;
+	uint32_t pad[2];
+};
+struct DevFloorSyntax {         // pov_floor1_syntax + what the Y walk needs from the floor itself
+	uint8_t n_partitions, n_classes, ybits, pad;
+	uint8_t partition_class[32];
+	uint8_t class_dim[16], class_subclass_bits[16], class_masterbook[16];
+	int16_t class_books[16][8];
+};
+
 struct DevSetup {
 	uint32_t channels;
 	uint32_t blocksize[2];
@@ -57,6 +78,13 @@ struct DevSetup {
 	const DevMapping*  mappings;
 	const DevResidue*  residues;
 	const DevCodebook* codebooks;
+	// entropy decode on the device (null when the setup came without codebook lengths / floor syntax)
+	const uint32_t*       huff;        // arena
+	const DevHuffBook*    hbooks;      // [n_codebooks]
+	const DevFloorSyntax* fsyntax;     // [n_floors]
+	uint32_t classbook[64];            // per residue (pov_residue::classbook)
+	uint32_t mode_bits;                // ilog(n_modes - 1): bits of the mode number (hpp:1146)
+	uint32_t pad_e;
 	// Rising window slope of length blocksize[k]/2 (hpp:850-853); the falling slope is its mirror image
 	// (same argument expression, hpp:857) and everything else of a window is exactly 0 or 1.
 	const float*  slope[2];

@@ -96,13 +96,17 @@ static uint32_t pow_u32(uint32_t base, uint32_t e) {   // Utils.hpp:205-217 with
 
 // Vorbis I 3.2.1: every entry takes the lowest-valued free codeword of its length; the tree must end up exactly
 // full (hpp:151-185 rejects over- and under-specified trees, a single-entry book included).
-static bool assign_codewords(const std::vector<uint8_t>& lens, const std::vector<uint32_t>& nums, HuffBook& book, const Fail& fail) {
+bool build_huff_tables(const uint8_t* lengths, uint32_t n_entries, int lut_bits, HuffTables& out, std::string& why) {
+	std::vector<uint8_t> lens;
+	std::vector<uint32_t> nums;
+	for(uint32_t i = 0; i < n_entries; ++i) if(lengths[i]) { lens.push_back(lengths[i]); nums.push_back(i); }
 	uint32_t avail[33];
 	memset(avail, 0, sizeof avail);
 	const size_t n = lens.size();
 	std::vector<uint32_t> code(n);
 	size_t k = 0;
-	REQUIRE(n > 0, "codebook: no used entries (hpp:183 underspecified)");
+	if(n == 0) { why = "codebook: no used entries (hpp:183 underspecified)"; return false; }
+	for(size_t i = 0; i < n; ++i) if(lens[i] > 32) { why = "codebook: codeword length > 32 (hpp:132)"; return false; }
 	// first entry takes the all-zero codeword
 	{
 		const int L = lens[0];
@@ -113,33 +117,44 @@ static bool assign_codewords(const std::vector<uint8_t>& lens, const std::vector
 	for(; k < n; ++k) {
 		int z = lens[k];
 		while(z > 0 && !avail[z]) --z;
-		REQUIRE(z > 0, "codebook: overspecified Huffman tree (hpp:159,168)");
+		if(z <= 0) { why = "codebook: overspecified Huffman tree (hpp:159,168)"; return false; }
 		const uint32_t res = avail[z];
 		avail[z] = 0;
 		code[k] = res;                                   // left-aligned (MSB-first) codeword
 		for(int y = lens[k]; y > z; --y) avail[y] = res + (1u << (32 - y));
 	}
-	for(int i = 1; i <= 32; ++i) REQUIRE(avail[i] == 0, "codebook: underspecified Huffman tree (hpp:183-184)");
-	// sorted table for the slow path + LUT for codes of <= kFastBits
+	for(int i = 1; i <= 32; ++i) if(avail[i] != 0) { why = "codebook: underspecified Huffman tree (hpp:183-184)"; return false; }
+	// sorted table for the slow path + LUT for codes of <= lut_bits
 	std::vector<size_t> order(n);
 	for(size_t i = 0; i < n; ++i) order[i] = i;
 	std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return code[a] < code[b]; });
-	book.sorted_code.resize(n); book.sorted_entry.resize(n); book.sorted_len.resize(n);
+	out.sorted_code.resize(n); out.sorted_entry.resize(n); out.sorted_len.resize(n);
 	for(size_t i = 0; i < n; ++i) {
-		book.sorted_code[i] = code[order[i]];
-		book.sorted_entry[i] = nums[order[i]];
-		book.sorted_len[i] = lens[order[i]];
+		out.sorted_code[i] = code[order[i]];
+		out.sorted_entry[i] = nums[order[i]];
+		out.sorted_len[i] = lens[order[i]];
 	}
-	book.fast.assign(1u << HuffBook::kFastBits, 0);
+	out.lut.assign((size_t) 1 << lut_bits, 0);
 	for(size_t i = 0; i < n; ++i) {
 		const int L = lens[i];
-		if(L > HuffBook::kFastBits) continue;
+		if(L > lut_bits) continue;
 		// the stream delivers the codeword MSB first into the LSb-first bit order: reverse the L code bits
 		uint32_t rev = 0;
 		for(int b = 0; b < L; ++b) if(code[i] & (1u << (31 - b))) rev |= 1u << b;
-		for(uint32_t fill = rev; fill < (1u << HuffBook::kFastBits); fill += 1u << L)
-			book.fast[fill] = (nums[i] << 6) | (uint32_t) L;
+		for(uint32_t fill = rev; fill < (1u << lut_bits); fill += 1u << L)
+			out.lut[fill] = (nums[i] << 6) | (uint32_t) L;
 	}
+	return true;
+}
+
+static bool assign_codewords(HuffBook& book, const Fail& fail) {
+	HuffTables t;
+	std::string why;
+	if(!build_huff_tables(book.lengths.data(), book.n_entries, HuffBook::kFastBits, t, why)) return fail("%s", why.c_str());
+	book.fast = std::move(t.lut);
+	book.sorted_code = std::move(t.sorted_code);
+	book.sorted_entry = std::move(t.sorted_entry);
+	book.sorted_len = std::move(t.sorted_len);
 	return true;
 }
 
@@ -172,8 +187,7 @@ static bool parse_codebook(BitCursor& br, HuffBook& book, const Fail& fail) {
 	REQUIRE(book.dim > 0, "codebook: dimensions == 0 (hpp:257)");
 	book.n_entries = br.get(24);
 	REQUIRE(book.n_entries > 0, "codebook: entries == 0 (hpp:259)");
-	std::vector<uint8_t> lens;
-	std::vector<uint32_t> nums;
+	book.lengths.assign(book.n_entries, 0);
 	const bool ordered = br.get(1);
 	if(!ordered) {
 		const bool sparse = br.get(1);
@@ -182,8 +196,7 @@ static bool parse_codebook(BitCursor& br, HuffBook& book, const Fail& fail) {
 		REQUIRE((uint64_t) book.n_entries * (sparse ? 1u : 5u) <= br.nbits - std::min(br.nbits, br.pos), "codebook: truncated (hpp:327)");
 		for(uint32_t i = 0; i < book.n_entries; ++i) {
 			if(sparse && !br.get(1)) continue;
-			lens.push_back((uint8_t) (br.get(5) + 1));
-			nums.push_back(i);
+			book.lengths[i] = (uint8_t) (br.get(5) + 1);
 		}
 		REQUIRE(!br.overrun, "codebook: truncated (hpp:327)");
 	} else {
@@ -192,13 +205,13 @@ static bool parse_codebook(BitCursor& br, HuffBook& book, const Fail& fail) {
 			const uint32_t number = br.get(ilog(book.n_entries - cur));
 			REQUIRE(cur + number <= book.n_entries, "codebook: ordered lengths overflow (hpp:290)");
 			REQUIRE(len <= 32, "codebook: codeword length > 32 (hpp:132)");
-			for(uint32_t i = cur; i < cur + number; ++i) { lens.push_back((uint8_t) len); nums.push_back(i); }
+			for(uint32_t i = cur; i < cur + number; ++i) book.lengths[i] = (uint8_t) len;
 			cur += number;
 			++len;
 			REQUIRE(!br.overrun, "codebook: truncated (hpp:327)");
 		}
 	}
-	if(!assign_codewords(lens, nums, book, fail)) return false;
+	if(!assign_codewords(book, fail)) return false;
 	book.lookup_type = br.get(4);
 	REQUIRE(book.lookup_type <= 2, "codebook: lookup type %u (hpp:299)", book.lookup_type);
 	if(book.lookup_type != 0) {
@@ -508,7 +521,7 @@ static bool decode_residue_submap(BitCursor& br, const VorbisSetup& s, const Res
 	return true;
 }
 
-static bool decode_audio_packet(StreamWork& st, const uint8_t* p, size_t len, int64_t expected_end, const Fail& fail) {
+static bool decode_audio_packet(StreamWork& st, const uint8_t* p, size_t len, int64_t expected_end, const Fail& fail, const ParseOptions& opt) {
 	const VorbisSetup& s = st.setup;
 	BitCursor br;
 	br.reset(p, len);
@@ -530,7 +543,15 @@ static bool decode_audio_packet(StreamWork& st, const uint8_t* p, size_t len, in
 	pk.window_flags = (uint8_t) wflags;
 	pk.ys_off = st.ys.size();
 	pk.spec_off = st.payload.size();
-
+	if(st.raw) {
+		// the device walks the packet from here (POV_INPUT_PACKETS): hand over the bytes, zero padded to a multiple of 4.
+		// The checks the host walk would have made on the way (floor0, hpp:402; empty submap, hpp:680) depend on the setup
+		// only and are made once, by setup_supports_device_entropy(), before a stream is decoded this way.
+		REQUIRE(len <= 0xFFFFFFFFull, "audio packet too large");
+		pk.packet_bytes = (uint32_t) len;
+		st.payload.insert(st.payload.end(), p, p + len);
+		st.payload.resize((st.payload.size() + 3) & ~(size_t) 3, 0);
+	} else {
 	// 4.3.2 floor curve decode (hpp:478-518): Y values only, the curve itself is rendered on the GPU
 	uint32_t used = 0;
 	for(uint32_t c = 0; c < C; ++c) {
@@ -578,6 +599,7 @@ static bool decode_audio_packet(StreamWork& st, const uint8_t* p, size_t len, in
 		} else {
 			if(!decode_residue_submap(br, s, r, nch, ch_used, half, st.payload, fail)) return false;
 		}
+	}
 	}
 	// emit bookkeeping (hpp:1061-1067, 1019-1059)
 	st.prev_n = st.cur_n;
@@ -640,11 +662,11 @@ static bool check_comment_packet(const uint8_t* p, size_t len, const Fail& fail)
 	return true;
 }
 
-static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err);
+static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err, const ParseOptions& opt);
 // Never throws: an allocation failure (or any other exception) while parsing hostile input is a parse error like the rest.
-bool parse_ogg_file(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err) {
+bool parse_ogg_file(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err, const ParseOptions& opt) {
 	try {
-		return parse_ogg_file_checked(data, len, streams, err);
+		return parse_ogg_file_checked(data, len, streams, err, opt);
 	} catch(const std::bad_alloc&) {
 		err.failed = true; err.msg = "out of memory while parsing (sizes in the stream beyond what this machine can hold)";
 	} catch(const std::exception& e) {
@@ -655,7 +677,7 @@ bool parse_ogg_file(const uint8_t* data, size_t len, std::vector<StreamWork>& st
 	return false;
 }
 
-static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err) {
+static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err, const ParseOptions& opt) {
 	Fail fail{err};
 	std::map<uint32_t, size_t> live;                     // serial -> index into streams (erased at EOS, hpp:1480)
 	size_t pos = 0;
@@ -721,8 +743,9 @@ static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<
 					cached_setup = st.setup;
 				}
 				st.have_setup = true;
+				st.raw = opt.raw_packets && setup_supports_device_entropy(st.setup);
 			} else {
-				if(!decode_audio_packet(st, pp, plen, expected, fail)) {
+				if(!decode_audio_packet(st, pp, plen, expected, fail, opt)) {
 					err.msg = "audio packet " + std::to_string(st.packets.size()) + ": " + err.msg;
 					return false;
 				}
@@ -740,6 +763,19 @@ static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<
 // ---------------------------------------------------------------------------------------------------------------
 // parsed setup -> ABI structs
 // ---------------------------------------------------------------------------------------------------------------
+bool setup_supports_device_entropy(const VorbisSetup& s) {
+	if(s.books.size() > 255) return false;
+	for(const Floor1Setup& f : s.floors)
+		if(f.type != 1 || f.partition_class.size() > 31 || f.classes.size() > 16) return false;      // floor0: hpp:402
+	for(const MappingSetup& m : s.mappings)
+		for(uint32_t sm = 0; sm < m.n_submaps; ++sm) {
+			bool any = false;
+			for(uint8_t x : m.mux) any |= (x == sm);
+			if(!any) return false;                                                                    // hpp:680, fatal per packet
+		}
+	return true;
+}
+
 bool setup_to_abi(const VorbisSetup& in, SetupAbi& out, std::string& why) {
 	memset(&out.s, 0, sizeof out.s);
 	if(in.channels > POV_MAX_CHANNELS) { why = "more than 8 channels"; return false; }
@@ -750,9 +786,25 @@ bool setup_to_abi(const VorbisSetup& in, SetupAbi& out, std::string& why) {
 		out.cbs[i].lookup_type = in.books[i].lookup_type;
 		out.cbs[i].reserved = 0;
 		out.cbs[i].vq = in.books[i].lookup_type ? in.books[i].vq.data() : nullptr;
+		out.cbs[i].lengths = in.books[i].lengths.empty() ? nullptr : in.books[i].lengths.data();
 	}
 	out.floors.resize(in.floors.size());
+	out.floor_syntax.resize(in.floors.size());
 	for(size_t i = 0; i < in.floors.size(); ++i) {
+		pov_floor1_syntax& fs = out.floor_syntax[i];
+		memset(&fs, 0, sizeof fs);
+		if(in.floors[i].type == 1 && in.floors[i].partition_class.size() <= 32 && in.floors[i].classes.size() <= 16) {
+			const Floor1Setup& f = in.floors[i];
+			fs.n_partitions = (uint8_t) f.partition_class.size();
+			fs.n_classes = (uint8_t) f.classes.size();
+			for(size_t k = 0; k < f.partition_class.size(); ++k) fs.partition_class[k] = f.partition_class[k];
+			for(size_t k = 0; k < f.classes.size(); ++k) {
+				fs.class_dim[k] = (uint8_t) f.classes[k].dim;
+				fs.class_subclass_bits[k] = (uint8_t) f.classes[k].subclass_bits;
+				fs.class_masterbook[k] = (uint8_t) f.classes[k].masterbook;
+				for(int b = 0; b < 8; ++b) fs.class_books[k][b] = (b < (1 << f.classes[k].subclass_bits)) ? (int16_t) f.classes[k].books[b] : (int16_t) -1;
+			}
+		}
 		memset(&out.floors[i], 0, sizeof(pov_floor1));
 		if(in.floors[i].type != 1) {
 			// floor0 cannot be decoded by the reference either (hpp:402); give the slot a harmless 2-post placeholder,
@@ -792,6 +844,7 @@ bool setup_to_abi(const VorbisSetup& in, SetupAbi& out, std::string& why) {
 	s.n_residues = (uint32_t) out.residues.size(); s.residues = out.residues.data();
 	s.n_mappings = (uint32_t) out.mappings.size(); s.mappings = out.mappings.data();
 	s.n_modes = (uint32_t) out.modes.size(); s.modes = out.modes.data();
+	s.floor_syntax = out.floor_syntax.data();
 	return true;
 }
 

@@ -34,6 +34,7 @@ struct BitCursor {
 struct HuffBook {
 	uint32_t dim = 0, n_entries = 0, lookup_type = 0;
 	std::vector<float> vq;                   // [n_entries*dim] when lookup_type != 0 (hpp:212-245)
+	std::vector<uint8_t> lengths;            // codeword length per entry, 0 = unused (hpp:126, 270-272)
 	// decode tables
 	static constexpr int kFastBits = 10;
 	std::vector<uint32_t> fast;              // [1<<kFastBits]: (entry << 6) | len, len == 0 -> slow path
@@ -92,6 +93,7 @@ struct StreamWork {
 	uint32_t serial = 0;
 	VorbisSetup setup;
 	bool have_id = false, have_comment = false, have_setup = false, ended = false;
+	bool raw = false;                         // the payload holds raw audio packets (POV_INPUT_PACKETS), not entry numbers
 	std::string setup_key;                    // raw id + setup packet bytes: identical keys <=> identical setups
 	uint32_t packets_seen = 0;
 	// per audio packet
@@ -108,9 +110,22 @@ struct StreamWork {
 
 struct ParseError { bool failed = false; std::string msg; };
 
+// raw_packets: audio packets are not entropy-decoded here; the descriptors carry the packet bytes (POV_INPUT_PACKETS:
+// mode, window flags and the emit bookkeeping only need the first bits of a packet) and the device walks the rest.
+struct ParseOptions { bool raw_packets = false; };
+
 // Parses a whole Ogg file from memory (hpp:1428 full_read_from_memory). Streams appear in order of their BOS page.
 // Returns false and fills err on the first failing check, like the reference's OkOrError chain.
-bool parse_ogg_file(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err);
+bool parse_ogg_file(const uint8_t* data, size_t len, std::vector<StreamWork>& streams, ParseError& err, const ParseOptions& opt = ParseOptions());
+
+// Huffman decode tables from codeword lengths (Vorbis I 3.2.1, hpp:151-185): a first-level table indexed by the next
+// `lut_bits` stream bits ((entry << 6) | length, 0 = longer codeword) and the codewords sorted by their left-aligned value
+// for the rest. Shared by the host decoder (HuffBook) and the device tables of pov_setup_register. False: not a full tree.
+struct HuffTables {
+	std::vector<uint32_t> lut, sorted_code, sorted_entry;
+	std::vector<uint8_t> sorted_len;
+};
+bool build_huff_tables(const uint8_t* lengths, uint32_t n_entries, int lut_bits, HuffTables& out, std::string& why);
 
 // Converts a parsed setup into the ABI structs (storage owned by `keep`).
 struct SetupAbi {
@@ -120,8 +135,11 @@ struct SetupAbi {
 	std::vector<pov_residue> residues;
 	std::vector<pov_mapping> mappings;
 	std::vector<pov_mode> modes;
+	std::vector<pov_floor1_syntax> floor_syntax;
 };
 bool setup_to_abi(const VorbisSetup& in, SetupAbi& out, std::string& why_unsupported);
+// Can the packets of a stream with this setup be walked on the device? (floor1 only, no empty submap, table sizes in range)
+bool setup_supports_device_entropy(const VorbisSetup& s);
 
 uint32_t ogg_crc(uint32_t crc, const uint8_t* p, size_t n);
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_c_compiler(tmp_path):
-    names = ["pov_codebook", "pov_floor1", "pov_residue", "pov_mapping", "pov_mode", "pov_setup", "pov_stream",
+    names = ["pov_codebook", "pov_floor1", "pov_floor1_syntax", "pov_residue", "pov_mapping", "pov_mode", "pov_setup", "pov_stream",
              "pov_packet", "pov_batch", "pov_decoded"]
     src = tmp_path / "s.c"
     src.write_text('#include <stdio.h>\n#include "pov_synth.h"\nint main(){' +

@@ -188,3 +188,57 @@ def test_corpus_output_edge_stops_when_the_sink_says_so(ctx):
     assert "gotPcmData" in str(ei.value) and calls[-1] == 70 and calls == list(range(71))
     f, t, _ = ctx.decode_corpus(files, host_threads=3)           # the context keeps working
     assert len(f) == 200 and t > 0
+
+
+def _stage_all(ctx, h, b, s, npk_blocksizes, stage, count_of):
+    out = []
+    for p, n in enumerate(npk_blocksizes):
+        for c in range(int(s.channels)):
+            k = count_of(int(n))
+            buf = np.empty(k, np.float32)
+            ctx._check(ctx.L.pov_batch_fetch_stage(ctx.ctx, h, p, c, stage, buf.ctypes.data_as(C.c_void_p), buf.nbytes))
+            out.append(buf)
+    return out
+
+
+@pytest.mark.parametrize("name", list(FIX))
+def test_device_entropy_decode_is_bit_exact(ctx, golden, name):
+    """f2: the audio packets go to the device as raw bytes (POV_INPUT_PACKETS) and k_packet_decode walks them: floor flags,
+    coded Ys, classifications and VQ entry numbers. `after_residue` must equal the reference dump bit for bit (hpp:696-760,
+    347-374), the status words must be clean, and the PCM must equal what the host-decoded batch gives, bit for bit."""
+    g = golden[name]
+    data = _load(name)
+    po = lib.ParsedOgg(data, raw_packets=True)
+    s, b = po.get(0)
+    assert b.input_kind == abi.POV_INPUT_PACKETS
+    sid = C.c_uint32(0)
+    ctx._check(ctx.L.pov_setup_register(ctx.ctx, C.byref(s), C.byref(sid)))
+    st = abi.pov_stream.from_address(C.addressof(b.streams.contents))
+    st.setup_id = sid.value
+    h = C.c_void_p(None)
+    ctx._check(ctx.L.pov_batch_upload(ctx.ctx, C.byref(b), C.byref(h)))
+    ctx._check(ctx.L.pov_batch_run_staged(ctx.ctx, h))
+    status = np.zeros(int(b.n_packets), np.uint32)
+    ctx._check(ctx.L.pov_batch_status(ctx.ctx, h, status.ctypes.data_as(C.POINTER(C.c_uint32)), status.size))
+    assert not status.any()
+    res = _stage_all(ctx, h, b, s, g["blocksize"], abi.POV_STAGE_AFTER_RESIDUE, lambda n: n // 2)
+    got = np.concatenate(res)
+    assert np.array_equal(got, g["after_residue"])            # (value equality: libvorbis' golden carries a few -0.0)
+    env = np.concatenate(_stage_all(ctx, h, b, s, g["blocksize"], abi.POV_STAGE_AFTER_ENVELOPE, lambda n: n // 2))
+    assert np.array_equal(env, g["after_envelope"])
+    ctx._check(ctx.L.pov_batch_run(ctx.ctx, h))
+    pcm_dev = np.empty(int(b.pcm_floats), np.float32)
+    ctx._check(ctx.L.pov_batch_fetch_pcm(ctx.ctx, h, pcm_dev.ctypes.data_as(C.POINTER(C.c_float)), pcm_dev.size, 1))
+    st.setup_id = 0
+    ctx.L.pov_batch_free(ctx.ctx, h)
+    po.close()
+    # the same file with the host walk
+    ctx.set_device_entropy(False)
+    try:
+        pcm_host, _, _ = ctx.decode_ogg(data)
+    finally:
+        ctx.set_device_entropy(True)
+    pcm_auto, _, _ = ctx.decode_ogg(data)
+    assert np.array_equal(pcm_host, pcm_auto)
+    assert np.array_equal(pcm_dev.reshape(pcm_host.shape), pcm_host)
+    assert np.abs(pcm_auto - g["pcm"]).max() <= 1e-5
