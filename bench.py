@@ -92,6 +92,46 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out += list(range(int(a), int(b or a) + 1))
+    return out
+
+
+def bind_to_gpu_numa(local, world):
+    """Pin this rank (and every thread it starts: parser workers, CUDA's helper threads) to its share of the cores of the
+    NUMA node its GPU hangs off, BEFORE any pinned allocation is made, so that staging buffers and PCM land in that node's
+    memory (first touch) and the ranks do not time-slice each other's parser threads. Returns what was done."""
+    import torch
+    info = {"node": None, "cpus": None}
+    try:
+        def node_of(g):
+            pr = torch.cuda.get_device_properties(g)
+            pci = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            with open("/sys/bus/pci/devices/%s/numa_node" % pci) as f:
+                return int(f.read())
+        nodes = [node_of(g) for g in range(world)]
+        mine = nodes[local]
+        allowed = sorted(os.sched_getaffinity(0))
+        if mine >= 0:
+            with open("/sys/devices/system/node/node%d/cpulist" % mine) as f:
+                cpus = [c for c in _cpulist(f.read()) if c in allowed] or allowed
+        else:
+            cpus = allowed
+        peers = [g for g in range(world) if nodes[g] == mine]
+        k, n = peers.index(local), len(peers)
+        share = cpus[k * len(cpus) // n:(k + 1) * len(cpus) // n] or cpus
+        os.sched_setaffinity(0, share)
+        info = {"node": mine, "cpus": len(share), "ranks_on_node": n}
+    except Exception as e:      # no sysfs / no permission: run unpinned
+        info["error"] = str(e)
+    return info
+
+
 def pinned_like(arr):
     import torch
     t = torch.empty(arr.shape, dtype=getattr(torch, str(arr.dtype)) if arr.dtype.names is None else torch.uint8,
@@ -254,6 +294,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local)
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local, world)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -330,8 +372,8 @@ def main():
         with open(CORPUS_FILE, "rb") as f:
             one = f.read()
         files = [bytes(bytearray(one)) for _ in range(args.corpus_files)]       # distinct host copies (255 MB for 10 000)
-        cores = os.cpu_count() or 1
-        threads = args.corpus_threads or max(1, cores // world - 1)
+        cores = len(os.sched_getaffinity(0))        # this rank's share (bind_to_gpu_numa)
+        threads = args.corpus_threads or max(1, cores - 1)
         cctx = SynthContext(local)
         frames, total, chk = cctx.decode_corpus(files, host_threads=threads)    # warm-up: tables, pinned pools and arenas at full size
         b0 = cctx.io_bytes()
@@ -354,7 +396,7 @@ def main():
                "h2d_bytes_per_step": int((b1[0] - b0[0]) // args.corpus_steps), "d2h_bytes_per_step": int((b1[1] - b0[1]) // args.corpus_steps),
                "steps": args.corpus_steps, "ms_per_step": float(tt.item()) / args.corpus_steps,
                "files_per_step_per_gpu": args.corpus_files, "ogg_bytes_per_step_per_gpu": len(one) * args.corpus_files,
-               "host_threads_per_rank": threads, "host_cores": cores,
+               "host_threads_per_rank": threads, "host_cores_of_rank": cores, "numa": numa,
                "per_rank_gb_per_s": {"h2d": (b1[0] - b0[0]) / wall / 1e9, "d2h": (b1[1] - b0[1]) / wall / 1e9},
                "pcm_values_per_step_ok": bool(total == expect), "checksum": chk,
                "timing": "host clock around pov_decode_corpus (parse + H2D + kernels + D2H into pinned host memory), barrier + "
@@ -450,6 +492,7 @@ def main():
         if e2e_dense:
             line["e2e_dense"] = e2e_dense
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, full_affinity)          # the CPU baseline gets every core of the box
             line["cpu_baseline"] = cpu_baseline_port(setup, batch, args.cpu_streams or (os.cpu_count() or 1))
         print(json.dumps(line))
     bh.free()

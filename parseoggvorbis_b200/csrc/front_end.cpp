@@ -269,7 +269,9 @@ struct Chunk {
 // their device arenas and pinned PCM buffers, and the pool of pinned staging buffers the workers assemble chunks into.
 struct CorpusState {
 	int device = 0;
-	pov_ctx* sibling = nullptr;
+	static constexpr int kSlots = 4;           // chunks in flight: while two copy their PCM out, the others compute (the copy-out,
+	                                           // 4 bytes per PCM sample over PCIe, is the bound of the whole decode)
+	pov_ctx* sibling[kSlots - 1] = {nullptr};
 	struct Slot {
 		pov_ctx* ctx = nullptr;                // slot 0: the caller's context; slot 1: the sibling, so that the copies of one
 		                                       // chunk never wait for the other chunk's work
@@ -282,7 +284,7 @@ struct CorpusState {
 		uint32_t n_packets = 0, first_file = 0;
 		std::unique_ptr<Chunk> in_flight;      // its pinned buffer is the source of copies that may still be running
 		bool busy = false;
-	} slot[2];
+	} slot[kSlots];
 	std::mutex pmu;
 	std::condition_variable pcv;
 	std::vector<PinnedBuf> free_bufs;
@@ -329,7 +331,7 @@ struct CorpusState {
 			if(sl.d_sum) cudaFree(sl.d_sum);
 		}
 		for(auto& b : free_bufs) cudaFreeHost(b.p);
-		if(sibling) pov_ctx_destroy(sibling);
+		for(pov_ctx* sb : sibling) if(sb) pov_ctx_destroy(sb);
 	}
 };
 void corpus_state_free(void* p) { delete (CorpusState*) p; }
@@ -372,8 +374,12 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 		std::unique_ptr<CorpusState> cs(new CorpusState());
 		cs->device = ctx->device;
 		const char* e = nullptr;
-		if(pov_ctx_create(ctx->device, &cs->sibling, &e) != POV_OK) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: %s", e ? e : "sibling context");
-		cs->slot[0].ctx = ctx; cs->slot[1].ctx = cs->sibling;
+		cs->slot[0].ctx = ctx;
+		for(int k = 1; k < CorpusState::kSlots; ++k) {
+			if(pov_ctx_create(ctx->device, &cs->sibling[k - 1], &e) != POV_OK) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: %s", e ? e : "sibling context");
+			cs->sibling[k - 1]->device_entropy = ctx->device_entropy;
+			cs->slot[k].ctx = cs->sibling[k - 1];
+		}
 		for(auto& sl : cs->slot) {
 			if(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess || cudaMalloc(&sl.d_sum, sizeof(double)) != cudaSuccess)
 				return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventCreate / cudaMalloc failed");
@@ -382,10 +388,11 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 		ctx->corpus_free = corpus_state_free;
 	}
 	CorpusState& cs = *(CorpusState*) ctx->corpus;
-	cs.max_bufs = std::max(cs.max_bufs, max_ready + host_threads + 3);       // queued + being filled + two in flight + one spare
+	cs.max_bufs = std::max(cs.max_bufs, max_ready + host_threads + CorpusState::kSlots + 1);       // queued + being filled + in flight + one spare
 	for(auto& sl : cs.slot)
 		if(cudaMemsetAsync(sl.d_sum, 0, sizeof(double), sl.ctx->stream) != cudaSuccess) return pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaMemset failed");
-	const uint64_t sibling_launches0 = cs.sibling->launches, sibling_h2d0 = cs.sibling->h2d_bytes, sibling_d2h0 = cs.sibling->d2h_bytes;
+	uint64_t sibling_launches0 = 0, sibling_h2d0 = 0, sibling_d2h0 = 0;
+	for(pov_ctx* sb : cs.sibling) { sibling_launches0 += sb->launches; sibling_h2d0 += sb->h2d_bytes; sibling_d2h0 += sb->d2h_bytes; }
 
 	std::atomic<uint32_t> next_chunk(0);
 	std::mutex mu;
@@ -549,7 +556,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 		if(!ck->error.empty()) { rc = pov_fail(ctx, POV_ERR_STREAM, "%s", ck->error.c_str()); cs.release(ck->buf); break; }
 		if(frames_out) for(uint32_t i = 0; i < ck->n_files; ++i) frames_out[ck->first_file + i] = ck->frames[i];
 		if(ck->view.n_packets == 0) { cs.release(ck->buf); continue; }
-		Slot& sl = cs.slot[ci & 1];
+		Slot& sl = cs.slot[ci % CorpusState::kSlots];
 		pov_ctx* cx = sl.ctx;
 		std::vector<uint32_t> ids(ck->setups.size(), 0);
 		for(size_t k = 0; k < ck->setups.size() && rc == POV_OK; ++k) {
@@ -603,8 +610,8 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 		total += pcm_floats;
 		t_fetch += now() - t0;
 	}
-	for(uint32_t k = 0; k < 2; ++k) {          // oldest chunk first: chunk n-2 sits in slot n & 1 (file order at the output edge)
-		const int r2 = retire(cs.slot[(n_chunks + k) & 1]);
+	for(uint32_t k = 0; k < (uint32_t) CorpusState::kSlots; ++k) {          // oldest chunk first (file order at the output edge)
+		const int r2 = retire(cs.slot[(n_chunks + k) % CorpusState::kSlots]);
 		if(rc == POV_OK) rc = r2;
 	}
 	if(timing)
@@ -627,9 +634,13 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 		h_sum += part;
 		cudaStreamSynchronize(sl.ctx->stream);
 	}
-	ctx->launches += cs.sibling->launches - sibling_launches0;
-	ctx->h2d_bytes += cs.sibling->h2d_bytes - sibling_h2d0;
-	ctx->d2h_bytes += cs.sibling->d2h_bytes - sibling_d2h0;
+	{
+		uint64_t l1 = 0, a1 = 0, b1 = 0;
+		for(pov_ctx* sb : cs.sibling) { l1 += sb->launches; a1 += sb->h2d_bytes; b1 += sb->d2h_bytes; }
+		ctx->launches += l1 - sibling_launches0;
+		ctx->h2d_bytes += a1 - sibling_h2d0;
+		ctx->d2h_bytes += b1 - sibling_d2h0;
+	}
 	if(total_values_out) *total_values_out = total;
 	if(checksum_out) *checksum_out = h_sum;
 	return rc;
