@@ -259,6 +259,18 @@ void pov_batch_free(pov_ctx* ctx, pov_batch_handle* h);
 
 /* ---- drop-in for the reference's only C symbols on the path: mdct_backward (src/mdct.h:105) ---------------- */
 /* `count` independent inverse MDCTs of size n (R^(n/2) -> R^n, no scaling), host buffers in/out. */
+/* Feature matrices straight from the device (the reference's downstream use: returnn_import.py:74-115 builds them in
+ * Python from a debug dump, demo_live_extract.py:262-505): `kind` as below with the readers' default arguments, for one
+ * stream of the batch; (rows, output_dim) floats, row-major, only the matrix crosses PCIe. Runs the staged kernels if they
+ * have not run yet. out == NULL: only *rows_out is set (size query).
+ *   FLOOR_FINAL_YS           get_features_from_raw_bytes(kind="floor_final_ys")            one row per decoded floor curve
+ *   FLOOR_FINAL_YS_RENDERED  kind="floor_final_ys_rendered"
+ *   RESIDUE_YS               kind="residue_ys"               rows of the packets whose (last channel's) floor has most posts
+ *   RESIDUE_YS_WITH_FLOOR    kind="residue_ys_with_floor"    (exp() is the device's: within 1e-6 relative of numpy's) */
+enum { POV_FEAT_FLOOR_FINAL_YS = 0, POV_FEAT_FLOOR_FINAL_YS_RENDERED = 1, POV_FEAT_RESIDUE_YS = 2, POV_FEAT_RESIDUE_YS_WITH_FLOOR = 3 };
+int  pov_batch_features(pov_ctx* ctx, pov_batch_handle* h, uint32_t stream, int kind, uint32_t output_dim,
+                        float* out, uint64_t rows_cap, uint64_t* rows_out);
+
 int  pov_mdct_backward_batch(pov_ctx* ctx, uint32_t n, uint64_t count, const float* in, float* out);
 
 /* ---- whole-stream decode through the host front-end (mirrors ogg_vorbis_full_read_from_memory, hpp:1493) - */

@@ -592,6 +592,7 @@ static void release_batch(pov_batch_handle* h) {
 	h->d_streams.release(); h->d_packets.release(); h->d_ys.release(); h->d_payload.release(); h->d_spec_off.release();
 	h->d_stage_off.release(); h->d_runs.release(); h->d_pcm.release(); h->d_status.release(); h->d_spectra.release();
 	h->d_entries.release(); h->d_pk_off.release();
+	h->d_feat_rows.release(); h->d_feat_floors.release(); h->d_feat_out.release();
 	h->st_final_ys.release(); h->st_flag.release(); h->st_floor.release(); h->st_floor_out.release();
 	h->st_env.release(); h->st_mdct.release();
 	if(h->h_derived) { cudaFreeHost(h->h_derived); h->h_derived = nullptr; h->h_derived_cap = 0; }
@@ -622,6 +623,8 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	// ---- validation + derived arrays (one pass over the packets) ----
 	const uint32_t P = b->n_packets;
 	h->spec_off.resize(P); h->stage_off.resize(P); h->pk_n.resize(P); h->pk_setup.resize(P);
+	h->pk_used.resize(P); h->pk_mode.resize(P);
+	h->streams_host.assign(b->streams, b->streams + b->n_streams);
 	const bool raw_packets = b->input_kind == POV_INPUT_PACKETS;
 	h->pk_ys_off.resize(raw_packets ? P : 0); h->pk_ent_off.resize(raw_packets ? P : 0); h->pk_raw_off.resize(raw_packets ? P : 0);
 	h->ys_cap = h->ent_cap = 0;
@@ -714,6 +717,7 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 			h->stage_off[p] = stage_floats;
 			stage_floats += (uint64_t) C * n;
 			h->pk_n[p] = n; h->pk_setup[p] = st.setup_id;
+			h->pk_used[p] = pk.floor_used; h->pk_mode[p] = pk.mode;
 			n_prev = n;
 		}
 		// runs of <= run_len packets, each later run re-transforming one halo packet. For the persistent warp kernel the
@@ -1047,6 +1051,92 @@ int pov_batch_fetch_stage_all(pov_ctx* ctx, pov_batch_handle* h, StageHost& out)
 // ---------------------------------------------------------------------------------------------------------------
 // drop-in for mdct_backward (src/mdct.h:105)
 // ---------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+// feature matrices for RETURNN-style front ends
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int pov_batch_features(pov_ctx* ctx, pov_batch_handle* h, uint32_t stream, int kind, uint32_t output_dim,
+                                  float* out, uint64_t rows_cap, uint64_t* rows_out) try {
+	if(!ctx || !h || !rows_out) return POV_ERR_ARG;
+	if(kind < POV_FEAT_FLOOR_FINAL_YS || kind > POV_FEAT_RESIDUE_YS_WITH_FLOOR) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: unknown kind %d", kind);
+	if(stream >= h->n_streams) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: stream out of range");
+	if(output_dim < 1 || output_dim > 4096) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: output_dim out of range");
+	cudaSetDevice(ctx->device);
+	int rc = POV_OK;
+	if(!h->staged_ready && (rc = pov_batch_run_staged(ctx, h)) != POV_OK) return rc;
+	const pov_stream& st = h->streams_host[stream];
+	const SetupRec& su = ctx->setups[st.setup_id];
+	const uint32_t C = su.channels, nf = (uint32_t) su.floors_host.size();
+	// which floors were decoded: the host's descriptors, or what k_packet_decode found in the packets
+	std::vector<uint16_t> used(h->pk_used);
+	if(h->input_kind == POV_INPUT_PACKETS) {
+		std::vector<pov_packet> tmp(h->n_packets);
+		CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), h->d_packets.ptr, sizeof(pov_packet) * h->n_packets, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		ctx->d2h_bytes += sizeof(pov_packet) * h->n_packets;
+		for(uint32_t p = 0; p < h->n_packets; ++p) used[p] = tmp[p].floor_used;
+	}
+	uint32_t biggest = 0;                 // demo_live_extract.py:313 / :442: the first floor with the most posts
+	for(uint32_t i = 1; i < nf; ++i) if(su.floors_host[i].n_posts > su.floors_host[biggest].n_posts) biggest = i;
+	if((kind == POV_FEAT_RESIDUE_YS || kind == POV_FEAT_RESIDUE_YS_WITH_FLOOR) && output_dim < su.floors_host[biggest].n_posts)
+		return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: output_dim %u < %u posts of the biggest floor (the reference asserts, demo_live_extract.py:486)",
+		                output_dim, su.floors_host[biggest].n_posts);
+	std::vector<FeatRow> rows;
+	uint64_t base = ~0ull;
+	uint32_t base_n = 0;
+	for(uint32_t k = 0; k < st.n_packets; ++k) {
+		const uint32_t p = st.first_packet + k, n = h->pk_n[p];
+		const DevMapping& mp = su.maps_host[su.mode_mapping[h->pk_mode[p]]];
+		if(kind <= POV_FEAT_FLOOR_FINAL_YS_RENDERED) {
+			for(uint32_t c = 0; c < C; ++c) {
+				if(!((used[p] >> c) & 1)) continue;
+				FeatRow r;
+				memset(&r, 0, sizeof r);
+				r.src = kind == POV_FEAT_FLOOR_FINAL_YS ? (uint64_t) p * h->max_channels + c : h->stage_off[p] + (uint64_t) c * n;
+				r.floor = mp.floor_of_ch[c]; r.n = n; r.base = ~0ull;
+				rows.push_back(r);
+			}
+		} else {
+			for(uint32_t c = 0; c < C; ++c)           // "floor1 floor" entries of this packet come before its "after_residue" entries
+				if(((used[p] >> c) & 1) && mp.floor_of_ch[c] == biggest) { base = h->stage_off[p] + (uint64_t) c * n; base_n = n; }
+			const uint32_t recent = mp.floor_of_ch[C - 1];     // the last "floor_number" entry before the residues (demo_live_extract.py:455)
+			if(recent != biggest) continue;
+			for(uint32_t c = 0; c < C; ++c) {
+				FeatRow r;
+				memset(&r, 0, sizeof r);
+				r.src = h->spec_off[p] + (uint64_t) c * (n / 2);
+				r.floor = recent; r.n = n;
+				r.base = kind == POV_FEAT_RESIDUE_YS_WITH_FLOOR ? base : ~0ull; r.base_n = base_n;
+				rows.push_back(r);
+			}
+		}
+	}
+	*rows_out = rows.size();
+	if(!out) return POV_OK;                                  // size query
+	if(rows.size() > rows_cap) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: %llu rows, room for %llu", (unsigned long long) rows.size(), (unsigned long long) rows_cap);
+	if(rows.empty()) return POV_OK;
+	std::vector<FeatFloor> ff(nf);
+	for(uint32_t i = 0; i < nf; ++i) {
+		memset(&ff[i], 0, sizeof(FeatFloor));
+		ff[i].tag = (float) (((double) i + 1.0) / (double) nf - 0.5);
+		ff[i].multiplier = su.floors_host[i].multiplier; ff[i].n_posts = su.floors_host[i].n_posts;
+		for(uint32_t k = 0; k < su.floors_host[i].n_posts; ++k) ff[i].xs[k] = su.floors_host[i].xs[k];
+	}
+	CUDA_TRY(ctx, h->d_feat_rows.reserve(rows.size() * sizeof(FeatRow)));
+	CUDA_TRY(ctx, h->d_feat_floors.reserve(ff.size() * sizeof(FeatFloor)));
+	CUDA_TRY(ctx, h->d_feat_out.reserve(rows.size() * (size_t) output_dim * sizeof(float)));
+	CUDA_TRY(ctx, cudaMemcpyAsync(h->d_feat_rows.ptr, rows.data(), rows.size() * sizeof(FeatRow), cudaMemcpyHostToDevice, ctx->stream));
+	CUDA_TRY(ctx, cudaMemcpyAsync(h->d_feat_floors.ptr, ff.data(), ff.size() * sizeof(FeatFloor), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->h2d_bytes += rows.size() * sizeof(FeatRow) + ff.size() * sizeof(FeatFloor);
+	const float* residue = (h->input_kind == POV_INPUT_DENSE) ? (const float*) h->d_payload.ptr : (const float*) h->d_spectra.ptr;
+	CUDA_TRY(ctx, launch_features(kind, (const FeatRow*) h->d_feat_rows.ptr, rows.size(), (const FeatFloor*) h->d_feat_floors.ptr, output_dim,
+	                              (const uint32_t*) h->st_final_ys.ptr, (const uint16_t*) h->st_floor.ptr, residue, (float*) h->d_feat_out.ptr,
+	                              ctx->stream, &ctx->launches));
+	CUDA_TRY(ctx, cudaMemcpyAsync(out, h->d_feat_out.ptr, rows.size() * (size_t) output_dim * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	ctx->d2h_bytes += rows.size() * (size_t) output_dim * sizeof(float);
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // rows / ff live on this stack frame
+	return POV_OK;
+} POV_NOTHROW_END(ctx)
+
 extern "C" int pov_mdct_backward_batch(pov_ctx* ctx, uint32_t n, uint64_t count, const float* in, float* out) try {
 	if(!ctx || (count && (!in || !out))) return POV_ERR_ARG;
 	if(!is_pow2_in(n, 64, 8192)) return pov_fail(ctx, POV_ERR_ARG, "pov_mdct_backward_batch: n = %u is not a power of two in 64..8192 (hpp:1295)", n);

@@ -99,6 +99,10 @@ struct pov_batch_handle {
 	std::vector<uint64_t> pk_ys_off, pk_ent_off, pk_raw_off;     // POV_INPUT_PACKETS: capacity-based places of a packet's Y lists / entries payload
 	uint64_t ys_cap = 0, ent_cap = 0;
 	std::vector<uint32_t> pk_n, pk_setup;
+	std::vector<uint16_t> pk_used;                   // floor_used as the host saw it (POV_INPUT_PACKETS: decoded on the device instead)
+	std::vector<uint8_t> pk_mode;
+	std::vector<pov_stream> streams_host;
+	DevBuf d_feat_rows, d_feat_floors, d_feat_out;   // pov_batch_features
 	std::vector<DevRun> runs;
 	DevBuf d_streams, d_packets, d_ys, d_payload, d_spec_off, d_stage_off, d_runs, d_pcm, d_status, d_spectra;
 	DevBuf d_entries, d_pk_off;                      // POV_INPUT_PACKETS: entries payload written by k_packet_decode; ys_off | ent_off

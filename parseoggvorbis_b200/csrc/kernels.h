@@ -52,6 +52,19 @@ cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_ru
                         uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
                         const float2* const tw8[2], const float2* const fp[2], const float* tmtab, uint32_t* d_counter, int sm_count, cudaStream_t st,
                         uint64_t* launches);
+// One row of a feature matrix (pov_batch_features; reference: demo_live_extract.py:262-505): where its values come from.
+struct FeatRow {
+	uint64_t src;        // kinds 0: index of the channel-packet's final_ys slot; 1: float offset of its rendered floor (u16);
+	                     // 2, 3: float offset of its after_residue vector
+	uint64_t base;       // kind 3: float offset of the rendered floor that scales the row, ~0 = none
+	uint32_t floor;      // floor number (row of the per-floor tables)
+	uint32_t n;          // block size of the source (and, kind 3, of the base floor in base_n)
+	uint32_t base_n;
+	uint32_t pad;
+};
+struct FeatFloor { float tag; uint32_t multiplier, n_posts, pad; uint16_t xs[POV_MAX_POSTS]; };   // tag = (floor + 1) / floors - 0.5
+cudaError_t launch_features(int kind, const FeatRow* rows, uint64_t n_rows, const FeatFloor* floors, uint32_t output_dim,
+                            const uint32_t* final_ys, const uint16_t* floor, const float* residue, float* out, cudaStream_t st, uint64_t* launches);
 cudaError_t launch_packet_decode(const DevBatchView& b, pov_packet* packets, uint16_t* ys_out, uint8_t* ent_out, const uint64_t* ys_off,
                                  const uint64_t* ent_off, const uint64_t* raw_off, uint32_t n_packets, cudaStream_t st, uint64_t* launches);
 cudaError_t launch_mdct_backward(const DevSetup* dummy, uint32_t n, uint64_t count, const float* in, float* out,

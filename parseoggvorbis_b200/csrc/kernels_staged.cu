@@ -405,6 +405,56 @@ cudaError_t launch_staged(const DevBatchView& b, const DevStageBuffers& sb, uint
 	return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Feature matrices: what the reference's Python readers compute from a debug dump
+// (demo_live_extract.py: read_floor_ys :262-408, read_residue_ys :410-505, default arguments), gathered on the device
+// from the staged kernels' intermediates. One warp per row, lanes over the columns; the expressions keep the readers'
+// float32 operation order so that kinds 0-2 come out bit for bit.
+//   0 floor_final_ys           [tag | (final_y * multiplier - 127.5) / 127.5 ...]          one row per decoded floor curve
+//   1 floor_final_ys_rendered  [tag | (floor[x_i] - 127.5) / 127.5 ...]                     x_i = the floor's X list, bitstream order
+//   2 residue_ys               [after_residue[min(x_i, n/2 - 1)] ...]                       packets of the floor with most posts
+//   3 residue_ys_with_floor    the same times exp(floor[min(x_i, n - 1)] / 255 - 1)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_features(int kind, const FeatRow* __restrict__ rows, uint64_t n_rows, const FeatFloor* __restrict__ floors, uint32_t dim,
+                           const uint32_t* __restrict__ final_ys, const uint16_t* __restrict__ floor, const float* __restrict__ residue,
+                           float* __restrict__ out) {
+	const uint64_t r = (uint64_t) blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+	if(r >= n_rows) return;
+	const int lane = threadIdx.x & 31;
+	const FeatRow row = rows[r];
+	const FeatFloor& F = floors[row.floor];
+	float* o = out + r * dim;
+	for(uint32_t c = lane; c < dim; c += 32) {
+		float v = 0.f;
+		if(kind <= 1) {
+			if(c == 0) v = F.tag;
+			else if(c - 1 < F.n_posts) {
+				const uint32_t i = c - 1;
+				const float y = kind == 0 ? __fmul_rn((float) final_ys[row.src * POV_MAX_POSTS + i], (float) F.multiplier)
+				                          : (float) floor[row.src + F.xs[i]];
+				v = __fdiv_rn(__fsub_rn(y, 127.5f), 127.5f);
+			}
+		} else if(c < F.n_posts) {
+			const uint32_t x = min((uint32_t) F.xs[c], row.n / 2 - 1);
+			v = residue[row.src + x];
+			if(kind == 3 && row.base != ~0ull) {
+				const uint32_t xb = min((uint32_t) F.xs[c], row.base_n - 1);
+				const float fb = __fdiv_rn((float) floor[row.base + xb], 255.0f);
+				v = __fmul_rn(v, expf(__fsub_rn(fb, 1.0f)));
+			}
+		}
+		o[c] = v;
+	}
+}
+
+cudaError_t launch_features(int kind, const FeatRow* rows, uint64_t n_rows, const FeatFloor* floors, uint32_t output_dim,
+                            const uint32_t* final_ys, const uint16_t* floor, const float* residue, float* out, cudaStream_t st, uint64_t* launches) {
+	if(n_rows == 0) return cudaSuccess;
+	k_features<<<(unsigned) ((n_rows + 7) / 8), 256, 0, st>>>(kind, rows, n_rows, floors, output_dim, final_ys, floor, residue, out);
+	if(launches) ++*launches;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_mdct_backward(const DevSetup*, uint32_t n, uint64_t count, const float* in, float* out,
                                  const float2* rot, const float2* fft, cudaStream_t st, uint64_t* launches) {
 	if(count == 0) return cudaSuccess;

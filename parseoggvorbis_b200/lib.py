@@ -22,7 +22,7 @@ SYMBOLS = [
     "pov_abi_version", "pov_inverse_db_table", "pov_window", "pov_ctx_create", "pov_ctx_destroy", "pov_last_error", "pov_ctx_stream",
     "pov_ctx_launch_count", "pov_ctx_io_bytes", "pov_ctx_set_device_entropy", "pov_ogg_parse_memory_ex", "pov_setup_register", "pov_setup_entry_bits", "pov_setup_get_window",
     "pov_batch_upload", "pov_batch_run", "pov_batch_kernel_name", "pov_batch_run_staged", "pov_batch_fetch_pcm", "pov_batch_pcm_dev",
-    "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_mdct_backward_batch",
+    "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_batch_features", "pov_mdct_backward_batch",
     "pov_ogg_vorbis_decode_memory", "pov_decoded_free", "pov_decode_corpus", "pov_decode_corpus_pcm", "pov_ogg_vorbis_full_read_from_memory",
     "pov_ogg_parse_memory", "pov_parsed_stream_count", "pov_parsed_get", "pov_parsed_free",
 ]
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
     L.pov_batch_sync.argtypes = [vp, vp]
     L.pov_batch_free.argtypes = [vp, vp]
     L.pov_batch_free.restype = None
+    L.pov_batch_features.argtypes = [vp, vp, u32, i32, u32, C.POINTER(C.c_float), u64, C.POINTER(u64)]
     L.pov_mdct_backward_batch.argtypes = [vp, u32, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.pov_ogg_vorbis_decode_memory.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.POINTER(abi.pov_decoded)]
     L.pov_decoded_free.argtypes = [C.POINTER(abi.pov_decoded)]
@@ -283,6 +284,36 @@ class SynthContext:
             return pcm, int(d.sample_rate), int(d.audio_packets)
         finally:
             self.L.pov_decoded_free(C.byref(d))
+
+    FEATURE_KINDS = {"floor_final_ys": 0, "floor_final_ys_rendered": 1, "residue_ys": 2, "residue_ys_with_floor": 3}
+
+    def features_from_raw_bytes(self, raw_bytes: bytes, output_dim: int, kind: str = "floor_final_ys", raw_packets: bool = True):
+        """The device-side counterpart of returnn_import.ParseOggVorbisLib.get_features_from_raw_bytes (reference:
+        returnn_import.py:74-115), default reader arguments: a (time, output_dim) float32 matrix for the first logical
+        stream of an Ogg/Vorbis file. Only the matrix comes back from the device."""
+        po = ParsedOgg(raw_bytes, raw_packets=raw_packets)
+        try:
+            s, b = po.get(0)
+            sid = C.c_uint32(0)
+            self._check(self.L.pov_setup_register(self.ctx, C.byref(s), C.byref(sid)))
+            st = abi.pov_stream.from_address(C.addressof(b.streams.contents))
+            st.setup_id = sid.value
+            h = C.c_void_p(None)
+            try:
+                self._check(self.L.pov_batch_upload(self.ctx, C.byref(b), C.byref(h)))
+                rows = C.c_uint64(0)
+                k = self.FEATURE_KINDS[kind]
+                self._check(self.L.pov_batch_features(self.ctx, h, 0, k, output_dim, None, 0, C.byref(rows)))
+                out = np.zeros((int(rows.value), output_dim), np.float32)
+                self._check(self.L.pov_batch_features(self.ctx, h, 0, k, output_dim, out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                      rows.value, C.byref(rows)))
+                return out
+            finally:
+                st.setup_id = 0
+                if h:
+                    self.L.pov_batch_free(self.ctx, h)
+        finally:
+            po.close()
 
     def decode_corpus(self, files, host_threads: int = 0):
         """files: list of bytes. Returns (frames per file, total PCM values, checksum)."""

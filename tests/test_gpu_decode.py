@@ -242,3 +242,27 @@ def test_device_entropy_decode_is_bit_exact(ctx, golden, name):
     assert np.array_equal(pcm_host, pcm_auto)
     assert np.array_equal(pcm_dev.reshape(pcm_host.shape), pcm_host)
     assert np.abs(pcm_auto - g["pcm"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["stereo44khz", "mono44khz", "synth_two_submaps", "synth_surround51"])
+@pytest.mark.parametrize("raw_packets", [True, False])
+def test_feature_matrices_match_the_reference_readers(ctx, name, raw_packets):
+    """f3: the (frames, dim) matrices the reference builds in Python from a debug dump (returnn_import.py:74-115,
+    demo_live_extract.py:262-505), produced on the device. Goldens: the reference's own readers on the reference
+    decoder's dump (tests/golden/make_feature_golden.py). Kinds without exp() are bit exact."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "features.npz"))
+    data = _load(name)
+    checked = 0
+    for key in gold.files:
+        fx, kind, dim = key.split("/")
+        if fx != name:
+            continue
+        ref = gold[key]
+        got = ctx.features_from_raw_bytes(data, int(dim), kind, raw_packets=raw_packets)
+        assert got.shape == ref.shape, (key, got.shape, ref.shape)
+        if kind == "residue_ys_with_floor":
+            assert np.allclose(got, ref, rtol=2e-6, atol=1e-9), (key, float(np.abs(got - ref).max()))
+        else:
+            assert np.array_equal(got, ref), (key, float(np.abs(got - ref).max()))
+        checked += 1
+    assert checked >= 10
