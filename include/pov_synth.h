@@ -213,6 +213,9 @@ uint64_t    pov_ctx_launch_count(const pov_ctx* ctx);
 /* Whole-file and corpus decode hand the audio packets to the device as they are (entropy decode in k_packet_decode) when
  * `on` is non-zero — the default; environment POV_DEVICE_ENTROPY=0 turns it off — and walk them on the host otherwise. */
 void        pov_ctx_set_device_entropy(pov_ctx* ctx, int on);
+/* Whole-file and corpus decode accept packets spanning pages when `on` is non-zero (default off = the reference's hpp:89;
+ * environment POV_ALLOW_SPANNING=1 turns it on). */
+void        pov_ctx_set_page_spanning(pov_ctx* ctx, int on);
 /* Bytes this context has copied host -> device and device -> host so far (descriptor/payload arenas, PCM, status words). */
 void        pov_ctx_io_bytes(const pov_ctx* ctx, uint64_t* h2d_out, uint64_t* d2h_out);
 
@@ -314,6 +317,9 @@ int      pov_ogg_parse_memory(const uint8_t* data, size_t len, pov_parsed** out,
 /* flags: POV_PARSE_RAW_PACKETS — do not entropy-decode the audio packets; the batches are POV_INPUT_PACKETS (a stream whose
  * setup cannot be walked on the device — floor0, a submap without channels — still comes back as POV_INPUT_ENTRIES). */
 #define POV_PARSE_RAW_PACKETS 1u
+/*        POV_PARSE_ALLOW_SPANNING — accept packets that continue on the next page of their stream (RFC 3533). The reference
+ * refuses such files (hpp:89: "we don't support packets spanning pages"), which stays the default for parity. */
+#define POV_PARSE_ALLOW_SPANNING 2u
 int      pov_ogg_parse_memory_ex(const uint8_t* data, size_t len, uint32_t flags, pov_parsed** out, const char** error_out);
 uint32_t pov_parsed_stream_count(const pov_parsed* p);
 int      pov_parsed_get(const pov_parsed* p, uint32_t stream, pov_setup* setup_out, pov_batch* batch_out);

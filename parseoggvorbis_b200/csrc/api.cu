@@ -113,6 +113,7 @@ extern "C" int pov_ctx_create(int device, pov_ctx** out, const char** error_out)
 	if((e = cudaMalloc((void**) &ctx->d_counter, 256)) != cudaSuccess) return fail("cudaMalloc work counter", e);
 	if(const char* k = getenv("POV_KERNEL")) ctx->kernel_choice = !strcmp(k, "fused") ? 1 : !strcmp(k, "warp") ? 2 : 0;
 	if(const char* de = getenv("POV_DEVICE_ENTROPY")) ctx->device_entropy = atoi(de) != 0;
+	if(const char* sp = getenv("POV_ALLOW_SPANNING")) ctx->allow_spanning = atoi(sp) != 0;
 	const char* rl = getenv("POV_RUN_LEN");
 	ctx->run_len = rl ? (uint32_t) std::min(64, std::max(2, atoi(rl))) : 0;   // the fused kernel keeps <= 65 descriptors per run
 	ctx->err[0] = 0;
@@ -145,6 +146,7 @@ extern "C" const char* pov_last_error(const pov_ctx* ctx) { return ctx ? ctx->er
 extern "C" void* pov_ctx_stream(pov_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
 extern "C" uint64_t pov_ctx_launch_count(const pov_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void pov_ctx_set_device_entropy(pov_ctx* ctx, int on) { if(ctx) ctx->device_entropy = on != 0; }
+extern "C" void pov_ctx_set_page_spanning(pov_ctx* ctx, int on) { if(ctx) ctx->allow_spanning = on != 0; }
 extern "C" void pov_ctx_io_bytes(const pov_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
 	if(h2d) *h2d = ctx ? ctx->h2d_bytes : 0;
 	if(d2h) *d2h = ctx ? ctx->d2h_bytes : 0;

@@ -70,6 +70,7 @@ struct pov_ctx {
 	uint64_t h2d_bytes = 0, d2h_bytes = 0;   // what this context copied between host and device (pov_ctx_io_bytes)
 	uint32_t run_len = 0;         // 0 = automatic
 	int kernel_choice = 0;        // POV_KERNEL: 0 automatic, 1 force the CTA-per-run fused kernel, 2 require the warp kernel
+	bool allow_spanning = false;  // accept packets that span pages (the reference refuses them, hpp:89)
 	bool device_entropy = true;   // whole-file / corpus decode: audio packets are entropy-decoded on the device (POV_DEVICE_ENTROPY=0: on the host)
 	uint32_t* d_counter = nullptr; // work counter of the persistent kernel
 	const float* d_inv_db = nullptr;

@@ -67,6 +67,7 @@ extern "C" int pov_ogg_parse_memory_ex(const uint8_t* data, size_t len, uint32_t
 	ParseError err;
 	ParseOptions opt;
 	opt.raw_packets = (flags & POV_PARSE_RAW_PACKETS) != 0;
+	opt.allow_spanning = (flags & POV_PARSE_ALLOW_SPANNING) != 0;
 	if(!parse_ogg_file(data, len, P->streams, err, opt)) {
 		snprintf(errbuf, sizeof errbuf, "check failed: %s", err.msg.c_str());
 		if(error_out) *error_out = errbuf;
@@ -174,6 +175,7 @@ extern "C" int pov_ogg_vorbis_decode_memory(pov_ctx* ctx, const uint8_t* data, s
 	// host-side Y lists, so that path keeps the host walk. A file whose streams cannot all be walked on the device is parsed again.
 	ParseOptions opt;
 	opt.raw_packets = ctx->device_entropy && !debug_out;
+	opt.allow_spanning = ctx->allow_spanning;
 	for(int attempt = 0; attempt < 2; ++attempt) {
 		streams.clear();
 		err = ParseError();
@@ -416,6 +418,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 			hb.clear();
 			ParseOptions opt;
 			opt.raw_packets = ctx->device_entropy;
+			opt.allow_spanning = ctx->allow_spanning;
 			try {                  // a worker never lets an exception escape its thread: the chunk carries the error instead
 			for(int attempt = 0; attempt < 2; ++attempt) {       // (second round only if a stream cannot be walked on the device)
 			bool mixed = false;

@@ -695,7 +695,8 @@ static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<
 		const uint8_t* seg = h + 27;
 		uint32_t body = 0;
 		for(uint32_t i = 0; i < nseg; ++i) body += seg[i];
-		if(nseg) REQUIRE(seg[nseg - 1] != 255, "page: packets spanning pages are not supported (hpp:89)");
+		const bool spans_out = nseg && seg[nseg - 1] == 255;
+		if(!opt.allow_spanning) REQUIRE(!spans_out, "page: packets spanning pages are not supported (hpp:89)");
 		REQUIRE(len - pos - 27 - nseg >= body, "page: truncated body (hpp:90)");
 		const uint8_t* payload = seg + nseg;
 		{
@@ -715,45 +716,59 @@ static bool parse_ogg_file_checked(const uint8_t* data, size_t len, std::vector<
 		}
 		REQUIRE(live.count(serial), "page: unknown stream serial (hpp:1439)");
 		StreamWork& st = streams[live[serial]];
+		if(opt.allow_spanning) {
+			// a page either continues the packet its predecessor left open, or it does not (RFC 3533 section 6, header_type bit 0)
+			REQUIRE(((flags & 1) != 0) == !st.pending.empty(), "page: continuation flag does not match the previous page of the stream");
+		}
+		// the granule position belongs to the last packet that ENDS on this page (hpp:1456-1459; RFC 3533: -1 if none does)
+		int last_end = -1;
+		for(uint32_t i = 0; i < nseg; ++i) if(seg[i] != 255) last_end = (int) i;
 		size_t off = 0;
 		uint32_t plen = 0;
 		for(uint32_t i = 0; i < nseg; ++i) {
 			plen += seg[i];
 			if(seg[i] == 255) continue;
 			const uint8_t* pp = payload + off;
-			const int64_t expected = (i == nseg - 1) ? granule : -1;     // hpp:1456-1459
+			size_t pbytes = plen;
+			if(!st.pending.empty()) {                        // the tail of a packet begun on an earlier page
+				st.pending.insert(st.pending.end(), pp, pp + plen);
+				pp = st.pending.data(); pbytes = st.pending.size();
+			}
+			const int64_t expected = ((int) i == last_end) ? granule : -1;
 			if(st.packets_seen == 0) {
-				if(!parse_id_packet(pp, plen, st.setup, fail)) return false;
+				if(!parse_id_packet(pp, pbytes, st.setup, fail)) return false;
 				st.have_id = true;
-				st.setup_key.assign((const char*) pp, plen);
+				st.setup_key.assign((const char*) pp, pbytes);
 			} else if(st.packets_seen == 1) {
-				if(!check_comment_packet(pp, plen, fail)) return false;
+				if(!check_comment_packet(pp, pbytes, fail)) return false;
 				st.have_comment = true;
 			} else if(st.packets_seen == 2) {
 				// A corpus usually repeats a handful of setups: reuse the last one parsed by this thread when the raw
 				// header bytes are identical (codebook + VQ table construction is the expensive part of a short file).
 				static thread_local std::string cached_key;
 				static thread_local VorbisSetup cached_setup;
-				st.setup_key.append((const char*) pp, plen);
+				st.setup_key.append((const char*) pp, pbytes);
 				if(st.setup_key == cached_key) {
 					st.setup = cached_setup;
 				} else {
-					if(!parse_setup_packet(pp, plen, st.setup, fail)) return false;
+					if(!parse_setup_packet(pp, pbytes, st.setup, fail)) return false;
 					cached_key = st.setup_key;
 					cached_setup = st.setup;
 				}
 				st.have_setup = true;
 				st.raw = opt.raw_packets && setup_supports_device_entropy(st.setup);
 			} else {
-				if(!decode_audio_packet(st, pp, plen, expected, fail, opt)) {
+				if(!decode_audio_packet(st, pp, pbytes, expected, fail, opt)) {
 					err.msg = "audio packet " + std::to_string(st.packets.size()) + ": " + err.msg;
 					return false;
 				}
 			}
 			++st.packets_seen;
+			st.pending.clear();
 			off += plen;
 			plen = 0;
 		}
+		if(plen) st.pending.insert(st.pending.end(), payload + off, payload + off + plen);      // (only with allow_spanning)
 		if(flags & 4) { st.ended = true; live.erase(serial); }          // hpp:1478-1481
 		pos += 27 + nseg + body;
 	}

@@ -93,6 +93,7 @@ struct StreamWork {
 	uint32_t serial = 0;
 	VorbisSetup setup;
 	bool have_id = false, have_comment = false, have_setup = false, ended = false;
+	std::vector<uint8_t> pending;             // allow_spanning: the bytes so far of a packet that continues on the next page
 	bool raw = false;                         // the payload holds raw audio packets (POV_INPUT_PACKETS), not entry numbers
 	std::string setup_key;                    // raw id + setup packet bytes: identical keys <=> identical setups
 	uint32_t packets_seen = 0;
@@ -112,7 +113,10 @@ struct ParseError { bool failed = false; std::string msg; };
 
 // raw_packets: audio packets are not entropy-decoded here; the descriptors carry the packet bytes (POV_INPUT_PACKETS:
 // mode, window flags and the emit bookkeeping only need the first bits of a packet) and the device walks the rest.
-struct ParseOptions { bool raw_packets = false; };
+// allow_spanning: packets may continue on the next page of their stream (RFC 3533 lacing value 255 at a page end +
+// "continued" flag). The reference refuses such files (hpp:89) and so does the default here; real-world encoders produce
+// them routinely (setup headers above 4 KB, high bit rates).
+struct ParseOptions { bool raw_packets = false; bool allow_spanning = false; };
 
 // Parses a whole Ogg file from memory (hpp:1428 full_read_from_memory). Streams appear in order of their BOS page.
 // Returns false and fills err on the first failing check, like the reference's OkOrError chain.

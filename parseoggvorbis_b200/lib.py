@@ -20,7 +20,7 @@ _LIB: Optional[C.CDLL] = None
 # every symbol include/pov_synth.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [
     "pov_abi_version", "pov_inverse_db_table", "pov_window", "pov_ctx_create", "pov_ctx_destroy", "pov_last_error", "pov_ctx_stream",
-    "pov_ctx_launch_count", "pov_ctx_io_bytes", "pov_ctx_set_device_entropy", "pov_ogg_parse_memory_ex", "pov_setup_register", "pov_setup_entry_bits", "pov_setup_get_window",
+    "pov_ctx_launch_count", "pov_ctx_io_bytes", "pov_ctx_set_device_entropy", "pov_ctx_set_page_spanning", "pov_ogg_parse_memory_ex", "pov_setup_register", "pov_setup_entry_bits", "pov_setup_get_window",
     "pov_batch_upload", "pov_batch_run", "pov_batch_kernel_name", "pov_batch_run_staged", "pov_batch_fetch_pcm", "pov_batch_pcm_dev",
     "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_batch_features", "pov_mdct_backward_batch",
     "pov_ogg_vorbis_decode_memory", "pov_decoded_free", "pov_decode_corpus", "pov_decode_corpus_pcm", "pov_ogg_vorbis_full_read_from_memory",
@@ -95,6 +95,8 @@ def load() -> C.CDLL:
     L.pov_ogg_parse_memory_ex.argtypes = [C.c_char_p, C.c_size_t, u32, C.POINTER(vp), C.POINTER(C.c_char_p)]
     L.pov_ctx_set_device_entropy.argtypes = [vp, i32]
     L.pov_ctx_set_device_entropy.restype = None
+    L.pov_ctx_set_page_spanning.argtypes = [vp, i32]
+    L.pov_ctx_set_page_spanning.restype = None
     L.pov_parsed_stream_count.argtypes = [vp]
     L.pov_parsed_stream_count.restype = u32
     L.pov_parsed_get.argtypes = [vp, u32, C.POINTER(abi.pov_setup), C.POINTER(abi.pov_batch)]
@@ -107,13 +109,14 @@ def load() -> C.CDLL:
 class ParsedOgg:
     """Host-only parse of one Ogg/Vorbis file into descriptor batches (no GPU involved)."""
 
-    def __init__(self, data: bytes, raw_packets: bool = False):
-        """raw_packets: leave the audio packets as they are (POV_INPUT_PACKETS batches: entropy decode on the device)."""
+    def __init__(self, data: bytes, raw_packets: bool = False, allow_spanning: bool = False):
+        """raw_packets: leave the audio packets as they are (POV_INPUT_PACKETS batches: entropy decode on the device).
+        allow_spanning: accept packets that continue on the next page (the reference refuses them, hpp:89)."""
         self.L = load()
         self.h = C.c_void_p(None)
         self._data = data
         err = C.c_char_p(None)
-        rc = self.L.pov_ogg_parse_memory_ex(data, len(data), 1 if raw_packets else 0, C.byref(self.h), C.byref(err))
+        rc = self.L.pov_ogg_parse_memory_ex(data, len(data), (1 if raw_packets else 0) | (2 if allow_spanning else 0), C.byref(self.h), C.byref(err))
         if rc != 0:
             raise PovError(rc, (err.value or b"?").decode())
 
@@ -193,6 +196,9 @@ class SynthContext:
     @property
     def launch_count(self) -> int:
         return int(self.L.pov_ctx_launch_count(self.ctx))
+
+    def set_page_spanning(self, on: bool):
+        self.L.pov_ctx_set_page_spanning(self.ctx, 1 if on else 0)
 
     def set_device_entropy(self, on: bool):
         self.L.pov_ctx_set_device_entropy(self.ctx, 1 if on else 0)

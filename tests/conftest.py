@@ -10,7 +10,8 @@ if ROOT not in sys.path:
 
 # written by tools/vorbis_writer.py and decoded by the unmodified reference (tests/golden/make_synthetic_golden.py);
 # "shared_submap" is decoded by the hook-patched libvorbis instead (the reference is off-spec there, hpp:755)
-SYNTHETIC = ("synth_res0_mono", "synth_two_submaps", "synth_surround51", "synth_codebooks", "synth_shared_submap")
+SYNTHETIC = ("synth_res0_mono", "synth_two_submaps", "synth_surround51", "synth_codebooks", "synth_shared_submap",
+             "synth_residue_edges")
 
 
 def pytest_configure(config):

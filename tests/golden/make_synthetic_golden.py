@@ -229,12 +229,47 @@ def scen_shared_submap(rng):
     return s, stream_packets(rng, s, block_pattern(rng, 30), {0: [0], 1: [1]}), 0
 
 
+def scen_residue_edges(rng):
+    """Mono: residue `end` beyond the decode length on both block sizes (hpp:697-698 clamps), `begin` beyond it on the short
+    one (nothing to read, hpp:704-705), a one-partition residue, multiplier 3 and 1."""
+    books = []
+    f0 = make_floor(rng, books, workloads.FIXTURE_XS_SHORT, 3, True)
+    f1 = make_floor(rng, books, workloads.FIXTURE_XS_LONG, 1, False)
+    vq = [len(books) + i for i in range(2)]
+    books += [vq_book(rng, 2, 5), vq_book(rng, 4, 3)]
+    r0 = make_residue(rng, books, 1, 200, 5000, 16, 3, vq)       # begin 200 > 128 = n/2: empty
+    r1 = make_residue(rng, books, 0, 0, 5000, 1024, 3, vq)       # end 5000 > 1024: one partition of 1024
+    s = vw.StreamSetup(1, 8000, (256, 2048), books, [f0, f1], [r0, r1],
+                       [vw.Mapping([0], [0], [0]), vw.Mapping([0], [1], [1])], [vw.Mode(0, 0), vw.Mode(1, 1)])
+    return s, stream_packets(rng, s, block_pattern(rng, 20), {0: [0], 1: [1]}), 40
+
+
+def scen_bad_vq_book(rng):
+    """A residue class points at a scalar (lookup type 0) codebook: the reference fails its decodeVector CHECK
+    (hpp:369-370 via :739/:748) on the first packet that uses the class. Both decoders must refuse the file."""
+    books = []
+    f0 = make_floor(rng, books, workloads.FIXTURE_XS_SHORT, 4, False)
+    f1 = make_floor(rng, books, workloads.FIXTURE_XS_LONG, 2, False)
+    good = len(books)
+    books.append(vq_book(rng, 2, 5))
+    bad = len(books)
+    books.append(vw.Book(2, vw.full_tree_lengths(25, rng)))      # lookup type 0, same geometry
+    classbook = len(books)
+    books.append(vw.Book(2, vw.full_tree_lengths(9, rng)))
+    r = vw.Residue(1, 0, 512, 32, classbook, [[-1] * 8, [good] + [-1] * 7, [-1, bad] + [-1] * 6])
+    s = vw.StreamSetup(1, 44100, (256, 2048), books, [f0, f1], [r],
+                       [vw.Mapping([0], [0], [0]), vw.Mapping([0], [1], [0])], [vw.Mode(0, 0), vw.Mode(1, 1)])
+    return s, stream_packets(rng, s, block_pattern(rng, 8), {0: [0], 1: [1]}, dense=0.9), 0
+
+
 SCENARIOS = {
     "res0_mono": (scen_res0_mono, 11, "reference"),
     "two_submaps": (scen_two_submaps, 12, "reference"),
     "surround51": (scen_surround51, 13, "reference"),
     "codebooks": (scen_codebooks, 14, "reference"),
     "shared_submap": (scen_shared_submap, 15, "libvorbis"),
+    "residue_edges": (scen_residue_edges, 16, "reference"),
+    "bad_vq_book": (scen_bad_vq_book, 17, "reference-fails"),
 }
 
 
@@ -257,6 +292,11 @@ def main():
             with open(ogg, "wb") as f:
                 f.write(data)
             dbg = os.path.join(tmp, name + ".dbg")
+            if decoder == "reference-fails":
+                r = subprocess.run([OURS, "--in", ogg, "--debug_out", dbg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                assert r.returncode != 0 and "check failed" in r.stdout, (r.returncode, r.stdout[-300:])
+                print("%-14s the reference refuses it: %s" % (name, r.stdout.strip().splitlines()[-1][:120]))
+                continue
             if decoder == "reference":
                 subprocess.check_call([OURS, "--in", ogg, "--debug_out", dbg], stdout=subprocess.DEVNULL)
             else:

@@ -143,3 +143,48 @@ def test_crc_known_answer():
         for _ in range(8):
             crc = ((crc << 1) ^ 0x04C11DB7) & 0xFFFFFFFF if crc & 0x80000000 else (crc << 1) & 0xFFFFFFFF
     assert crc == stored
+
+
+def test_scalar_book_used_as_vq_book_is_refused_like_the_reference():
+    """synth_bad_vq_book.ogg: a residue class points at a lookup-type-0 codebook; the reference's decodeVector CHECK fails
+    (hpp:369-370, 748 — verified when the fixture was generated). The host walk must refuse the file the same way."""
+    with open(os.path.join(ROOT, "tests", "golden", "synth_bad_vq_book.ogg"), "rb") as f:
+        data = f.read()
+    _expect_error(data, "invalid VQ entry")
+
+
+def _spanning_twin(name):
+    """The synthetic stream `name` muxed with packets continuing across pages (tools/vorbis_writer.write_stream_spanning)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_synthetic_golden as msg
+    import vorbis_writer as vw
+    fn, seed, _ = msg.SCENARIOS[name]
+    s, packets, trim = fn(np.random.default_rng(seed))
+    plain = vw.write_stream(s, packets, serial=0x5000 + seed, packets_per_page=6, trim_last=trim)
+    with open(os.path.join(ROOT, "tests", "golden", "synth_%s.ogg" % name), "rb") as f:
+        assert f.read() == plain, "the committed fixture is what the generator writes"
+    return vw.write_stream_spanning(s, packets, serial=0x5000 + seed, segments_per_page=5, trim_last=trim)
+
+
+@pytest.mark.parametrize("name", ["two_submaps", "codebooks"])
+def test_packets_spanning_pages(golden, name):
+    """f4 (hpp:89): refused by default, like the reference; with POV_PARSE_ALLOW_SPANNING the same packets muxed across page
+    boundaries decode to exactly what the reference decodes from the non-spanning file."""
+    data = _spanning_twin(name)
+    _expect_error(data, "spanning pages")
+    g = golden["synth_" + name]
+    po = lib.ParsedOgg(data, allow_spanning=True)
+    s, b = po.get(0)
+    assert b.n_packets == len(g["blocksize"])
+    pcm, status, cap = ob.synth_batch_raw(s, b, imdct="reference" if ob.reference_lib() is not None else "fast", capture=True)
+    assert not status.any()
+    out = pcm.reshape(int(g["channels"]), -1)
+    assert out.shape == g["pcm"].shape and np.abs(out - g["pcm"]).max() <= 1e-5
+    oh = 0
+    for p, n in enumerate(g["blocksize"]):
+        for c in range(int(g["channels"])):
+            assert np.array_equal(cap["after_residue"][p, c, :int(n) // 2], g["after_residue"][oh:oh + int(n) // 2]), (p, c)
+            oh += int(n) // 2
+    po.close()

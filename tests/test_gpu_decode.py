@@ -266,3 +266,37 @@ def test_feature_matrices_match_the_reference_readers(ctx, name, raw_packets):
             assert np.array_equal(got, ref), (key, float(np.abs(got - ref).max()))
         checked += 1
     assert checked >= 10
+
+
+@pytest.mark.parametrize("device_entropy", [True, False])
+def test_scalar_book_used_as_vq_book_fails_on_the_device_too(ctx, device_entropy):
+    """The same file through the whole-file decode: with the entropy decode on the device the packet is flagged
+    POV_PKT_VQ_ENTRY by the kernels and the decode fails with the reference's check (hpp:739,748)."""
+    with open(os.path.join(ROOT, "tests", "golden", "synth_bad_vq_book.ogg"), "rb") as f:
+        data = f.read()
+    ctx.set_device_entropy(device_entropy)
+    try:
+        with pytest.raises(lib.PovError) as ei:
+            ctx.decode_ogg(data)
+    finally:
+        ctx.set_device_entropy(True)
+    assert ei.value.code == abi.POV_ERR_STREAM and "check failed" in ei.value.msg
+
+
+def test_packets_spanning_pages_on_the_device(ctx, golden):
+    """f4 end to end: a stream whose packets continue across pages, decoded with both entropy-decode modes."""
+    from tests.test_front_end_cpu import _spanning_twin
+    data = _spanning_twin("two_submaps")
+    g = golden["synth_two_submaps"]
+    with pytest.raises(lib.PovError):
+        ctx.decode_ogg(data)                       # default: refused like the reference (hpp:89)
+    ctx.set_page_spanning(True)
+    try:
+        for dev in (True, False):
+            ctx.set_device_entropy(dev)
+            pcm, _, npk = ctx.decode_ogg(data)
+            assert npk == len(g["blocksize"]) and pcm.shape == g["pcm"].shape
+            assert np.abs(pcm - g["pcm"]).max() <= 1e-5
+    finally:
+        ctx.set_page_spanning(False)
+        ctx.set_device_entropy(True)

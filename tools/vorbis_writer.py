@@ -522,3 +522,54 @@ def write_stream(s: StreamSetup, packets: Sequence[PacketChoice], serial: int = 
         out += ogg_page(group, serial, seq, gran, eos=last)
         seq += 1
     return bytes(out)
+
+
+def write_stream_spanning(s: StreamSetup, packets: Sequence[PacketChoice], serial: int = 0x1234, segments_per_page: int = 5,
+                          trim_last: int = 0) -> bytes:
+    """The same stream muxed the way real encoders do it (RFC 3533): the lacing values of all packets form one sequence
+    that is cut into pages of `segments_per_page` segments wherever the cut falls, so packets continue across pages
+    (header_type bit 0 on the continuing page). A page's granule position is the position after the last packet that ends
+    on it, -1 if none does. Header packets keep their own pages (Vorbis I A.2)."""
+    out = bytearray()
+    seq = 0
+
+    def emit(lacing, body, gran, cont, bos=False, eos=False):
+        nonlocal seq, out
+        hdr = bytearray(b"OggS\x00" + bytes([(1 if cont else 0) | (2 if bos else 0) | (4 if eos else 0)]) +
+                        struct.pack("<qIII", gran, serial, seq, 0) + bytes([len(lacing)]) + bytes(lacing))
+        crc = ogg_crc(bytes(hdr) + bytes(body))
+        hdr[22:26] = struct.pack("<I", crc)
+        out += bytes(hdr) + bytes(body)
+        seq += 1
+
+    def mux(pkts, grans, bos_first=False, eos_last=False):
+        """pkts: packet byte strings; grans[i]: granule position after packet i."""
+        lacing, body, cont, gran, first = [], bytearray(), False, -1, True
+        for i, p in enumerate(pkts):
+            segs = [255] * (len(p) // 255) + [len(p) % 255]
+            at = 0
+            for k, v in enumerate(segs):
+                lacing.append(v)
+                body += p[at:at + v]
+                at += v
+                if k == len(segs) - 1:
+                    gran = grans[i]
+                last_of_all = i == len(pkts) - 1 and k == len(segs) - 1
+                if len(lacing) == segments_per_page or last_of_all:
+                    emit(lacing, body, gran, cont, bos=bos_first and first, eos=eos_last and last_of_all)
+                    cont = (v == 255)
+                    lacing, body, gran, first = [], bytearray(), -1, False
+
+    mux([s.id_packet()], [0], bos_first=True)
+    mux([s.comment_packet()], [0])
+    mux([s.setup_packet()], [0])
+    datas = [write_audio_packet(s, pc) for pc in packets]
+    grans, total, prev_n = [], 0, 0
+    for i, pc in enumerate(packets):
+        n = s.blocksize[s.modes[pc.mode].blockflag]
+        if prev_n:
+            total += prev_n // 4 + n // 4
+        prev_n = n
+        grans.append(total - (trim_last if i == len(packets) - 1 else 0))
+    mux(datas, grans, eos_last=True)
+    return bytes(out)
