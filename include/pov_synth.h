@@ -270,6 +270,7 @@ void pov_batch_free(pov_ctx* ctx, pov_batch_handle* h);
  *   FLOOR_FINAL_YS_RENDERED  kind="floor_final_ys_rendered"
  *   RESIDUE_YS               kind="residue_ys"               rows of the packets whose (last channel's) floor has most posts
  *   RESIDUE_YS_WITH_FLOOR    kind="residue_ys_with_floor"    (exp() is the device's: within 1e-6 relative of numpy's) */
+#define POV_ALL_STREAMS 0xFFFFFFFFu   /* `stream`: the rows of every stream of the batch, one after the other (one setup) */
 enum { POV_FEAT_FLOOR_FINAL_YS = 0, POV_FEAT_FLOOR_FINAL_YS_RENDERED = 1, POV_FEAT_RESIDUE_YS = 2, POV_FEAT_RESIDUE_YS_WITH_FLOOR = 3 };
 int  pov_batch_features(pov_ctx* ctx, pov_batch_handle* h, uint32_t stream, int kind, uint32_t output_dim,
                         float* out, uint64_t rows_cap, uint64_t* rows_out);

@@ -1060,13 +1060,20 @@ extern "C" int pov_batch_features(pov_ctx* ctx, pov_batch_handle* h, uint32_t st
                                   float* out, uint64_t rows_cap, uint64_t* rows_out) try {
 	if(!ctx || !h || !rows_out) return POV_ERR_ARG;
 	if(kind < POV_FEAT_FLOOR_FINAL_YS || kind > POV_FEAT_RESIDUE_YS_WITH_FLOOR) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: unknown kind %d", kind);
-	if(stream >= h->n_streams) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: stream out of range");
+	const bool all_streams = stream == POV_ALL_STREAMS;
+	if(!all_streams && stream >= h->n_streams) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: stream out of range");
+	if(h->n_streams == 0) { *rows_out = 0; return POV_OK; }
+	if(all_streams) {
+		for(uint32_t i = 1; i < h->n_streams; ++i)
+			if(h->streams_host[i].setup_id != h->streams_host[0].setup_id)
+				return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: POV_ALL_STREAMS needs one setup for the whole batch");
+		stream = 0;
+	}
 	if(output_dim < 1 || output_dim > 4096) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: output_dim out of range");
 	cudaSetDevice(ctx->device);
 	int rc = POV_OK;
 	if(!h->staged_ready && (rc = pov_batch_run_staged(ctx, h)) != POV_OK) return rc;
-	const pov_stream& st = h->streams_host[stream];
-	const SetupRec& su = ctx->setups[st.setup_id];
+	const SetupRec& su = ctx->setups[h->streams_host[stream].setup_id];
 	const uint32_t C = su.channels, nf = (uint32_t) su.floors_host.size();
 	// which floors were decoded: the host's descriptors, or what k_packet_decode found in the packets
 	std::vector<uint16_t> used(h->pk_used);
@@ -1083,7 +1090,9 @@ extern "C" int pov_batch_features(pov_ctx* ctx, pov_batch_handle* h, uint32_t st
 		return pov_fail(ctx, POV_ERR_ARG, "pov_batch_features: output_dim %u < %u posts of the biggest floor (the reference asserts, demo_live_extract.py:486)",
 		                output_dim, su.floors_host[biggest].n_posts);
 	std::vector<FeatRow> rows;
-	uint64_t base = ~0ull;
+	for(uint32_t si = stream; si < (all_streams ? h->n_streams : stream + 1); ++si) {
+	const pov_stream& st = h->streams_host[si];
+	uint64_t base = ~0ull;                 // (the reader's floor_base starts as None for every file)
 	uint32_t base_n = 0;
 	for(uint32_t k = 0; k < st.n_packets; ++k) {
 		const uint32_t p = st.first_packet + k, n = h->pk_n[p];
@@ -1111,6 +1120,7 @@ extern "C" int pov_batch_features(pov_ctx* ctx, pov_batch_handle* h, uint32_t st
 				rows.push_back(r);
 			}
 		}
+	}
 	}
 	*rows_out = rows.size();
 	if(!out) return POV_OK;                                  // size query
