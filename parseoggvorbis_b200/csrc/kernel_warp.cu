@@ -728,14 +728,17 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 	const int off[4] = {o0, o1, o2, o3};
 	// (no hand-written register prefetch: with 20 warps per SM the loads of a whole iteration issued together hide
 	// their latency behind the other warps, and the 16 registers it would cost are what keeps the kernel spill free)
+	// this lane's first quad and its mirror, as pointers: a load is then one 32-bit offset and one wide multiply-add
+	const float* const lane_lo = base + 4 * u;
+	const float* const lane_hi = base + (M - 4 - 4 * u);
 #pragma unroll 1
 	for(int m = 0; m < 4; ++m) {
-		const int q = u + LPF * m;
+		const int q = u + LPF * m, d = 4 * LPF * m;
 		float4 lo[NL], hi[NL];
 #pragma unroll
 		for(int i = 0; i < NL; ++i) {
-			lo[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + 4 * q)));
-			hi[i] = __ldg(reinterpret_cast<const float4*>(base + (off[i] + M - 4 - 4 * q)));
+			lo[i] = __ldg(reinterpret_cast<const float4*>(lane_lo + (off[i] + d)));
+			hi[i] = __ldg(reinterpret_cast<const float4*>(lane_hi + (off[i] - d)));
 		}
 		// the floor evaluation needs none of the loaded values: it runs while the loads are in flight
 		const float4 fl = curve_quad(rec, tab, (uint32_t) (4 * q), invdb);
@@ -1138,7 +1141,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 						G.pr = prev_right; G.rbp = prev_n / 4 - prev_right / 2;
 						G.slL = (lc == N1 / 2) ? s_slope1 : s_slope0;
 						G.slR = (prev_right == N1 / 2) ? s_slope1 : s_slope0;
-						G.pperm = prev_perm; G.cperm = (kTm == 2) && flag && !kLongGrouped;
+						G.pperm = (kTm == 2) && prev_perm; G.cperm = (kTm == 2) && flag && !kLongGrouped;     // (compile-time false unless kTm == 2)
 						for(uint32_t j = (uint32_t) lane; j < emit; j += 32u) {
 							const float v = ola_one(G, prev_lo, cur_hi, (int) j);
 							dst[planar ? (size_t) j : (size_t) j * (size_t) C] = v;
