@@ -223,19 +223,23 @@ static void serialize_setup(const pov_setup* s, std::string& out) {
 // Compact tables of the warp-autonomous kernel. Returns false when the setup is outside what kernel_warp.cu handles
 // (those batches run on the CTA-per-run fused kernel instead).
 static bool build_fast_tables(const pov_setup* s, const std::vector<DevFloor>& floors, const std::vector<DevMapping>& maps,
-                              const uint32_t posts_cls[2], FastTables& ft, uint32_t& short_cap) {
+                              const uint32_t posts_cls[2], FastTables& ft, uint32_t& short_cap, uint32_t& long_cap, bool& wide) {
 	memset(&ft, 0, sizeof ft);
 	if(!warp_kernel_supports(s->blocksize[0], s->blocksize[1])) return false;
 	if(s->channels > POV_MAX_CHANNELS || s->n_floors > POV_FAST_MAX_FLOORS || s->n_mappings > POV_FAST_MAX_MAPPINGS) return false;
-	if(posts_cls[0] > 32 || posts_cls[1] > 32) return false;
+	if(posts_cls[0] > POV_FAST_MAX_POSTS || posts_cls[1] > POV_FAST_MAX_POSTS) return false;
 	short_cap = (posts_cls[0] + 3u) & ~3u;
 	if(short_cap < 4) short_cap = 4;
+	wide = posts_cls[0] > 32 || posts_cls[1] > 32;
+	long_cap = wide ? 64u : 32u;             // (the wide kernel keeps 64 records per long curve whichever class has the big floor)
 	ft.channels = s->channels;
 	ft.short_posts_cap = short_cap;
+	ft.long_posts_cap = long_cap;
+	ft.wide = wide ? 1u : 0u;
 	for(uint32_t i = 0; i < s->n_floors; ++i) {
 		const DevFloor& f = floors[i];
 		FastFloor& o = ft.floors[i];
-		if(f.n_posts > 32) {            // only reachable floors matter, but an unreachable big floor is not worth a special case
+		if(f.n_posts > POV_FAST_MAX_POSTS) {            // only reachable floors matter, but an unreachable big floor is not worth a special case
 			bool used = false;
 			for(uint32_t m = 0; m < s->n_mappings && !used; ++m)
 				for(uint32_t c = 0; c < s->channels; ++c) if(maps[m].floor_of_ch[c] == i) used = true;
@@ -286,7 +290,7 @@ static bool build_fast_tables(const pov_setup* s, const std::vector<DevFloor>& f
 		}
 	}
 	for(uint32_t i = 0; i < s->n_modes; ++i) { ft.mode_flag[i] = s->modes[i].blockflag ? 1 : 0; ft.mode_map[i] = s->modes[i].mapping; }
-	return warp_kernel_smem_bytes(s->blocksize[0], s->blocksize[1], short_cap, nullptr, nullptr, nullptr) <= 227 * 1024;
+	return warp_kernel_smem_bytes(s->blocksize[0], s->blocksize[1], short_cap, long_cap, nullptr, nullptr, nullptr) <= 227 * 1024;
 }
 
 extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id_out) try {
@@ -439,7 +443,7 @@ extern "C" int pov_setup_register(pov_ctx* ctx, const pov_setup* s, uint32_t* id
 	d.floors = rec.d_floors; d.mappings = rec.d_mappings; d.residues = rec.d_residues; d.codebooks = rec.d_codebooks;
 	{
 		FastTables ft;
-		rec.fast_ok = build_fast_tables(s, floors, maps, rec.posts_cls, ft, rec.fast_short_cap);
+		rec.fast_ok = build_fast_tables(s, floors, maps, rec.posts_cls, ft, rec.fast_short_cap, rec.fast_long_cap, rec.fast_wide);
 		rec.fast_max_nl = 1;
 		for(uint32_t m = 0; m < s->n_mappings && m < POV_FAST_MAX_MAPPINGS; ++m)
 			for(uint32_t c = 0; c < s->channels; ++c) rec.fast_max_nl = std::max<uint32_t>(rec.fast_max_nl, ft.couple[m][c].nl);
@@ -644,15 +648,17 @@ extern "C" int pov_batch_upload(pov_ctx* ctx, const pov_batch* b, pov_batch_hand
 	}
 	h->warp_ok = warp_ok;
 	h->warp_setup = warp_ok ? b->streams[0].setup_id : 0;
+	bool any_wide = false;               // a stream whose floors have 33..64 posts: its runs hold at most 15 packets + halo
+	for(uint32_t si = 0; si < b->n_streams && warp_ok; ++si) any_wide |= ctx->setups[b->streams[si].setup_id].fast_wide;
 	// enough work for several items per warp: worth ordering the items so that the short ones come last
-	const bool balance_tail = warp_ok && (uint64_t) P * ctx->setups[h->warp_setup].channels >= (uint64_t) ctx->sm_count * warp_kernel_warps() * warp_kernel_max_run() * 4;
+	const bool balance_tail = warp_ok && (uint64_t) P * ctx->setups[h->warp_setup].channels >= (uint64_t) ctx->sm_count * warp_kernel_warps() * warp_kernel_max_run(any_wide) * 4;
 	uint32_t run_len = ctx->run_len;
 	if(warp_ok) {
 		// work items = runs x channels, taken dynamically by sm_count*16 warps: aim for >= 8 items per warp, keep the
 		// halo overhead (one re-transformed packet per run) small; a run holds <= 32 packet descriptors, halo included
 		const uint64_t C = ctx->setups[h->warp_setup].channels;
 		const uint64_t want_items = (uint64_t) ctx->sm_count * warp_kernel_warps() * 8;
-		const uint64_t max_run = warp_kernel_max_run();
+		const uint64_t max_run = warp_kernel_max_run(any_wide);
 		const uint64_t auto_len = std::min<uint64_t>(max_run, std::max<uint64_t>(8, (uint64_t) P * C / want_items));
 		run_len = run_len ? std::min<uint32_t>(run_len, (uint32_t) max_run) : (uint32_t) auto_len;
 	} else if(run_len == 0) {
@@ -931,7 +937,7 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) try {
 		for(const WarpGroup& g : h->warp_groups) {      // one persistent launch per setup (its tables live in shared memory)
 			const SetupRec& su = ctx->setups[g.setup];
 			CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr + g.first_run, g.n_runs, su.channels, su.d_fast, su.blocksize[0], su.blocksize[1],
-			                          su.fast_short_cap, su.fast_max_nl, su.dev.slope, su.dev.rot, su.dev.fft8, su.dev.fftp,
+			                          su.fast_short_cap, su.fast_long_cap, su.fast_max_nl, su.dev.slope, su.dev.rot, su.dev.fft8, su.dev.fftp,
 			                          ctx->blk_tables.count(2048) ? ctx->blk_tables[2048].d_tm : nullptr, ctx->d_counter, ctx->sm_count, ctx->stream,
 			                          &ctx->launches));
 		}

@@ -49,7 +49,8 @@ struct SetupRec {
 	const float* d_vq = nullptr;
 	// warp-autonomous kernel (kernel_warp.cu): eligible setups carry their compact tables
 	bool fast_ok = false;
-	uint32_t fast_short_cap = 4;
+	uint32_t fast_short_cap = 4, fast_long_cap = 32;
+	bool fast_wide = false;           // a reachable floor has 33..64 posts: shorter runs (72-byte Y records)
 	uint32_t fast_max_nl = 1;         // largest channel set a coupling program of this setup needs
 	const FastTables* d_fast = nullptr;
 	// device entropy decode (POV_INPUT_PACKETS): tables + per-mode arena capacities of one packet

@@ -26,6 +26,8 @@
 #include "kernels.h"
 #include "fft_core.cuh"
 #include <stdlib.h>
+#include <algorithm>
+#include <type_traits>
 
 namespace pov {
 namespace wk {
@@ -208,7 +210,10 @@ __device__ __forceinline__ float uncouple_ang(float m, float a) {
 // posts serially (the neighbour DAG makes the posts of one curve sequential, but the <= 32 curves of a run are
 // independent). The final Y values leave in ascending-x order as bytes, with the step2 flags as a bit mask, 36 bytes per
 // packet; the hpp:536 / hpp:587 checks are evaluated here with full-width values and reported per packet.
-// scratch: [32 posts][32 lanes] uint16, aliasing the (idle) FFT work regions.
+// scratch: [posts][32 lanes] uint16, aliasing the (idle) FFT work regions.
+// kWide: floors of 33..64 posts (libvorbis' high-quality setups): 64-bit flag masks, 72-byte Y records (64 bytes + mask), so
+// a run then holds at most 16 packets (the record area of a warp is the same 1152 bytes).
+template <bool kWide>
 __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, const WPkt* __restrict__ wp, const pov_packet* __restrict__ pk0, int run_n, int ch,
                                         const uint16_t* __restrict__ ys, uint16_t* __restrict__ scratch, unsigned char* __restrict__ fs,
                                         uint32_t* __restrict__ status, uint32_t n0, uint32_t n1, int lane) {
@@ -227,7 +232,10 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 		if((used >> cc) & 1u) yo += tb->floors[tb->floor_of_ch[mapping][cc]].n_posts;
 	const uint16_t* yp = ys + yo;
 	const uint32_t range = F->range;
-	uint32_t flags = 3u, bad = 0u;
+	using MaskT = typename std::conditional<kWide, uint64_t, uint32_t>::type;
+	constexpr int kStride = kWide ? 72 : 36, kMaskAt = kWide ? 64 : 32;
+	MaskT flags = 3u;
+	uint32_t bad = 0u;
 	uint16_t* col = scratch + lane;
 	if(act) { col[0] = __ldg(yp); col[32] = __ldg(yp + 1); }
 	for(int i = 2; i < maxposts; ++i) {
@@ -249,7 +257,7 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 			const uint32_t room = min(high_room, low_room) * 2;
 			uint32_t fin = predicted;
 			if(val != 0) {
-				flags |= (1u << lo) | (1u << hi) | (1u << i);
+				flags |= ((MaskT) 1 << lo) | ((MaskT) 1 << hi) | ((MaskT) 1 << i);
 				if(val >= room) fin = (high_room > low_room) ? val - low_room + predicted : predicted - val + high_room - 1;
 				else fin = (val & 1) ? predicted - (val + 1) / 2 : predicted + val / 2;
 			}
@@ -260,16 +268,17 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 	// monotone, so the maxima are at rendered end points; a segment cut by bin n-1 needs y(n-1)
 	const uint32_t n = tb->mode_flag[mode] ? n1 : n0;
 	const uint32_t mult = F->multiplier;
-	uint32_t smask = 0u, xp = 0u, ypv = 0u;
+	MaskT smask = 0u;
+	uint32_t xp = 0u, ypv = 0u;
 	bool havep = false;
-	unsigned char* out = fs + lane * kFsStride;
+	unsigned char* out = fs + lane * kStride;
 	for(int sidx = 0; sidx < maxposts; ++sidx) {
 		if(sidx < posts) {
 			const uint32_t si = F->post[sidx][0] >> 24, x = F->post[sidx][3] & 0xffffu;
 			const uint32_t y = col[si * 32];
 			out[sidx] = (unsigned char) min(y, 255u);
 			if((flags >> si) & 1u) {
-				smask |= 1u << sidx;
+				smask |= (MaskT) 1 << sidx;
 				const uint32_t yv = min(y * mult, 0xFFFFu);
 				if(x < n && yv >= 256u) bad |= POV_PKT_FLOOR_RANGE;
 				if(havep && xp < n && x > n - 1) {
@@ -283,7 +292,7 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 		}
 	}
 	if(act) {
-		*reinterpret_cast<uint32_t*>(out + 32) = smask;
+		*reinterpret_cast<MaskT*>(out + kMaskAt) = smask;
 		if(bad) atomicOr(status + lane, bad);
 	}
 	__syncwarp();
@@ -293,43 +302,55 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 // Rank table: for every 32-bin word w of the curve, tab[w] = (bitmap of the flagged posts inside the word,
 // number of flagged posts before the word - 1); the record that contains bin x is
 //   tab[x >> 5].y + popc(tab[x >> 5].x & (0xFFFFFFFF >> (31 - (x & 31)))).
+template <bool kWide>
 __device__ __forceinline__ void build_records(const FastFloor* __restrict__ F, const unsigned char* __restrict__ fsp, unsigned char* __restrict__ curve,
                                            uint32_t rec_cap, uint32_t nwords, const uint32_t* __restrict__ recip, int lane) {
+	using MaskT = typename std::conditional<kWide, uint64_t, uint32_t>::type;
+	constexpr int kMaskAt = kWide ? 64 : 32, kRounds = kWide ? 2 : 1;
 	const int posts = (int) F->n_posts;
-	const bool have = lane < posts;
-	const uint32_t mask = *reinterpret_cast<const uint32_t*>(fsp + 32);
-	const uint32_t yb = fsp[lane];
-	const uint32_t x0 = F->xs_sorted[lane];
-	const bool f = have && ((mask >> lane) & 1u);
-	const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-	const uint32_t y0 = min(yb * F->multiplier, 1023u);
-	const uint32_t above = (lane == 31) ? 0u : (mask & ~((2u << lane) - 1u));
-	const bool last = above == 0u;
-	const int nlane = last ? lane : (__ffs((int) above) - 1);
-	const uint32_t pn = __shfl_sync(FULL, x0 | (y0 << 16), nlane);
-	const uint32_t x1 = pn & 0xffffu, y1 = pn >> 16;
-
+	const MaskT mask = *reinterpret_cast<const MaskT*>(fsp + kMaskAt);
 	uint2* rec = reinterpret_cast<uint2*>(curve);
 	uint2* tab = rec + rec_cap;
 	uint32_t* bits = reinterpret_cast<uint32_t*>(tab);          // word w at bits[2w] while the bitmap is collected
 	if((uint32_t) lane < nwords) bits[2 * lane] = 0u;
 	__syncwarp();
-	if(f) {
-		uint2 r;
-		if(last) r = make_uint2(y0 << 20, 0u);
-		else {
-			const bool down = y1 < y0;
-			const uint32_t ady = down ? y0 - y1 : y1 - y0, adx = x1 - x0;
-			// slope = ceil(2^20 |dy| / dx) = floor(N / dx), N = (|dy| << 20) + dx - 1 < 2^31: the table quotient is exact or one too big
-			const uint32_t N = (ady << 20) + adx - 1u;
-			uint32_t q = __umulhi(N, recip[adx]);
-			if(q * adx > N) --q;
-			if(adx == 1u) q = N;
-			const uint32_t b = down ? 0u - q : q;
-			r = make_uint2((y0 << 20) + (down ? 0xFFFFFu : 0u) - x0 * b, b);
+#pragma unroll
+	for(int h = 0; h < kRounds; ++h) {                          // post p = lane + 32 h (ascending-x order)
+		const int p = lane + 32 * h;
+		const bool have = p < posts;
+		const uint32_t yb = have ? fsp[p] : 0u;
+		const uint32_t x0 = have ? F->xs_sorted[p] : 0u;
+		const bool f = have && ((mask >> p) & 1u);
+		const uint32_t rank = kWide ? (uint32_t) __popcll((uint64_t) mask & (((uint64_t) 1 << p) - 1u)) : (uint32_t) __popc((uint32_t) mask & ((1u << p) - 1u));
+		const uint32_t y0 = min(yb * F->multiplier, 1023u);
+		// the next flagged post (the segment's right end): (x1, y1) straight from the tables, no shuffle
+		const MaskT above = (p == (kWide ? 63 : 31)) ? (MaskT) 0 : (MaskT) (mask & ~(((MaskT) 2 << p) - 1u));
+		const bool last = above == 0;
+		const int np = last ? p : (kWide ? __ffsll((long long) above) : __ffs((int) above)) - 1;
+		uint32_t x1, y1;
+		if constexpr(kWide) {
+			x1 = f ? F->xs_sorted[np] : 0u; y1 = f ? min((uint32_t) fsp[np] * F->multiplier, 1023u) : 0u;
+		} else {                                                  // one round: the next post is another lane's (x0, y0)
+			const uint32_t pn = __shfl_sync(FULL, x0 | (y0 << 16), np);
+			x1 = pn & 0xffffu; y1 = pn >> 16;
 		}
-		rec[rank] = r;
-		if((x0 >> 5) < nwords) atomicOr(&bits[2 * (x0 >> 5)], 1u << (x0 & 31u));
+		if(f) {
+			uint2 r;
+			if(last) r = make_uint2(y0 << 20, 0u);
+			else {
+				const bool down = y1 < y0;
+				const uint32_t ady = down ? y0 - y1 : y1 - y0, adx = x1 - x0;
+				// slope = ceil(2^20 |dy| / dx) = floor(N / dx), N = (|dy| << 20) + dx - 1 < 2^31: the table quotient is exact or one too big
+				const uint32_t N = (ady << 20) + adx - 1u;
+				uint32_t q = __umulhi(N, recip[adx]);
+				if(q * adx > N) --q;
+				if(adx == 1u) q = N;
+				const uint32_t b = down ? 0u - q : q;
+				r = make_uint2((y0 << 20) + (down ? 0xFFFFFu : 0u) - x0 * b, b);
+			}
+			rec[rank] = r;
+			if((x0 >> 5) < nwords) atomicOr(&bits[2 * (x0 >> 5)], 1u << (x0 & 31u));
+		}
 	}
 	__syncwarp();
 	{
@@ -903,7 +924,9 @@ __device__ __forceinline__ int curve_mode(const FastTables* tb, uint32_t mapping
 	return ((prop >> c) & 1u) ? 2 : 1;
 }
 
-template <int Q0, int Q1, bool kPlanar, int kMaxNL>
+// kWide: a floor of 33..64 posts is reachable (compile time, so that the common case keeps its constants: 32 records per long
+// curve, 36-byte Y records, 32-bit step-2 masks); instantiated with the generic coupling class only.
+template <int Q0, int Q1, bool kPlanar, int kMaxNL, bool kWide>
 __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	using M = Map<Q0, Q1>;
 	constexpr int N0 = 4 * Q0, N1 = 4 * Q1;              // block sizes
@@ -1036,7 +1059,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			first_of_stream = run.first_packet == st.first_packet;
 		}
 		__syncwarp();
-		unwrap_run(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, (uint32_t) N0, (uint32_t) N1, lane);
+		unwrap_run<kWide>(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, (uint32_t) N0, (uint32_t) N1, lane);
 
 		// State carried from step to step, packed into one register (the FFT in between needs every register it can get):
 		//   bit 0 step parity (which half regions the step uses) | bit 1 a previous frame exists | bit 2 it was a long block |
@@ -1083,13 +1106,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			// (unused) part of the work area, so that every lane reaches the warp barriers
 			const int u = lane & (lpf - 1);
 			const int f = lane / lpf;                    // 0 for a whole-warp FFT
-			constexpr uint32_t kLongCurveBytes = 32u * 8u + (uint32_t) (Q1 / 16) * 8u;
-			const uint32_t cstride = flag ? (kLongGrouped ? kLongCurveBytes : 0u) : P.short_curve_stride, rcap = flag ? 32u : tb->short_posts_cap,
+			constexpr uint32_t kLongCap = kWide ? 64u : 32u;              // records of a long curve (= FastTables::long_posts_cap)
+			constexpr uint32_t kLongCurveBytes = kLongCap * 8u + (uint32_t) (Q1 / 16) * 8u;
+			const uint32_t cstride = flag ? (kLongGrouped ? kLongCurveBytes : 0u) : P.short_curve_stride, rcap = flag ? kLongCap : tb->short_posts_cap,
 			               nwords = (uint32_t) Qs / 16u;
 			for(int g = 0; g < count; ++g) {
 				const int md = curve_mode(tb, mapping, wp[first + g].meta >> 16, ch);
 				unsigned char* cv = curves + (size_t) g * cstride;
-				if(md == 0) build_records(F, fs + (first + g) * kFsStride, cv, rcap, nwords, s_recip, lane);
+				if(md == 0) build_records<kWide>(F, fs + (first + g) * (kWide ? 72 : kFsStride), cv, rcap, nwords, s_recip, lane);
 				else flat_curve(cv, rcap, nwords, md == 1 ? 255u : 256u, lane);
 			}
 			// FFT buffer of FFT f: Q/64 sub-FFT rows of 72 slots (one row for Q = 64)
@@ -1193,43 +1217,52 @@ template <int Q0, int Q1> static size_t smem_for(uint32_t cb) {
 	return (size_t) wk::Map<Q0, Q1>::kOffWarps + (size_t) wk::kWarps * ((size_t) wk::kWarpFixedBytes + cb);
 }
 
-size_t warp_kernel_smem_bytes(uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out,
-                              uint32_t* short_stride_out) {
+size_t warp_kernel_smem_bytes(uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t long_posts_cap, uint32_t* group_short_out,
+                              uint32_t* curve_bytes_out, uint32_t* short_stride_out) {
 	const uint32_t Q0 = bs0 / 4, Q1 = bs1 / 4;
 	const uint32_t stride = short_posts_cap * 8u + (Q0 / 16u) * 8u;       // records + rank-table words of one short curve
 	uint32_t group = 512u / Q0;                                           // short FFTs a warp transforms at once (Q0/16 lanes each)
-	uint32_t cb = 32u * 8u + (Q1 / 16u) * 8u;                             // one long curve: 32 records + rank table
+	uint32_t cb = long_posts_cap * 8u + (Q1 / 16u) * 8u;                  // one long curve: records (32 or 64) + rank table
 	if(Q1 < 512u) cb *= 512u / Q1;                                         // long packets of < 512 points are grouped too (kLongGrouped)
 	while(group > 1 && group * stride > wk::kCurveMax) --group;
-	if(group * stride > cb) cb = group * stride;
-	cb = (cb + 15u) & ~15u;
+	const uint32_t cb_long = cb;
+	auto total = [&](uint32_t g) -> size_t {
+		uint32_t c = std::max(cb_long, g * stride);
+		c = (c + 15u) & ~15u;
+		switch(Q0 * 1024u + Q1) {
+			case 64u * 1024u + 128u:  return smem_for<64, 128>(c);
+			case 64u * 1024u + 256u:  return smem_for<64, 256>(c);
+			case 64u * 1024u + 512u:  return smem_for<64, 512>(c);
+			case 128u * 1024u + 256u: return smem_for<128, 256>(c);
+			case 128u * 1024u + 512u: return smem_for<128, 512>(c);
+			case 256u * 1024u + 512u: return smem_for<256, 512>(c);
+			default: return (size_t) 1 << 30;
+		}
+	};
+	// a setup with big short-block floors keeps the kernel by transforming fewer short packets per step rather than losing it
+	while(group > 1 && total(group) > 227u * 1024u) --group;
+	cb = (std::max(cb_long, group * stride) + 15u) & ~15u;
 	if(group_short_out) *group_short_out = group;
 	if(curve_bytes_out) *curve_bytes_out = cb;
 	if(short_stride_out) *short_stride_out = stride;
-	switch(Q0 * 1024u + Q1) {
-		case 64u * 1024u + 128u:  return smem_for<64, 128>(cb);
-		case 64u * 1024u + 256u:  return smem_for<64, 256>(cb);
-		case 64u * 1024u + 512u:  return smem_for<64, 512>(cb);
-		case 128u * 1024u + 256u: return smem_for<128, 256>(cb);
-		case 128u * 1024u + 512u: return smem_for<128, 512>(cb);
-		case 256u * 1024u + 512u: return smem_for<256, 512>(cb);
-		default: return (size_t) 1 << 30;
-	}
+	return total(group);
 }
 
-uint32_t warp_kernel_max_run(void) { return (uint32_t) wk::kPktCap - 1u; }
+// packets of a run (halo excluded): the Y records of a run share 1152 bytes: 32 of 36 bytes, or 16 of 72 (floors of 33..64 posts)
+uint32_t warp_kernel_max_run(bool wide) { return wide ? (uint32_t) (wk::kPktCap * wk::kFsStride / 72) - 1u : (uint32_t) wk::kPktCap - 1u; }
 uint32_t warp_kernel_warps(void) { return (uint32_t) wk::kWarps; }
 
-template <int Q0, int Q1, bool kPlanar, int kMaxNL>
+template <int Q0, int Q1, bool kPlanar, int kMaxNL, bool kWide = false>
 static cudaError_t launch_one(const wk::Params& P, uint32_t grid, size_t smem, cudaStream_t st) {
-	cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1, kPlanar, kMaxNL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	cudaError_t e = cudaFuncSetAttribute(wk::k_warp_synth<Q0, Q1, kPlanar, kMaxNL, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if(e != cudaSuccess) return e;
-	wk::k_warp_synth<Q0, Q1, kPlanar, kMaxNL><<<grid, wk::kThreads, smem, st>>>(P);
+	wk::k_warp_synth<Q0, Q1, kPlanar, kMaxNL, kWide><<<grid, wk::kThreads, smem, st>>>(P);
 	return cudaGetLastError();
 }
 
 template <int Q0, int Q1>
-static cudaError_t launch_geom(const wk::Params& P, uint32_t max_nl, uint32_t grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_geom(const wk::Params& P, uint32_t max_nl, bool wide, uint32_t grid, size_t smem, cudaStream_t st) {
+	if(wide) return P.b.pcm_layout == POV_PCM_PLANAR ? launch_one<Q0, Q1, true, 4, true>(P, grid, smem, st) : launch_one<Q0, Q1, false, 4, true>(P, grid, smem, st);
 	const int cls = max_nl <= 1 ? 1 : max_nl == 2 ? 2 : 4;
 	if(P.b.pcm_layout == POV_PCM_PLANAR) {
 		if(cls == 1) return launch_one<Q0, Q1, true, 1>(P, grid, smem, st);
@@ -1242,7 +1275,7 @@ static cudaError_t launch_geom(const wk::Params& P, uint32_t max_nl, uint32_t gr
 }
 
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
-                        uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
+                        uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t long_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
                         const float2* const tw8[2], const float2* const fp[2], const float* tmtab, uint32_t* d_counter, int sm_count, cudaStream_t st,
                         uint64_t* launches) {
 	if(n_runs == 0) return cudaSuccess;
@@ -1250,7 +1283,7 @@ cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_ru
 	P.b = b; P.runs = runs; P.n_runs = n_runs; P.C = channels; P.n_items = n_runs * channels;
 	P.counter = d_counter; P.tabs = d_tabs; P.tmtab = tmtab;
 	for(int k = 0; k < 2; ++k) { P.slope[k] = slope[k]; P.rot[k] = rot[k]; P.tw8[k] = tw8[k]; P.fp[k] = fp[k]; }
-	const size_t smem = warp_kernel_smem_bytes(bs0, bs1, short_posts_cap, &P.group_short, &P.curve_bytes, &P.short_curve_stride);
+	const size_t smem = warp_kernel_smem_bytes(bs0, bs1, short_posts_cap, long_posts_cap, &P.group_short, &P.curve_bytes, &P.short_curve_stride);
 	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 	cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st);
 	if(e != cudaSuccess) return e;
@@ -1258,12 +1291,12 @@ cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_ru
 	const uint32_t need = (P.n_items + wk::kWarps - 1) / wk::kWarps;
 	if(grid > need) grid = need;
 	switch((bs0 / 4) * 1024u + bs1 / 4) {
-		case 64u * 1024u + 128u:  e = launch_geom<64, 128>(P, max_nl, grid, smem, st); break;
-		case 64u * 1024u + 256u:  e = launch_geom<64, 256>(P, max_nl, grid, smem, st); break;
-		case 64u * 1024u + 512u:  e = launch_geom<64, 512>(P, max_nl, grid, smem, st); break;
-		case 128u * 1024u + 256u: e = launch_geom<128, 256>(P, max_nl, grid, smem, st); break;
-		case 128u * 1024u + 512u: e = launch_geom<128, 512>(P, max_nl, grid, smem, st); break;
-		case 256u * 1024u + 512u: e = launch_geom<256, 512>(P, max_nl, grid, smem, st); break;
+		case 64u * 1024u + 128u:  e = launch_geom<64, 128>(P, max_nl, long_posts_cap > 32, grid, smem, st); break;
+		case 64u * 1024u + 256u:  e = launch_geom<64, 256>(P, max_nl, long_posts_cap > 32, grid, smem, st); break;
+		case 64u * 1024u + 512u:  e = launch_geom<64, 512>(P, max_nl, long_posts_cap > 32, grid, smem, st); break;
+		case 128u * 1024u + 256u: e = launch_geom<128, 256>(P, max_nl, long_posts_cap > 32, grid, smem, st); break;
+		case 128u * 1024u + 512u: e = launch_geom<128, 512>(P, max_nl, long_posts_cap > 32, grid, smem, st); break;
+		case 256u * 1024u + 512u: e = launch_geom<256, 512>(P, max_nl, long_posts_cap > 32, grid, smem, st); break;
 		default: return cudaErrorInvalidConfiguration;
 	}
 	if(launches) ++*launches;

@@ -44,12 +44,12 @@ size_t fused_smem_bytes(uint32_t max_channels, uint32_t max_blocksize, uint32_t 
                         uint32_t table_float2);
 // Warp-autonomous persistent kernel (kernel_warp.cu): single-setup batches with blocksizes 256/2048.
 bool warp_kernel_supports(uint32_t bs0, uint32_t bs1);     // block size pairs the warp kernel is instantiated for
-size_t warp_kernel_smem_bytes(uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out,
+size_t warp_kernel_smem_bytes(uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t long_posts_cap, uint32_t* group_short_out, uint32_t* curve_bytes_out,
                               uint32_t* short_stride_out);
-uint32_t warp_kernel_max_run(void);   // packets per run without the halo
+uint32_t warp_kernel_max_run(bool wide);   // packets per run without the halo (wide: a floor of 33..64 posts is reachable)
 uint32_t warp_kernel_warps(void);     // resident warps per SM
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
-                        uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
+                        uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t long_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
                         const float2* const tw8[2], const float2* const fp[2], const float* tmtab, uint32_t* d_counter, int sm_count, cudaStream_t st,
                         uint64_t* launches);
 // One row of a feature matrix (pov_batch_features; reference: demo_live_extract.py:262-505): where its values come from.

@@ -109,6 +109,7 @@ struct DevSetup {
 #define POV_FAST_MAX_MAPPINGS 4
 #define POV_FAST_MAX_STEPS    8     // coupling steps per mapping
 #define POV_FAST_MAX_DEPS     4     // channels one channel's un-coupled value may depend on (itself included)
+#define POV_FAST_MAX_POSTS    64    // floor posts on the warp kernel's path (libvorbis' floors have up to 65; the fixtures' 9 / 29)
 #define POV_FAST_MAX_X        1024  // largest floor X (segment lengths index the reciprocal table)
 
 struct FastFloor {
@@ -118,8 +119,8 @@ struct FastFloor {
 	//   [1] (xs[i] - xs[lo]) | (xs[hi] - xs[lo]) << 16         (prediction numerator / denominator, Utils.hpp:122-137)
 	//   [2] ceil(2^32 / (xs[hi] - xs[lo]))                     (exact division by multiplication, see kernel_warp.cu)
 	//   [3] X of the i-th smallest post
-	uint32_t post[32][4];
-	uint32_t xs_sorted[32];            // X of the i-th smallest post again, unit stride (conflict-free per-lane reads)
+	uint32_t post[POV_FAST_MAX_POSTS][4];
+	uint32_t xs_sorted[POV_FAST_MAX_POSTS];   // X of the i-th smallest post again, unit stride (conflict-free per-lane reads)
 };
 
 // How the warp that owns channel c of a mapping un-couples it (hpp:1213-1241): the channels it has to load
@@ -140,7 +141,9 @@ struct FastTables {
 	uint8_t mode_flag[POV_MAX_MODES], mode_map[POV_MAX_MODES];
 	uint32_t channels;
 	uint32_t short_posts_cap;          // record capacity of a short-block curve (multiple of 4)
-	uint32_t pad[5];
+	uint32_t long_posts_cap;           // record capacity of a long-block curve (32 or 64)
+	uint32_t wide;                     // a reachable floor has more than 32 posts (64-bit step-2 masks, 72-byte Y records)
+	uint32_t pad[3];
 };
 static_assert(sizeof(FastTables) % 16 == 0, "FastTables is moved with 16-byte bulk copies");
 

@@ -344,7 +344,7 @@ def golden_setup_and_batch(g: Dict[str, np.ndarray]) -> Tuple[abi.Setup, abi.Bat
 
 # ---- randomised setups (parity stress: many floors, submaps, modes, coupling graphs) ------------------------------
 def random_setup(rng: np.random.Generator, channels: int, blocksizes=(256, 2048), max_posts: int = 32,
-                 max_couplings: int = 5, max_component: int = 4) -> abi.Setup:
+                 max_couplings: int = 5, max_component: int = 4, max_posts_short: Optional[int] = None) -> abi.Setup:
     """A random but well-formed setup: 1-2 floors per blocksize class with random distinct X lists and multipliers,
     1-3 submaps with their own floors, up to `max_couplings` coupling steps whose connected components stay within
     `max_component` channels, and 2-4 modes over 2-4 mappings. Floor class of a mapping follows its modes."""
@@ -352,7 +352,8 @@ def random_setup(rng: np.random.Generator, channels: int, blocksizes=(256, 2048)
     floors, cls_floors = [], {0: [], 1: []}
     for cls, half in ((0, bs0 // 2), (1, bs1 // 2)):
         for _ in range(int(rng.integers(1, 3))):
-            posts = int(rng.integers(2, min(max_posts, half) + 1))
+            cap = max_posts if (cls == 1 or max_posts_short is None) else max_posts_short
+            posts = int(rng.integers(2, min(cap, half) + 1))
             inner = rng.choice(np.arange(1, half), size=posts - 2, replace=False) if posts > 2 else np.zeros(0, int)
             xs = [0, half] + [int(v) for v in inner]
             cls_floors[cls].append(len(floors))

@@ -257,6 +257,27 @@ def test_random_setups_against_oracle(ctx, seed):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_floors_of_up_to_64_posts_stay_on_the_warp_kernel(ctx, seed):
+    """libvorbis' high-quality setups carry more than 32 floor posts (up to 65 by VIF_POSIT): floors of 33..64 posts take the
+    warp kernel's wide path (64-bit step-2 masks, 72-byte Y records, runs of <= 16 packets) and must equal the oracle —
+    PCM, status words and, on the staged kernels, after_envelope — like the narrow ones."""
+    rng = np.random.default_rng(7000 + seed)
+    C = int(rng.integers(1, 4))
+    for _ in range(50):                      # draw until a floor really has more than 32 posts
+        setup = workloads.random_setup(rng, C, max_posts=64, max_couplings=2, max_posts_short=32)
+        if max(len(f.xs) for f in setup.floors) > 32 and len(setup.floors) <= 4 and len(setup.mappings) <= 4:
+            break
+    assert max(len(f.xs) for f in setup.floors) > 32
+    batch = workloads.random_batch(setup, rng, streams=3, packets_per_stream=70)
+    batch.streams["setup_id"] = ctx.register_setup(setup)
+    bh = ctx.upload(batch)
+    assert ctx.kernel_name(bh) == "k_warp_synth", [len(f.xs) for f in setup.floors]
+    bh.free()
+    _check_against_oracle(ctx, setup, batch, stages=(seed % 2 == 0))
+
+
+@pytest.mark.gpu
 def test_random_setups_take_the_warp_kernel(ctx):
     taken = 0
     for seed in range(12):
