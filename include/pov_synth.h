@@ -262,6 +262,10 @@ void pov_batch_free(pov_ctx* ctx, pov_batch_handle* h);
 
 /* ---- drop-in for the reference's only C symbols on the path: mdct_backward (src/mdct.h:105) ---------------- */
 /* `count` independent inverse MDCTs of size n (R^(n/2) -> R^n, no scaling), host buffers in/out. */
+/* Parity hook of the production kernel: its own floor1 step-1 result (what hpp:521-559 computes), [n_packets][max channels][72]
+ * bytes: 64 final Ys in ascending-x order, clamped to 255 | 64-bit step-2 mask in the same order. Warp-kernel batches only. */
+int  pov_batch_fetch_fast_floor(pov_ctx* ctx, pov_batch_handle* h, uint8_t* out, uint64_t out_bytes);
+
 /* Feature matrices straight from the device (the reference's downstream use: returnn_import.py:74-115 builds them in
  * Python from a debug dump, demo_live_extract.py:262-505): `kind` as below with the readers' default arguments, for one
  * stream of the batch; (rows, output_dim) floats, row-major, only the matrix crosses PCIe. Runs the staged kernels if they

@@ -925,7 +925,30 @@ extern "C" int pov_batch_run_staged(pov_ctx* ctx, pov_batch_handle* h) try {
 	return POV_OK;
 } POV_NOTHROW_END(ctx)
 
+static int run_batch(pov_ctx* ctx, pov_batch_handle* h, unsigned char* dbg_floor);
 extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) try {
+	return run_batch(ctx, h, nullptr);
+} POV_NOTHROW_END(ctx)
+
+// The production kernel's own floor1 step-1 result, for parity tests: runs the batch on k_warp_synth with its floor hook on
+// and returns [n_packets][channels][72] bytes — 64 final Ys in ascending-x order (clamped to 255) | 64-bit step-2 mask —
+// for every channel-packet whose floor was decoded (others: unspecified).
+extern "C" int pov_batch_fetch_fast_floor(pov_ctx* ctx, pov_batch_handle* h, uint8_t* out, uint64_t out_bytes) try {
+	if(!ctx || !h || !out) return POV_ERR_ARG;
+	if(!h->warp_ok) return pov_fail(ctx, POV_ERR_UNSUPPORTED, "pov_batch_fetch_fast_floor: this batch does not run on the warp kernel");
+	const uint64_t need = (uint64_t) h->n_packets * h->max_channels * 72;
+	if(out_bytes != need) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_fast_floor: %llu bytes expected", (unsigned long long) need);
+	cudaSetDevice(ctx->device);
+	CUDA_TRY(ctx, h->d_feat_out.reserve(std::max<size_t>(need, 16)));
+	CUDA_TRY(ctx, cudaMemsetAsync(h->d_feat_out.ptr, 0, need, ctx->stream));
+	const int rc = run_batch(ctx, h, (unsigned char*) h->d_feat_out.ptr);
+	if(rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(out, h->d_feat_out.ptr, need, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return POV_OK;
+} POV_NOTHROW_END(ctx)
+
+static int run_batch(pov_ctx* ctx, pov_batch_handle* h, unsigned char* dbg_floor) {
 	if(!ctx || !h) return POV_ERR_ARG;
 	if(ctx->kernel_choice == 2 && !h->warp_ok) return pov_fail(ctx, POV_ERR_UNSUPPORTED, "POV_KERNEL=warp: this batch is outside what the warp kernel supports");
 	if(!h->warp_ok && !h->fused_ok) return pov_batch_run_staged(ctx, h);   // working set beyond one SM's shared memory: staged kernels
@@ -938,7 +961,7 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) try {
 			const SetupRec& su = ctx->setups[g.setup];
 			CUDA_TRY(ctx, launch_warp(v, (const DevRun*) h->d_runs.ptr + g.first_run, g.n_runs, su.channels, su.d_fast, su.blocksize[0], su.blocksize[1],
 			                          su.fast_short_cap, su.fast_long_cap, su.fast_max_nl, su.dev.slope, su.dev.rot, su.dev.fft8, su.dev.fftp,
-			                          ctx->blk_tables.count(2048) ? ctx->blk_tables[2048].d_tm : nullptr, ctx->d_counter, ctx->sm_count, ctx->stream,
+			                          ctx->blk_tables.count(2048) ? ctx->blk_tables[2048].d_tm : nullptr, dbg_floor, ctx->d_counter, ctx->sm_count, ctx->stream,
 			                          &ctx->launches));
 		}
 		return POV_OK;
@@ -946,7 +969,7 @@ extern "C" int pov_batch_run(pov_ctx* ctx, pov_batch_handle* h) try {
 	CUDA_TRY(ctx, launch_fused(v, (const DevRun*) h->d_runs.ptr, (uint32_t) h->runs.size(), h->max_channels, h->max_blocksize,
 	                           h->min_blocksize, h->floor_cap_cls, h->table_float2, h->only_256_2048, ctx->stream, &ctx->launches));
 	return POV_OK;
-} POV_NOTHROW_END(ctx)
+}
 
 extern "C" const char* pov_batch_kernel_name(const pov_ctx* ctx, const pov_batch_handle* h) {
 	if(!ctx || !h) return "none";

@@ -73,6 +73,7 @@ struct Params {
 	const float2* tw8[2];
 	const float2* fp[2];         // twiddles of the first radix-2 / radix-4 pass (block sizes 512 and 1024)
 	const float* tmtab;          // [32][kTxTable] lane rows of the tensor-memory FFT (block size 2048; make_tm_lane_tables)
+	unsigned char* dbg_floor;    // null, or [n_packets][C][72]: this kernel's own floor1 step-1 result per channel-packet (parity tests)
 	uint32_t group_short;        // short packets per step (<= 8)
 	uint32_t curve_bytes;        // per-warp curve area
 	uint32_t short_curve_stride; // bytes of one short-block curve block
@@ -1060,6 +1061,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 		}
 		__syncwarp();
 		unwrap_run<kWide>(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, (uint32_t) N0, (uint32_t) N1, lane);
+		if(P.dbg_floor) {
+			// parity hook: the production kernel's integer floor stage as it is — final Ys (ascending x, clamped to 255) and the
+			// step-2 mask of every packet of the run — copied out for comparison with the reference's "floor1 final_ys" /
+			// "floor1 step2_flag" (pov_batch_fetch_fast_floor). 72 bytes per channel-packet: 64 Ys | 64-bit mask.
+			constexpr int kS = kWide ? 72 : kFsStride, kM = kWide ? 64 : 32;
+			if(lane < run_n) {
+				unsigned char* d = P.dbg_floor + ((size_t) (run.first_packet + lane) * C + ch) * 72;
+				const unsigned char* src = fs + lane * kS;
+				for(int i = 0; i < kM; ++i) d[i] = src[i];
+				for(int i = kM; i < 64; ++i) d[i] = 0;
+				for(int i = 0; i < 8; ++i) d[64 + i] = (i < (kWide ? 8 : 4)) ? src[kM + i] : (unsigned char) 0;
+			}
+			__syncwarp();
+		}
 
 		// State carried from step to step, packed into one register (the FFT in between needs every register it can get):
 		//   bit 0 step parity (which half regions the step uses) | bit 1 a previous frame exists | bit 2 it was a long block |
@@ -1276,12 +1291,12 @@ static cudaError_t launch_geom(const wk::Params& P, uint32_t max_nl, bool wide, 
 
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
                         uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t long_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
-                        const float2* const tw8[2], const float2* const fp[2], const float* tmtab, uint32_t* d_counter, int sm_count, cudaStream_t st,
-                        uint64_t* launches) {
+                        const float2* const tw8[2], const float2* const fp[2], const float* tmtab, unsigned char* dbg_floor, uint32_t* d_counter, int sm_count,
+                        cudaStream_t st, uint64_t* launches) {
 	if(n_runs == 0) return cudaSuccess;
 	wk::Params P;
 	P.b = b; P.runs = runs; P.n_runs = n_runs; P.C = channels; P.n_items = n_runs * channels;
-	P.counter = d_counter; P.tabs = d_tabs; P.tmtab = tmtab;
+	P.counter = d_counter; P.tabs = d_tabs; P.tmtab = tmtab; P.dbg_floor = dbg_floor;
 	for(int k = 0; k < 2; ++k) { P.slope[k] = slope[k]; P.rot[k] = rot[k]; P.tw8[k] = tw8[k]; P.fp[k] = fp[k]; }
 	const size_t smem = warp_kernel_smem_bytes(bs0, bs1, short_posts_cap, long_posts_cap, &P.group_short, &P.curve_bytes, &P.short_curve_stride);
 	if(smem > 227 * 1024) return cudaErrorInvalidConfiguration;

@@ -50,8 +50,8 @@ uint32_t warp_kernel_max_run(bool wide);   // packets per run without the halo (
 uint32_t warp_kernel_warps(void);     // resident warps per SM
 cudaError_t launch_warp(const DevBatchView& b, const DevRun* runs, uint32_t n_runs, uint32_t channels, const FastTables* d_tabs,
                         uint32_t bs0, uint32_t bs1, uint32_t short_posts_cap, uint32_t long_posts_cap, uint32_t max_nl, const float* const slope[2], const float2* const rot[2],
-                        const float2* const tw8[2], const float2* const fp[2], const float* tmtab, uint32_t* d_counter, int sm_count, cudaStream_t st,
-                        uint64_t* launches);
+                        const float2* const tw8[2], const float2* const fp[2], const float* tmtab, unsigned char* dbg_floor, uint32_t* d_counter, int sm_count,
+                        cudaStream_t st, uint64_t* launches);
 // One row of a feature matrix (pov_batch_features; reference: demo_live_extract.py:262-505): where its values come from.
 struct FeatRow {
 	uint64_t src;        // kinds 0: index of the channel-packet's final_ys slot; 1: float offset of its rendered floor (u16);

@@ -22,7 +22,7 @@ SYMBOLS = [
     "pov_abi_version", "pov_inverse_db_table", "pov_window", "pov_ctx_create", "pov_ctx_destroy", "pov_last_error", "pov_ctx_stream",
     "pov_ctx_launch_count", "pov_ctx_io_bytes", "pov_ctx_set_device_entropy", "pov_ctx_set_page_spanning", "pov_ogg_parse_memory_ex", "pov_setup_register", "pov_setup_entry_bits", "pov_setup_get_window",
     "pov_batch_upload", "pov_batch_run", "pov_batch_kernel_name", "pov_batch_run_staged", "pov_batch_fetch_pcm", "pov_batch_pcm_dev",
-    "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_batch_features", "pov_mdct_backward_batch",
+    "pov_batch_fetch_stage", "pov_batch_status", "pov_batch_sync", "pov_batch_free", "pov_batch_features", "pov_batch_fetch_fast_floor", "pov_mdct_backward_batch",
     "pov_ogg_vorbis_decode_memory", "pov_decoded_free", "pov_decode_corpus", "pov_decode_corpus_pcm", "pov_ogg_vorbis_full_read_from_memory",
     "pov_ogg_parse_memory", "pov_parsed_stream_count", "pov_parsed_get", "pov_parsed_free",
 ]
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
     L.pov_batch_sync.argtypes = [vp, vp]
     L.pov_batch_free.argtypes = [vp, vp]
     L.pov_batch_free.restype = None
+    L.pov_batch_fetch_fast_floor.argtypes = [vp, vp, C.POINTER(C.c_uint8), u64]
     L.pov_batch_features.argtypes = [vp, vp, u32, i32, u32, C.POINTER(C.c_float), u64, C.POINTER(u64)]
     L.pov_mdct_backward_batch.argtypes = [vp, u32, u64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.pov_ogg_vorbis_decode_memory.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.POINTER(abi.pov_decoded)]

@@ -300,3 +300,101 @@ def test_packets_spanning_pages_on_the_device(ctx, golden):
     finally:
         ctx.set_page_spanning(False)
         ctx.set_device_entropy(True)
+
+
+def _flip_bits_in_audio_packets(data: bytes, rng, flips: int) -> bytes:
+    """Corrupt `flips` random bits inside the bodies of the audio pages (page 4 onwards) and repair the page CRCs, so that
+    the damage reaches the packet decoders instead of being caught by the container check (hpp:92-98)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from vorbis_writer import ogg_crc
+    buf = bytearray(data)
+    pages, pos = [], 0
+    while pos + 27 <= len(buf):
+        nseg = buf[pos + 26]
+        body = sum(buf[pos + 27:pos + 27 + nseg])
+        pages.append((pos, 27 + nseg, body))
+        pos += 27 + nseg + body
+    audio = pages[3:]
+    for _ in range(flips):
+        p, hdr, body = audio[int(rng.integers(0, len(audio)))]
+        if body == 0:
+            continue
+        at = p + hdr + int(rng.integers(0, body))
+        buf[at] ^= 1 << int(rng.integers(0, 8))
+    for p, hdr, body in audio:
+        buf[p + 22:p + 26] = b"\0\0\0\0"
+        buf[p + 22:p + 26] = ogg_crc(bytes(buf[p:p + hdr + body])).to_bytes(4, "little")
+    return bytes(buf)
+
+
+@pytest.mark.parametrize("name", ["stereo44khz", "synth_two_submaps", "synth_codebooks"])
+def test_corrupted_packets_decode_identically_on_host_and_device(ctx, name):
+    """Random bit flips inside audio packets: whatever the bits now say, the device walk (k_packet_decode) and the host walk
+    must read the same thing — same error or the same PCM, bit for bit. (Zero fill past the packet end, long codewords,
+    classification words and cascade order are all exercised by garbage far better than by valid streams.)"""
+    rng = np.random.default_rng(99)
+    base = _load(name)
+    agree_ok = agree_err = 0
+    for trial in range(24):
+        data = _flip_bits_in_audio_packets(base, rng, flips=int(rng.integers(1, 12)))
+        out = []
+        for dev in (True, False):
+            ctx.set_device_entropy(dev)
+            try:
+                pcm, _, _ = ctx.decode_ogg(data)
+                out.append(pcm)
+            except lib.PovError as e:
+                out.append(e.code)
+            finally:
+                ctx.set_device_entropy(True)
+        if isinstance(out[0], int) or isinstance(out[1], int):
+            assert isinstance(out[0], int) and isinstance(out[1], int), (trial, out[0] if isinstance(out[0], int) else "ok", out[1] if isinstance(out[1], int) else "ok")
+            agree_err += 1
+        else:
+            assert out[0].shape == out[1].shape and np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32)), trial
+            agree_ok += 1
+    assert agree_ok + agree_err == 24 and agree_ok >= 3
+
+
+@pytest.mark.parametrize("name", ["stereo44khz", "mono44khz", "synth_res0_mono", "synth_two_submaps", "synth_surround51",
+                                  "synth_codebooks", "synth_residue_edges"])
+def test_production_kernel_floor_stage_is_bit_exact(ctx, golden, name):
+    """The integer floor1 stage of k_warp_synth ITSELF (not of the staged kernels): final Y values and step-2 flags of every
+    decoded curve, copied out of the kernel's shared memory by its parity hook, against the reference dump's
+    "floor1 final_ys" / "floor1 step2_flag" (hpp:521-559). The dump lists posts in bitstream order, the kernel keeps them in
+    ascending-x order (hpp:458-469)."""
+    g = golden[name]
+    po = lib.ParsedOgg(_load(name), raw_packets=True)
+    s, b = po.get(0)
+    sid = C.c_uint32(0)
+    ctx._check(ctx.L.pov_setup_register(ctx.ctx, C.byref(s), C.byref(sid)))
+    st = abi.pov_stream.from_address(C.addressof(b.streams.contents))
+    st.setup_id = sid.value
+    h = C.c_void_p(None)
+    ctx._check(ctx.L.pov_batch_upload(ctx.ctx, C.byref(b), C.byref(h)))
+    try:
+        assert ctx.L.pov_batch_kernel_name(ctx.ctx, h) == b"k_warp_synth"
+        Cn, P = int(g["channels"]), int(b.n_packets)
+        rec = np.zeros((P, Cn, 72), np.uint8)
+        ctx._check(ctx.L.pov_batch_fetch_fast_floor(ctx.ctx, h, rec.ctypes.data_as(C.POINTER(C.c_uint8)), rec.nbytes))
+        checked = 0
+        for p in range(P):
+            for c in range(Cn):
+                if not g["floor_used"][p, c]:
+                    continue
+                fl = int(g["floor_number"][p, c])
+                k = int(g["floor_nposts"][fl])
+                order = np.argsort(g["floor_xs"][fl, :k], kind="stable")
+                want_y = np.minimum(g["final_ys"][p, c, :k][order], 255).astype(np.uint8)
+                want_f = g["step2_flag"][p, c, :k][order]
+                mask = int.from_bytes(rec[p, c, 64:72].tobytes(), "little")
+                got_f = np.array([(mask >> i) & 1 for i in range(k)], bool)
+                assert np.array_equal(rec[p, c, :k], want_y), (p, c)
+                assert np.array_equal(got_f, want_f), (p, c)
+                checked += 1
+        assert checked > 10
+    finally:
+        st.setup_id = 0
+        ctx.L.pov_batch_free(ctx.ctx, h)
+        po.close()
