@@ -367,7 +367,19 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 	// transfers; with the host walk smaller chunks keep the parser threads and the device overlapped.
 	uint32_t files_per_chunk = ctx->device_entropy ? 256 : 64;
 	if(const char* e = getenv("POV_CORPUS_CHUNK")) files_per_chunk = std::max(1, atoi(e));
-	const uint32_t n_chunks = (n_files + files_per_chunk - 1) / files_per_chunk;
+	// The first chunks are small (an eighth, a quarter, half of the size) so that the device and the copy-out start after a
+	// fraction of a full chunk's parse time; chunk_first[k] = index of chunk k's first file.
+	std::vector<uint32_t> chunk_first;
+	{
+		uint32_t at = 0, size = std::max(1u, files_per_chunk / 8);
+		while(at < n_files) {
+			chunk_first.push_back(at);
+			at += std::min(size, n_files - at);
+			size = std::min(files_per_chunk, size * 2);
+		}
+		chunk_first.push_back(n_files);
+	}
+	const uint32_t n_chunks = (uint32_t) chunk_first.size() - 1;
 	const uint32_t max_ready = std::max<uint32_t>(4, 2 * host_threads);
 
 	// ---- resources that outlive the call ----
@@ -412,8 +424,8 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 			if(ci >= n_chunks || stop.load()) return;
 			std::unique_ptr<Chunk> ck(new Chunk());
 			memset(&ck->view, 0, sizeof ck->view);
-			ck->first_file = ci * files_per_chunk;
-			ck->n_files = std::min(files_per_chunk, n_files - ck->first_file);
+			ck->first_file = chunk_first[ci];
+			ck->n_files = chunk_first[ci + 1] - chunk_first[ci];
 			ck->frames.assign(ck->n_files, 0);
 			hb.clear();
 			ParseOptions opt;
