@@ -188,3 +188,41 @@ def test_packets_spanning_pages(golden, name):
             assert np.array_equal(cap["after_residue"][p, c, :int(n) // 2], g["after_residue"][oh:oh + int(n) // 2]), (p, c)
             oh += int(n) // 2
     po.close()
+
+
+def _remuxed(kind, names):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import vorbis_writer as vw
+    files = [_load(n) for n in names]
+    return vw.chain_files(files) if kind == "chain" else vw.multiplex_files(files)
+
+
+@pytest.mark.parametrize("kind", ["chain", "multiplex"])
+def test_chained_and_multiplexed_logical_streams(golden, kind):
+    """f4 (hpp:1433-1484): several logical streams in one physical stream, one after the other or page-interleaved. The
+    reference keeps one VorbisStream per live serial; so does the front end here. Every logical stream must come out with
+    exactly the descriptors (hence PCM) of the same stream in a file of its own. (The unmodified reference decodes both
+    files: 91136 + 15867 frames.)"""
+    names = ["stereo44khz", "synth_two_submaps", "mono44khz"]
+    po = lib.ParsedOgg(_remuxed(kind, names))
+    assert po.n_streams == len(names)
+    for i, name in enumerate(names):
+        g = golden[name]
+        s, b = po.get(i)
+        assert s.channels == int(g["channels"]) and s.sample_rate == int(g["sample_rate"])
+        assert b.n_packets == len(g["blocksize"])
+        pcm, status = ob.synth_batch_raw(s, b, imdct="reference" if ob.reference_lib() is not None else "fast")[:2]
+        assert not status.any()
+        out = pcm.reshape(int(g["channels"]), -1)
+        assert out.shape == g["pcm"].shape and np.abs(out - g["pcm"]).max() <= 1e-5
+    po.close()
+
+
+def test_duplicate_begin_of_stream_is_refused():
+    """hpp:1436: a second begin-of-stream page for a serial that is still live."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import vorbis_writer as vw
+    pages = vw.split_pages(_load("mono44khz"))
+    _expect_error(b"".join(pages[:3] + pages[:1] + pages[3:]), "duplicate begin-of-stream")

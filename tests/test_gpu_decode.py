@@ -190,6 +190,44 @@ def test_corpus_output_edge_stops_when_the_sink_says_so(ctx):
     assert len(f) == 200 and t > 0
 
 
+@pytest.mark.parametrize("kind", ["chain", "multiplex"])
+def test_chained_and_multiplexed_files_through_the_corpus_decode(ctx, golden, kind):
+    """f4 (hpp:1433-1484): files holding several logical streams (chained / page-interleaved, different channel counts and
+    rates). The sink is called once per logical stream, in begin-of-stream order, with the PCM the same stream gives in a
+    file of its own; frames_out holds the file's total. The unmodified reference decodes the same files."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import vorbis_writer as vw
+    names = ["stereo44khz", "synth_two_submaps", "mono44khz"]
+    mux = vw.chain_files if kind == "chain" else vw.multiplex_files
+    files = [mux([_load(n) for n in names], first_serial=0x100 * (i + 1)) if i % 2 == 0 else _load("mono44khz") for i in range(40)]
+    calls, bad = [], []
+
+    def sink(file_index, pcm):
+        k = sum(1 for f in calls if f == file_index)
+        ref = golden[names[k] if file_index % 2 == 0 else "mono44khz"]["pcm"]
+        if pcm.shape != ref.shape or float(np.abs(pcm - ref).max()) > 1e-5:
+            bad.append((file_index, k))
+        calls.append(file_index)
+        return False
+    frames, total, _ = ctx.decode_corpus_pcm(files, sink, host_threads=3)
+    assert not bad, bad
+    assert calls == [i for i in range(40) for _ in range(3 if i % 2 == 0 else 1)]
+    per_file = sum(golden[n]["pcm"].shape[1] for n in names)
+    assert list(frames) == [per_file if i % 2 == 0 else golden["mono44khz"]["pcm"].shape[1] for i in range(40)]
+
+
+def test_chained_streams_of_one_layout_decode_to_one_pcm_array(ctx, golden):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import vorbis_writer as vw
+    a = _load("stereo44khz")
+    pcm, rate, npk = ctx.decode_ogg(vw.chain_files([a, a]))
+    ref = np.concatenate([golden["stereo44khz"]["pcm"]] * 2, axis=1)
+    assert rate == 44100 and npk == 2 * len(golden["stereo44khz"]["blocksize"])
+    assert pcm.shape == ref.shape and np.abs(pcm - ref).max() <= 1e-5
+
+
 def _stage_all(ctx, h, b, s, npk_blocksizes, stage, count_of):
     out = []
     for p, n in enumerate(npk_blocksizes):

@@ -573,3 +573,43 @@ def write_stream_spanning(s: StreamSetup, packets: Sequence[PacketChoice], seria
         grans.append(total - (trim_last if i == len(packets) - 1 else 0))
     mux(datas, grans, eos_last=True)
     return bytes(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# page-level re-muxing of finished Ogg files (chained and multiplexed logical streams)
+# ---------------------------------------------------------------------------------------------------------------
+def split_pages(data: bytes) -> List[bytes]:
+    """The pages of an Ogg file as byte strings."""
+    pages, at = [], 0
+    while at < len(data):
+        assert data[at:at + 4] == b"OggS"
+        nseg = data[at + 26]
+        size = 27 + nseg + sum(data[at + 27:at + 27 + nseg])
+        pages.append(data[at:at + size])
+        at += size
+    return pages
+
+
+def with_serial(page: bytes, serial: int) -> bytes:
+    """The same page under another stream serial number (checksum redone)."""
+    p = bytearray(page)
+    p[14:18] = struct.pack("<I", serial)
+    p[22:26] = b"\0\0\0\0"
+    p[22:26] = struct.pack("<I", ogg_crc(bytes(p)))
+    return bytes(p)
+
+
+def chain_files(files: Sequence[bytes], first_serial: int = 0x7000) -> bytes:
+    """Logical streams one after the other (Ogg chaining), each under its own serial."""
+    return b"".join(with_serial(pg, first_serial + i) for i, f in enumerate(files) for pg in split_pages(f))
+
+
+def multiplex_files(files: Sequence[bytes], first_serial: int = 0x7100) -> bytes:
+    """Logical streams page-interleaved (Ogg grouping): all begin-of-stream pages first, then round robin."""
+    per = [[with_serial(pg, first_serial + i) for pg in split_pages(f)] for i, f in enumerate(files)]
+    out = [p[0] for p in per]
+    k = 1
+    while any(k < len(p) for p in per):
+        out += [p[k] for p in per if k < len(p)]
+        k += 1
+    return b"".join(out)
