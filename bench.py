@@ -387,7 +387,8 @@ def main():
             cctx._check(cctx.L.pov_decode_corpus(cctx.ctx, nfl, c_data, c_len, threads, c_frames.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                  C.byref(c_total), C.byref(c_chk)))
             return c_frames, int(c_total.value), float(c_chk.value)
-        frames, total, chk = decode_all()    # warm-up: tables, pinned pools and arenas at full size
+        for _ in range(2):                   # warm-up: tables, pinned pools and arenas settle at full size during the second call
+            frames, total, chk = decode_all()
         b0 = cctx.io_bytes()
         barrier()
         t0 = time.perf_counter()

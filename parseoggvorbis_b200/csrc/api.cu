@@ -106,6 +106,9 @@ extern "C" int pov_ctx_create(int device, pov_ctx** out, const char** error_out)
 	ctx->device = device;
 	ctx->sm_count = prop.multiProcessorCount;
 	if((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+	if((e = cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+	if((e = cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+	if((e = cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
 	float table[256];
 	make_inverse_db_table(table);
 	if((e = dev_upload((float**) &ctx->d_inv_db, table, 256, ctx->stream)) != cudaSuccess) return fail("upload inverse dB table", e);
@@ -138,6 +141,9 @@ extern "C" void pov_ctx_destroy(pov_ctx* ctx) {
 	cudaFree((void*) ctx->d_inv_db);
 	cudaFree((void*) ctx->d_counter);
 	ctx->mdct_in.release(); ctx->mdct_out.release();
+	if(ctx->out_stream) { cudaStreamSynchronize(ctx->out_stream); cudaStreamDestroy(ctx->out_stream); }
+	if(ctx->ev_compute) cudaEventDestroy(ctx->ev_compute);
+	if(ctx->ev_out) cudaEventDestroy(ctx->ev_out);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -984,12 +990,26 @@ extern "C" int pov_batch_sync(pov_ctx* ctx, pov_batch_handle* h) {
 	return POV_OK;
 }
 
+cudaError_t pov_copy_out_async(pov_ctx* ctx, void* dst, const void* src, size_t bytes, bool fork, bool join) {
+	cudaError_t e = cudaSuccess;
+	if(fork) {
+		if((e = cudaEventRecord(ctx->ev_compute, ctx->stream)) != cudaSuccess) return e;
+		if((e = cudaStreamWaitEvent(ctx->out_stream, ctx->ev_compute, 0)) != cudaSuccess) return e;
+	}
+	if(bytes && (e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->out_stream)) != cudaSuccess) return e;
+	ctx->d2h_bytes += bytes;
+	if(join) {
+		if((e = cudaEventRecord(ctx->ev_out, ctx->out_stream)) != cudaSuccess) return e;
+		if((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_out, 0)) != cudaSuccess) return e;
+	}
+	return e;
+}
+
 extern "C" int pov_batch_fetch_pcm(pov_ctx* ctx, pov_batch_handle* h, float* out, uint64_t n_floats, int sync) try {
 	if(!ctx || !h || (!out && n_floats)) return POV_ERR_ARG;
 	if(n_floats > h->pcm_floats) return pov_fail(ctx, POV_ERR_ARG, "pov_batch_fetch_pcm: %llu floats requested, arena holds %llu", (unsigned long long) n_floats, (unsigned long long) h->pcm_floats);
 	cudaSetDevice(ctx->device);
-	if(n_floats) CUDA_TRY(ctx, cudaMemcpyAsync(out, h->d_pcm.ptr, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-	ctx->d2h_bytes += n_floats * sizeof(float);
+	if(n_floats) CUDA_TRY(ctx, pov_copy_out_async(ctx, out, h->d_pcm.ptr, n_floats * sizeof(float)));
 	if(sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return POV_OK;
 } POV_NOTHROW_END(ctx)

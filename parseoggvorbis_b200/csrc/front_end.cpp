@@ -367,15 +367,16 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 	// transfers; with the host walk smaller chunks keep the parser threads and the device overlapped.
 	uint32_t files_per_chunk = ctx->device_entropy ? 256 : 64;
 	if(const char* e = getenv("POV_CORPUS_CHUNK")) files_per_chunk = std::max(1, atoi(e));
-	// The first chunks are small (an eighth, a quarter, half of the size) so that the device and the copy-out start after a
-	// fraction of a full chunk's parse time; chunk_first[k] = index of chunk k's first file.
+	// The first chunks are small and grow by half each (1/8 of the size, then x 1.5): every worker starts on a chunk of its own
+	// at once, one worker parses a file in about twice the time the copy-out of its PCM takes, so chunk k is ready just before
+	// the copy-out of chunks 0..k-1 ends and the link never waits for a parser. chunk_first[k] = index of chunk k's first file.
 	std::vector<uint32_t> chunk_first;
 	{
 		uint32_t at = 0, size = std::max(1u, files_per_chunk / 8);
 		while(at < n_files) {
 			chunk_first.push_back(at);
 			at += std::min(size, n_files - at);
-			size = std::min(files_per_chunk, size * 2);
+			size = std::min(files_per_chunk, size + (size + 1) / 2);
 		}
 		chunk_first.push_back(n_files);
 	}
@@ -518,6 +519,11 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 	const bool timing = getenv("POV_CORPUS_TIMING") != nullptr;
 	double g_copy_in_kernels = 0, g_copy_out = 0;
 	if(timing) for(auto& sl : cs.slot) if(!sl.t_begin) { cudaEventCreate(&sl.t_begin); cudaEventCreate(&sl.t_kernels); cudaEventCreate(&sl.t_end); }
+	// POV_CORPUS_TIMING=2: also a per-chunk timeline (four events per chunk: queued, copy-in done, kernels done, copy-out done)
+	const bool timeline = timing && atoi(getenv("POV_CORPUS_TIMING")) >= 2;
+	std::vector<cudaEvent_t> tl(timeline ? 4 * (size_t) n_chunks : 0, nullptr);
+	for(auto& e : tl) cudaEventCreate(&e);
+	std::vector<double> tl_host(timeline ? 4 * (size_t) n_chunks : 0, 0.0);    // host clock: chunk taken, slot free, upload queued, all queued
 	bool stopped = false;
 	auto retire = [&](Slot& sl) -> int {           // wait for a slot's chunk and turn its status words into the reference's error
 		if(!sl.busy) return POV_OK;
@@ -568,6 +574,7 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 			cv_space.notify_all();
 		}
 		t_wait += now() - t0; t0 = now();
+		if(timeline) tl_host[4 * ci] = t0 - t_begin;
 		if(!ck->error.empty()) { rc = pov_fail(ctx, POV_ERR_STREAM, "%s", ck->error.c_str()); cs.release(ck->buf); break; }
 		if(frames_out) for(uint32_t i = 0; i < ck->n_files; ++i) frames_out[ck->first_file + i] = ck->frames[i];
 		if(ck->view.n_packets == 0) { cs.release(ck->buf); continue; }
@@ -583,16 +590,20 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 		rc = retire(sl);                           // the chunk that used this slot two iterations ago
 		if(rc) { cs.release(ck->buf); break; }
 		t_retire += now() - t0; t0 = now();
+		if(timeline) tl_host[4 * ci + 1] = t0 - t_begin;
 		const pov_batch b = ck->view;
 		const uint64_t pcm_floats = b.pcm_floats;
 		const uint32_t n_packets = b.n_packets;
 		if(timing) cudaEventRecord(sl.t_begin, cx->stream);
-		rc = pov_batch_upload(cx, &b, &sl.h);      // pinned sources: the copies are queued, the chunk stays alive until retire()
+		if(timeline) cudaEventRecord(tl[4 * ci], cx->stream);
+		rc = pov_batch_upload(cx, &b, &sl.h);
+		if(timeline) cudaEventRecord(tl[4 * ci + 1], cx->stream);      // pinned sources: the copies are queued, the chunk stays alive until retire()
 		sl.in_flight = std::move(ck);
 		sl.busy = true;                            // from here on retire() has to wait for the stream before the buffer is reused
 		sl.n_packets = 0;
 		cudaEventRecord(sl.done, cx->stream);
 		t_upload += now() - t0; t0 = now();
+		if(timeline) tl_host[4 * ci + 2] = t0 - t_begin;
 		if(!rc) rc = pov_batch_run(cx, sl.h);
 		t_run += now() - t0; t0 = now();
 		if(rc && cx != ctx) pov_fail(ctx, rc, "%s", pov_last_error(cx));
@@ -614,16 +625,20 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 			cudaError_t e = pov_checksum_launch((const float*) pov_batch_pcm_dev(sl.h), pcm_floats, sl.d_sum, cx->stream, &cx->launches);
 			if(e != cudaSuccess) { rc = pov_fail(ctx, POV_ERR_CUDA, "checksum kernel: %s", cudaGetErrorString(e)); break; }
 			if(timing) cudaEventRecord(sl.t_kernels, cx->stream);
-			rc = pov_batch_fetch_pcm(cx, sl.h, sl.pinned, pcm_floats, 0);       // delivery of the PCM to the host (asynchronous)
-			if(!rc && cudaMemcpyAsync(sl.status, sl.h->d_status.ptr, sneed, cudaMemcpyDeviceToHost, cx->stream) != cudaSuccess)
-				rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: status copy failed");
-			cx->d2h_bytes += sneed;
-			if(timing) cudaEventRecord(sl.t_end, cx->stream);
-			if(!rc && cudaEventRecord(sl.done, cx->stream) != cudaSuccess) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventRecord failed");
+			if(timeline) cudaEventRecord(tl[4 * ci + 2], cx->stream);
+			// delivery of the PCM and the status words to the host, on the slot's copy-out stream: the next chunk's copy-in and
+			// kernels on cx->stream are then not queued behind the other slots' copy-outs (they only wait for this one)
+			cudaError_t ce = pov_copy_out_async(cx, sl.pinned, pov_batch_pcm_dev(sl.h), need, true, false);
+			if(ce == cudaSuccess) ce = pov_copy_out_async(cx, sl.status, sl.h->d_status.ptr, sneed, false, true);
+			if(ce != cudaSuccess) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: copy-out failed: %s", cudaGetErrorString(ce));
+			if(timing) cudaEventRecord(sl.t_end, cx->out_stream);
+			if(timeline) cudaEventRecord(tl[4 * ci + 3], cx->out_stream);
+			if(!rc && cudaEventRecord(sl.done, cx->out_stream) != cudaSuccess) rc = pov_fail(ctx, POV_ERR_CUDA, "pov_decode_corpus: cudaEventRecord failed");
 			if(!rc) { sl.n_packets = n_packets; sl.first_file = sl.in_flight->first_file; }
 		}
 		total += pcm_floats;
 		t_fetch += now() - t0;
+		if(timeline) tl_host[4 * ci + 3] = now() - t_begin;
 	}
 	for(uint32_t k = 0; k < (uint32_t) CorpusState::kSlots; ++k) {          // oldest chunk first (file order at the output edge)
 		const int r2 = retire(cs.slot[(n_chunks + k) % CorpusState::kSlots]);
@@ -634,6 +649,17 @@ static int decode_corpus(pov_ctx* ctx, uint32_t n_files, const uint8_t* const* d
 		        "setup ids + wait for the slot %.3f, validate+queue upload %.3f, launch %.3f, fetch/issue %.3f; on the streams (sum over chunks): "
 		        "copy in + kernels %.3f s, copy out %.3f s\n",
 		        n_chunks, now() - t_begin, t_wait, t_retire, t_upload, t_run, t_fetch, g_copy_in_kernels * 1e-3, g_copy_out * 1e-3);
+	if(timeline) {
+		for(uint32_t ci = 0; ci < n_chunks; ++ci) {
+			float t[4] = {-1, -1, -1, -1};
+			for(int k = 0; k < 4; ++k) if(cudaEventElapsedTime(&t[k], tl[0], tl[4 * ci + k]) != cudaSuccess) t[k] = -1;
+			fprintf(stderr, "chunk %3u files %4u..%4u: queued %8.3f copy-in done %8.3f kernels done %8.3f copy-out done %8.3f ms | host: taken %8.3f "
+			        "slot free %8.3f upload queued %8.3f all queued %8.3f ms\n", ci, chunk_first[ci], chunk_first[ci + 1], t[0], t[1], t[2], t[3],
+			        tl_host[4 * ci] * 1e3, tl_host[4 * ci + 1] * 1e3, tl_host[4 * ci + 2] * 1e3, tl_host[4 * ci + 3] * 1e3);
+		}
+		(void) cudaGetLastError();
+	}
+	for(auto& e : tl) if(e) cudaEventDestroy(e);
 	stop.store(true);
 	{ std::lock_guard<std::mutex> lk(mu); cv_space.notify_all(); }
 	{ std::lock_guard<std::mutex> lk(cs.pmu); cs.pcv.notify_all(); }
