@@ -4,6 +4,7 @@ host emits — coded floor Y lists, classifications and VQ entry numbers (bit-ex
 emit counts and granule trimming."""
 import ctypes as C
 import os
+import struct
 
 import numpy as np
 import pytest
@@ -226,3 +227,37 @@ def test_duplicate_begin_of_stream_is_refused():
     import vorbis_writer as vw
     pages = vw.split_pages(_load("mono44khz"))
     _expect_error(b"".join(pages[:3] + pages[:1] + pages[3:]), "duplicate begin-of-stream")
+
+
+def _crafted_codebook_file(dim, entries, lookup_type):
+    """A ~120-byte Ogg file whose setup header declares one ordered codebook of `entries` entries x `dim` dimensions with a
+    VQ lookup and then ends: the size fields are all a decoder gets to see before it would allocate the table."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import vorbis_writer as vw
+    w = vw.BitWriter()
+    w.put(0, 8)                                  # one codebook
+    w.put(0x564342, 24); w.put(dim, 16); w.put(entries, 24)
+    w.put(1, 1)                                  # ordered
+    w.put(0, 5)                                  # codeword length 1 ...
+    w.put(entries, vw.ilog(entries))             # ... for every entry
+    w.put(lookup_type, 4)
+    w.put(0, 32); w.put(0, 32); w.put(0, 4); w.put(0, 1)      # min, delta, value_bits - 1, sequence_p
+    ident = b"\x01vorbis" + struct.pack("<IBIiii", 0, 1, 44100, 0, 0, 0) + bytes([8 | (11 << 4), 1])
+    comment = b"\x03vorbis" + struct.pack("<I", 0) + struct.pack("<I", 0) + b"\x01"
+    return (vw.ogg_page([ident], 7, 0, 0, bos=True) + vw.ogg_page([comment], 7, 1, 0) +
+            vw.ogg_page([b"\x05vorbis" + w.bytes()], 7, 2, 0, eos=True))
+
+
+@pytest.mark.parametrize("dim,entries,lookup_type", [(32768, 1 << 17, 2), (65535, 1 << 20, 1), (65535, (1 << 24) - 1, 2)])
+def test_crafted_codebook_sizes_are_refused_not_allocated(dim, entries, lookup_type):
+    """Round-1 review: n_entries * dim wrapped in 32 bits (lookup type 2: an empty multiplicand table read out of bounds) or
+    asked for 275 GB (lookup type 1: std::bad_alloc across the C boundary). Both must come back as an ordinary stream
+    error, from the plain parse entry point and from the parse with raw packets."""
+    data = _crafted_codebook_file(dim, entries, lookup_type)
+    assert len(data) < 200
+    for raw in (False, True):
+        with pytest.raises(lib.PovError) as ei:
+            lib.ParsedOgg(data, raw_packets=raw)
+        assert ei.value.code in (abi.POV_ERR_STREAM, abi.POV_ERR_UNSUPPORTED), ei.value.msg
+        assert "codebook" in ei.value.msg, ei.value.msg
