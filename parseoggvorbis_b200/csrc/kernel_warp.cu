@@ -873,7 +873,7 @@ __device__ __forceinline__ float ola_one(const OlaGeom& G, const float* __restri
 // storage quad 32 i + L (and its mirror 127 - that), which holds the true quad tq = [sq6][sq1][sq0][sq5][sq2][sq4][sq3].
 template <int Q, bool kStrided, int kTm>
 __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, const float* __restrict__ chi, const float* __restrict__ sl,
-                                              float* __restrict__ dst, int stride, int lane, uint32_t tm) {
+                                              float* __restrict__ dst, int stride, int lane, uint32_t tm, float* __restrict__ stage = nullptr) {
 	// n = 4Q: the chunk has 2Q samples, half of them (Q) below the centre; 8 samples per lane and iteration
 #pragma unroll
 	for(int i = 0; i < Q / 128; ++i) {
@@ -903,11 +903,29 @@ __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, con
 		if constexpr(!kStrided) {
 			__stcs(reinterpret_cast<float4*>(dst + j), o1);
 			__stcs(reinterpret_cast<float4*>(dst + (2 * Q - 4) - j), o2);
-		} else {          // interleaved PCM: sample j of this channel lives at dst[j * channels]
-			float* a = dst + (size_t) j * stride;
-			float* b = dst + (size_t) ((2 * Q - 4) - j) * stride;
-			a[0] = o1.x; a[stride] = o1.y; a[2 * stride] = o1.z; a[3 * stride] = o1.w;
-			b[0] = o2.x; b[stride] = o2.y; b[2 * stride] = o2.z; b[3 * stride] = o2.w;
+		} else {
+			// interleaved PCM: sample j of this channel lives at dst[j * channels]. The lane's four samples would be four stores
+			// 16 * channels bytes apart from the next lane's; through a 512-byte stage (the step's curve block, dead by now) every
+			// store instruction covers 32 consecutive frames instead, i.e. a quarter of the sectors.
+			if constexpr(kTm == 2) {          // (fft512_tm's storage order: lanes are not frame-consecutive; plain strided stores)
+				float* a = dst + (size_t) j * stride;
+				float* b = dst + (size_t) ((2 * Q - 4) - j) * stride;
+				a[0] = o1.x; a[stride] = o1.y; a[2 * stride] = o1.z; a[3 * stride] = o1.w;
+				b[0] = o2.x; b[stride] = o2.y; b[2 * stride] = o2.z; b[3 * stride] = o2.w;
+				continue;
+			}
+			*reinterpret_cast<float4*>(stage + 4 * lane) = o1;
+			__syncwarp();
+			float* a = dst + (size_t) (128 * i + lane) * stride;
+#pragma unroll
+			for(int k = 0; k < 4; ++k) a[(size_t) (32 * k) * stride] = stage[32 * k + lane];
+			__syncwarp();
+			*reinterpret_cast<float4*>(stage + 124 - 4 * lane) = o2;
+			__syncwarp();
+			float* b = dst + (size_t) ((2 * Q - 128) - 128 * i + lane) * stride;
+#pragma unroll
+			for(int k = 0; k < 4; ++k) b[(size_t) (32 * k) * stride] = stage[32 * k + lane];
+			__syncwarp();
 		}
 	}
 }
@@ -1171,7 +1189,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 					float* const dst = out0 + (planar ? (size_t) w.pcm_rel : (size_t) w.pcm_rel * (size_t) C);
 					if(flag && prev_n == N1 && lc == N1 / 2 && prev_right == N1 / 2 && emit == (uint32_t) (N1 / 2) && (!planar || ((size_t) dst & 15) == 0)) {
 						if constexpr(planar) ola_long_long<Q1, false, kTm>(prev_lo, cur_hi, s_slope1, dst, 1, lane, tmw);
-						else ola_long_long<Q1, true, kTm>(prev_lo, cur_hi, s_slope1, dst, C, lane, tmw);
+						else ola_long_long<Q1, true, kTm>(prev_lo, cur_hi, s_slope1, dst, C, lane, tmw, reinterpret_cast<float*>(curves));
 					} else {
 						OlaGeom G;
 						G.Hp = prev_n / 4; G.H = Q;
