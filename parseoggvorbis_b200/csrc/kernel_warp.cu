@@ -30,6 +30,12 @@
 #include <type_traits>
 
 namespace pov {
+#ifdef POV_EXP_SAME_SPECTRUM      // timing experiment only (wrong output): every step reads the run's first spectrum, i.e. L1 / L2 hits
+#define POV_EXP_SPEC_REL(x) 0
+#else
+#define POV_EXP_SPEC_REL(x) (x)
+#endif
+
 namespace wk {
 
 #ifndef POV_WARP_WARPS
@@ -238,13 +244,23 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 	MaskT flags = 3u;
 	uint32_t bad = 0u;
 	uint16_t* col = scratch + lane;
-	if(act) { col[0] = __ldg(yp); col[32] = __ldg(yp + 1); }
+	// All coded values of this lane's packet first, eight independent loads at a time: one memory round trip per eight posts
+	// instead of one per post inside the serial walk below (measured: the walk was 9 % of the kernel, all of it load latency).
+	// col[i] holds the coded value of post i until step i replaces it by the final one (steps only read final values of
+	// posts before them).
+	for(int i0 = 0; i0 < maxposts; i0 += 8) {
+		uint16_t v[8];
+#pragma unroll
+		for(int k = 0; k < 8; ++k) v[k] = (i0 + k < posts) ? __ldg(yp + i0 + k) : (uint16_t) 0;
+#pragma unroll
+		for(int k = 0; k < 8; ++k) if(i0 + k < posts) col[(i0 + k) * 32] = v[k];
+	}
 	for(int i = 2; i < maxposts; ++i) {
 		if(i < posts) {
 			const uint4 t = *reinterpret_cast<const uint4*>(F->post[i]);
 			const uint32_t lo = t.x & 0xffu, hi = (t.x >> 8) & 0xffu;
 			const uint32_t y0 = col[lo * 32], y1 = col[hi * 32];
-			const uint32_t val = __ldg(yp + i);
+			const uint32_t val = col[i * 32];
 			const bool up = y1 >= y0;
 			const uint32_t ady = up ? (y1 - y0) : (y0 - y1);
 			// floor(ady * dxn / adx) by multiplication with m = ceil(2^32/adx): e = ady * dxn < 2^32 and m - 2^32/adx < 1 put the
@@ -763,8 +779,12 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 			hi[i] = __ldg(reinterpret_cast<const float4*>(lane_hi + (off[i] - d)));
 		}
 		// the floor evaluation needs none of the loaded values: it runs while the loads are in flight
+#ifdef POV_EXP_NO_FLOOR_EVAL      // timing experiment only (wrong output)
+		const float4 fl = make_float4(1.f, 1.f, 1.f, 1.f), fh = fl;
+#else
 		const float4 fl = curve_quad(rec, tab, (uint32_t) (4 * q), invdb);
 		const float4 fh = curve_quad(rec, tab, (uint32_t) (M - 4 - 4 * q), invdb);
+#endif
 		if(NL > 1 && !GEN) {
 			// single coupling step between two channels: only this warp's channel (local index 0) is needed
 			if(last_mag) {
@@ -1078,7 +1098,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			first_of_stream = run.first_packet == st.first_packet;
 		}
 		__syncwarp();
+#ifndef POV_EXP_NO_UNWRAP         // (defined: timing experiment only, wrong output)
 		unwrap_run<kWide>(tb, wp, pk0, run_n, ch, b.ys, reinterpret_cast<uint16_t*>(slotA), fs, b.status + run.first_packet, (uint32_t) N0, (uint32_t) N1, lane);
+#endif
 		if(P.dbg_floor) {
 			// parity hook: the production kernel's integer floor stage as it is — final Ys (ascending x, clamped to 255) and the
 			// step-2 mask of every packet of the run — copied out for comparison with the reference's "floor1 final_ys" /
@@ -1146,18 +1168,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			for(int g = 0; g < count; ++g) {
 				const int md = curve_mode(tb, mapping, wp[first + g].meta >> 16, ch);
 				unsigned char* cv = curves + (size_t) g * cstride;
+#ifdef POV_EXP_NO_RECORDS         // timing experiment only (wrong output)
+				if(md == 0) flat_curve(cv, rcap, nwords, 200u, lane);
+#else
 				if(md == 0) build_records<kWide>(F, fs + (first + g) * (kWide ? 72 : kFsStride), cv, rcap, nwords, s_recip, lane);
+#endif
 				else flat_curve(cv, rcap, nwords, md == 1 ? 255u : 256u, lane);
 			}
 			// FFT buffer of FFT f: Q/64 sub-FFT rows of 72 slots (one row for Q = 64)
 			const uint32_t Ts = smem_u32(T), Tfs = Ts + (uint32_t) f * (uint32_t) ((Qs >> 6) * 72 * 8);
 			const uint32_t rots = smem_u32(flag ? s_rot1 : s_rot0), tws = smem_u32(flag ? s_tw1 : s_tw0);
 			// (a whole-warp FFT has f = 0 in every lane: the call below is warp uniform there, which the tensor-memory loads need)
+#ifdef POV_EXP_NO_SPECTRAL        // timing experiment only (wrong output)
+			if(f < count && P.n_items == 0xffffffffu)
+#else
 			if(f < count)
-				spectral_dispatch<kMaxNL>(cp, spec_base + wp[first + f].spec_rel, 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u,
+#endif
+				spectral_dispatch<kMaxNL>(cp, spec_base + POV_EXP_SPEC_REL(wp[first + f].spec_rel), 2 * Qs, smem_u32(curves + (size_t) f * cstride), rcap, rots, Qs, Tfs, u,
 				                          (kTm != 0 && flag) ? tmw : 0u);
 			__syncwarp();
 			// last pass output: long: lo half -> survivor slot, hi half -> slot B; short: D of FFT f packed at T + Q0 f (lo | hi)
+#ifdef POV_EXP_NO_FFT             // timing experiment only (wrong output)
+			if(P.n_items != 0xffffffffu) { __syncwarp(); }
+			else
+#endif
 			if(flag && !kLongGrouped) {
 				if constexpr(kTm == 2) fft512_tm(Ts, lane, tmw, tmx, smem_u32(surv), smem_u32(slotB));
 				else fft_passes<Q1, kTm == 1>(Tfs, u, tws, smem_u32(smem + M::kOffFp1), rots, smem_u32(surv), smem_u32(slotB), tmw);
@@ -1185,7 +1219,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				const float* cur_lo = !grouped ? reinterpret_cast<const float*>(surv) : Dstep + (size_t) g * 2 * Q;
 				const float* cur_hi = !grouped ? reinterpret_cast<const float*>(slotB) : cur_lo + Q;
 				const bool emits = prev_valid && emit > 0 && !((stt & 32u) && first + g == 0);
+#ifdef POV_EXP_NO_OLA
+				if(emits && P.n_items == 0xffffffffu) {
+#else
 				if(emits) {
+#endif
 					float* const dst = out0 + (planar ? (size_t) w.pcm_rel : (size_t) w.pcm_rel * (size_t) C);
 					if(flag && prev_n == N1 && lc == N1 / 2 && prev_right == N1 / 2 && emit == (uint32_t) (N1 / 2) && (!planar || ((size_t) dst & 15) == 0)) {
 						if constexpr(planar) ola_long_long<Q1, false, kTm>(prev_lo, cur_hi, s_slope1, dst, 1, lane, tmw);
