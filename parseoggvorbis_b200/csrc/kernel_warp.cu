@@ -1067,6 +1067,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 	constexpr bool planar = kPlanar;       // PCM layout is a template parameter: the interleaved address arithmetic stays out of the planar kernel
 
 	for(;;) {
+		// (claiming the next item one run ahead, to take the atomic's round trip off the path, was measured slower: 2.274 against
+		// 2.232 ms — the items held back at the tail cost more than the latency that four other warps per scheduler already hide)
 		uint32_t item = 0;
 		if(lane == 0) item = atomicAdd(P.counter, 1u);
 		item = __shfl_sync(FULL, item, 0);
@@ -1151,7 +1153,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 				const uint32_t nmode = nw.meta & 0xffu;
 				const uint32_t nhalf = tb->mode_flag[nmode] ? 2u * Q1 : 2u * Q0;
 				const FastCouple* ncp = &tb->couple[tb->mode_map[nmode]][ch];
+#ifndef POV_EXP_NO_PREFETCH
 				if(lane < (int) ncp->nl) prefetch_l2_bulk(spec_base + nw.spec_rel + (int) (ncp->ch[lane] * nhalf), nhalf * 4u);
+#endif
 			}
 			// ================= one 2048-sample packet or a group of smaller packets: Q/16 lanes per FFT, same code for all classes,
 			//                   geometry in registers (256/2048: the whole warp is one 512-point FFT, or eight 64-point FFTs) ====
