@@ -30,6 +30,13 @@
 #include <type_traits>
 
 namespace pov {
+// POV_EXP_*: knock-out switches for timing experiments (tools/build_variant.sh): each removes one routine from the
+// kernel so that its marginal cost can be read off the launch time. Such a build computes garbage and says so at compile time;
+// the Makefile never sets them.
+#if defined(POV_EXP_SAME_SPECTRUM) || defined(POV_EXP_NO_FLOOR_EVAL) || defined(POV_EXP_NO_UNWRAP) || defined(POV_EXP_NO_RECORDS) || \
+    defined(POV_EXP_NO_SPECTRAL) || defined(POV_EXP_NO_FFT) || defined(POV_EXP_NO_OLA) || defined(POV_EXP_NO_PREFETCH)
+#pragma message("k_warp_synth: timing-experiment build (POV_EXP_*): output is wrong by construction, never ship this object")
+#endif
 #ifdef POV_EXP_SAME_SPECTRUM      // timing experiment only (wrong output): every step reads the run's first spectrum, i.e. L1 / L2 hits
 #define POV_EXP_SPEC_REL(x) 0
 #else
