@@ -260,7 +260,7 @@ static bool build_fast_tables(const pov_setup* s, const std::vector<DevFloor>& f
 			o.post[k][1] = (uint32_t) f.dxn[k] | ((uint32_t) f.adx[k] << 16);
 			o.post[k][2] = (k >= 2) ? (uint32_t) ((0x100000000ull + f.adx[k] - 1) / f.adx[k]) : 0u;
 			o.post[k][3] = f.xs[sidx];
-			o.xs_sorted[k] = f.xs[sidx];
+			o.xs_sorted[k] = f.xs[sidx] | (sidx << 16);        // X of the k-th smallest post | its post number
 		}
 	}
 	for(uint32_t m = 0; m < s->n_mappings; ++m) {

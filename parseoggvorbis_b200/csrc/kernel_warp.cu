@@ -222,7 +222,7 @@ __device__ __forceinline__ float uncouple_ang(float m, float a) {
 // Block layout: uint2 rec[cap] | uint2 tab[n/64] (rank table, see build_records).
 // floor1 step 1 (amplitude unwrap, hpp:521-559) for ALL packets of a run at once: lane p owns packet p and walks its
 // posts serially (the neighbour DAG makes the posts of one curve sequential, but the <= 32 curves of a run are
-// independent). The final Y values leave in ascending-x order as bytes, with the step2 flags as a bit mask, 36 bytes per
+// independent). The final Y values leave as bytes in POST order, with the step2 flags as a bit mask over posts, 36 bytes per
 // packet; the hpp:536 / hpp:587 checks are evaluated here with full-width values and reported per packet.
 // scratch: [posts][32 lanes] uint16, aliasing the (idle) FFT work regions.
 // kWide: floors of 33..64 posts (libvorbis' high-quality setups): 64-bit flag masks, 72-byte Y records (64 bytes + mask), so
@@ -249,18 +249,26 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 	using MaskT = typename std::conditional<kWide, uint64_t, uint32_t>::type;
 	constexpr int kStride = kWide ? 72 : 36, kMaskAt = kWide ? 64 : 32;
 	MaskT flags = 3u;
+	MaskT over = 0u;                        // posts whose final Y, scaled by the multiplier, is >= 256 (hpp:587 once they are flagged)
 	uint32_t bad = 0u;
+	const uint32_t mult = F->multiplier;
+	unsigned char* out = fs + lane * kStride;
 	uint16_t* col = scratch + lane;
 	// All coded values of this lane's packet first, eight independent loads at a time: one memory round trip per eight posts
-	// instead of one per post inside the serial walk below (measured: the walk was 9 % of the kernel, all of it load latency).
-	// col[i] holds the coded value of post i until step i replaces it by the final one (steps only read final values of
-	// posts before them).
+	// instead of one per post inside the serial walk below. col[i] holds the coded value of post i until step i replaces it
+	// by the final one (steps only read final values of posts before them).
 	for(int i0 = 0; i0 < maxposts; i0 += 8) {
 		uint16_t v[8];
 #pragma unroll
 		for(int k = 0; k < 8; ++k) v[k] = (i0 + k < posts) ? __ldg(yp + i0 + k) : (uint16_t) 0;
 #pragma unroll
 		for(int k = 0; k < 8; ++k) if(i0 + k < posts) col[(i0 + k) * 32] = v[k];
+	}
+	if(act) {
+		const uint32_t a = col[0], b2 = col[32];
+		out[0] = (unsigned char) min(a, 255u); out[1] = (unsigned char) min(b2, 255u);
+		if(min(a * mult, 0xFFFFu) >= 256u) over |= 1u;
+		if(min(b2 * mult, 0xFFFFu) >= 256u) over |= 2u;
 	}
 	for(int i = 2; i < maxposts; ++i) {
 		if(i < posts) {
@@ -285,38 +293,42 @@ __device__ __forceinline__ void unwrap_run(const FastTables* __restrict__ tb, co
 				if(val >= room) fin = (high_room > low_room) ? val - low_room + predicted : predicted - val + high_room - 1;
 				else fin = (val & 1) ? predicted - (val + 1) / 2 : predicted + val / 2;
 			}
-			col[i * 32] = (uint16_t) min(fin, 0xFFFFu);
+			fin = min(fin, 0xFFFFu);
+			col[i * 32] = (uint16_t) fin;
+			out[i] = (unsigned char) min(fin, 255u);
+			if(min(fin * mult, 0xFFFFu) >= 256u) over |= (MaskT) 1 << i;
 		}
 	}
-	// ascending-x order, step2 mask, and hpp:587 CHECK(floor[i] < 256) over the n bins the reference renders: segments are
-	// monotone, so the maxima are at rendered end points; a segment cut by bin n-1 needs y(n-1)
+	// hpp:587 CHECK(floor[i] < 256) over the n bins the reference renders: segments are monotone, so the maxima are at rendered
+	// end points. Every X of an ordinary floor lies below n (X <= n/2): then the flagged posts are all there is to check.
+	// A floor with posts at or beyond n (legal, never produced by an encoder) takes the walk in ascending-x order below: posts
+	// beyond n are not rendered, and the segment cut by bin n-1 needs y(n-1).
 	const uint32_t n = tb->mode_flag[mode] ? n1 : n0;
-	const uint32_t mult = F->multiplier;
-	MaskT smask = 0u;
-	uint32_t xp = 0u, ypv = 0u;
-	bool havep = false;
-	unsigned char* out = fs + lane * kStride;
-	for(int sidx = 0; sidx < maxposts; ++sidx) {
-		if(sidx < posts) {
-			const uint32_t si = F->post[sidx][0] >> 24, x = F->post[sidx][3] & 0xffffu;
-			const uint32_t y = col[si * 32];
-			out[sidx] = (unsigned char) min(y, 255u);
-			if((flags >> si) & 1u) {
-				smask |= (MaskT) 1 << sidx;
-				const uint32_t yv = min(y * mult, 0xFFFFu);
-				if(x < n && yv >= 256u) bad |= POV_PKT_FLOOR_RANGE;
-				if(havep && xp < n && x > n - 1) {
-					const bool down = yv < ypv;
-					const uint32_t ady = down ? ypv - yv : yv - ypv, dx = x - xp;
-					const uint32_t q = (uint32_t) (((uint64_t) (n - 1 - xp) * ady) / dx);
-					if((down ? ypv - q : ypv + q) >= 256u) bad |= POV_PKT_FLOOR_RANGE;
+	const bool beyond = act && F->xs_sorted[posts - 1] >= n;             // (low 16 bits: X; see build_records)
+	if(!beyond) { if(over & flags) bad |= POV_PKT_FLOOR_RANGE; }
+	if(__any_sync(FULL, beyond)) {
+		uint32_t xp = 0u, ypv = 0u;
+		bool havep = false;
+		for(int sidx = 0; sidx < maxposts; ++sidx) {
+			if(beyond && sidx < posts) {
+				const uint32_t e = F->xs_sorted[sidx], si = e >> 16, x = e & 0xffffu;
+				const uint32_t y = col[si * 32];
+				if((flags >> si) & 1u) {
+					const uint32_t yv = min(y * mult, 0xFFFFu);
+					if(x < n && yv >= 256u) bad |= POV_PKT_FLOOR_RANGE;
+					if(havep && xp < n && x > n - 1) {
+						const bool down = yv < ypv;
+						const uint32_t ady = down ? ypv - yv : yv - ypv, dx = x - xp;
+						const uint32_t q = (uint32_t) (((uint64_t) (n - 1 - xp) * ady) / dx);
+						if((down ? ypv - q : ypv + q) >= 256u) bad |= POV_PKT_FLOOR_RANGE;
+					}
+					xp = x; ypv = yv; havep = true;
 				}
-				xp = x; ypv = yv; havep = true;
 			}
 		}
 	}
 	if(act) {
-		*reinterpret_cast<MaskT*>(out + kMaskAt) = smask;
+		*reinterpret_cast<MaskT*>(out + kMaskAt) = flags;
 		if(bad) atomicOr(status + lane, bad);
 	}
 	__syncwarp();
@@ -332,19 +344,33 @@ __device__ __forceinline__ void build_records(const FastFloor* __restrict__ F, c
 	using MaskT = typename std::conditional<kWide, uint64_t, uint32_t>::type;
 	constexpr int kMaskAt = kWide ? 64 : 32, kRounds = kWide ? 2 : 1;
 	const int posts = (int) F->n_posts;
-	const MaskT mask = *reinterpret_cast<const MaskT*>(fsp + kMaskAt);
+	const MaskT flags = *reinterpret_cast<const MaskT*>(fsp + kMaskAt);     // step2 flags by post number
 	uint2* rec = reinterpret_cast<uint2*>(curve);
 	uint2* tab = rec + rec_cap;
 	uint32_t* bits = reinterpret_cast<uint32_t*>(tab);          // word w at bits[2w] while the bitmap is collected
 	if((uint32_t) lane < nwords) bits[2 * lane] = 0u;
 	__syncwarp();
+	// ascending-x order is made here, one lane per post (unwrap_run leaves post order): xs_sorted[p] = X | post number << 16 of
+	// the p-th smallest X; the flag mask in that order is a ballot
+	uint32_t xs_[kRounds], yb_[kRounds];
+	bool f_[kRounds];
+	MaskT mask = 0;
+#pragma unroll
+	for(int h = 0; h < kRounds; ++h) {
+		const int p = lane + 32 * h;
+		const bool have = p < posts;
+		const uint32_t e = have ? F->xs_sorted[p] : 0u;
+		xs_[h] = e & 0xffffu;
+		yb_[h] = have ? fsp[e >> 16] : 0u;
+		f_[h] = have && ((flags >> (e >> 16)) & 1u);
+		mask |= (MaskT) __ballot_sync(FULL, f_[h]) << (32 * h);
+	}
 #pragma unroll
 	for(int h = 0; h < kRounds; ++h) {                          // post p = lane + 32 h (ascending-x order)
 		const int p = lane + 32 * h;
-		const bool have = p < posts;
-		const uint32_t yb = have ? fsp[p] : 0u;
-		const uint32_t x0 = have ? F->xs_sorted[p] : 0u;
-		const bool f = have && ((mask >> p) & 1u);
+		const uint32_t yb = yb_[h];
+		const uint32_t x0 = xs_[h];
+		const bool f = f_[h];
 		const uint32_t rank = kWide ? (uint32_t) __popcll((uint64_t) mask & (((uint64_t) 1 << p) - 1u)) : (uint32_t) __popc((uint32_t) mask & ((1u << p) - 1u));
 		const uint32_t y0 = min(yb * F->multiplier, 1023u);
 		// the next flagged post (the segment's right end): (x1, y1) straight from the tables, no shuffle
@@ -353,7 +379,8 @@ __device__ __forceinline__ void build_records(const FastFloor* __restrict__ F, c
 		const int np = last ? p : (kWide ? __ffsll((long long) above) : __ffs((int) above)) - 1;
 		uint32_t x1, y1;
 		if constexpr(kWide) {
-			x1 = f ? F->xs_sorted[np] : 0u; y1 = f ? min((uint32_t) fsp[np] * F->multiplier, 1023u) : 0u;
+			const uint32_t en = f ? F->xs_sorted[np] : 0u;
+			x1 = en & 0xffffu; y1 = f ? min((uint32_t) fsp[en >> 16] * F->multiplier, 1023u) : 0u;
 		} else {                                                  // one round: the next post is another lane's (x0, y0)
 			const uint32_t pn = __shfl_sync(FULL, x0 | (y0 << 16), np);
 			x1 = pn & 0xffffu; y1 = pn >> 16;
@@ -1118,9 +1145,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_warp_synth(const Params P) {
 			if(lane < run_n) {
 				unsigned char* d = P.dbg_floor + ((size_t) (run.first_packet + lane) * C + ch) * 72;
 				const unsigned char* src = fs + lane * kS;
-				for(int i = 0; i < kM; ++i) d[i] = src[i];
-				for(int i = kM; i < 64; ++i) d[i] = 0;
-				for(int i = 0; i < 8; ++i) d[64 + i] = (i < (kWide ? 8 : 4)) ? src[kM + i] : (unsigned char) 0;
+				const uint32_t meta = wp[lane].meta;
+				const FastFloor* Fd = &tb->floors[tb->floor_of_ch[tb->mode_map[meta & 0xffu]][ch]];
+				const int np = ((meta >> 16) >> ch) & 1u ? (int) Fd->n_posts : 0;
+				unsigned long long fl = 0, sm = 0;
+				for(int i = 0; i < (kWide ? 8 : 4); ++i) fl |= (unsigned long long) src[kM + i] << (8 * i);
+				for(int i = 0; i < 64; ++i) {                 // the records hold post order; the dump is in ascending-x order
+					const uint32_t si = i < np ? Fd->xs_sorted[i] >> 16 : 0u;
+					d[i] = i < np ? src[si] : (unsigned char) 0;
+					if(i < np && ((fl >> si) & 1ull)) sm |= 1ull << i;
+				}
+				for(int i = 0; i < 8; ++i) d[64 + i] = (unsigned char) (sm >> (8 * i));
 			}
 			__syncwarp();
 		}

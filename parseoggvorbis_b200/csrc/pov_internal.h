@@ -120,7 +120,7 @@ struct FastFloor {
 	//   [2] ceil(2^32 / (xs[hi] - xs[lo]))                     (exact division by multiplication, see kernel_warp.cu)
 	//   [3] X of the i-th smallest post
 	uint32_t post[POV_FAST_MAX_POSTS][4];
-	uint32_t xs_sorted[POV_FAST_MAX_POSTS];   // X of the i-th smallest post again, unit stride (conflict-free per-lane reads)
+	uint32_t xs_sorted[POV_FAST_MAX_POSTS];   // X of the i-th smallest post | its post number << 16, unit stride (conflict-free per-lane reads)
 };
 
 // How the warp that owns channel c of a mapping un-couples it (hpp:1213-1241): the channels it has to load
