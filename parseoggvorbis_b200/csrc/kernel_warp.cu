@@ -63,6 +63,14 @@ constexpr int kSlotF2 = kRegionF2 / 2;  // the work area of a warp is three half
 #ifndef POV_TM_SPLIT_ST
 #define POV_TM_SPLIT_ST 0
 #endif
+#ifndef POV_SPECTRAL_UNROLL
+#define POV_SPECTRAL_UNROLL 1  // quads of the spectral stage unrolled per loop iteration (2 measured: see profiles/r02_ab_kernel_variants.log)
+#endif
+constexpr int kSpectralUnroll = POV_SPECTRAL_UNROLL;
+#ifndef POV_OLA_UNROLL
+#define POV_OLA_UNROLL 4
+#endif
+constexpr int kOlaUnroll = POV_OLA_UNROLL;   // iterations of ola_long_long unrolled (the hot code of 20 warps in different phases competes for the instruction cache)
 #ifndef POV_WARP_PKT_CAP
 #define POV_WARP_PKT_CAP 32
 #endif
@@ -803,7 +811,7 @@ __device__ __forceinline__ void spectral_stage(const float* __restrict__ base, i
 	// this lane's first quad and its mirror, as pointers: a load is then one 32-bit offset and one wide multiply-add
 	const float* const lane_lo = base + 4 * u;
 	const float* const lane_hi = base + (M - 4 - 4 * u);
-#pragma unroll 1
+#pragma unroll kSpectralUnroll
 	for(int m = 0; m < 4; ++m) {
 		const int q = u + LPF * m, d = 4 * LPF * m;
 		float4 lo[NL], hi[NL];
@@ -929,7 +937,7 @@ template <int Q, bool kStrided, int kTm>
 __device__ __forceinline__ void ola_long_long(const float* __restrict__ plo, const float* __restrict__ chi, const float* __restrict__ sl,
                                               float* __restrict__ dst, int stride, int lane, uint32_t tm, float* __restrict__ stage = nullptr) {
 	// n = 4Q: the chunk has 2Q samples, half of them (Q) below the centre; 8 samples per lane and iteration
-#pragma unroll
+#pragma unroll kOlaUnroll
 	for(int i = 0; i < Q / 128; ++i) {
 		const int js = 4 * lane + 128 * i;                                   // position in the stored halves
 		const int j = (kTm == 2) ? 4 * ((((lane & 3) << 4) | (lane & 4) | (lane >> 3)) + ((i & 2) << 5) + ((i & 1) << 3)) : js;   // true position
